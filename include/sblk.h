@@ -1,0 +1,91 @@
+/* sblk.h — C ABI of libsblk.so: the B200 (sm_100a) kernel library behind the drop-in visual encoder
+ * (Conv3d frontend -> per-frame ResNet-18 trunk -> transformer Encoder) of SBL_For_Multilingual_Lip_Reading.
+ *
+ * The reference has no native code and no plugin ABI for this path: every call below replaces a stock
+ * torch.nn call site of the reference (cited per function, paths relative to
+ * SBL_Multilingual_Lip_reading/).  Conventions:
+ *   - every pointer is a raw CUDA device pointer on the caller's CURRENT device; `stream` is a cudaStream_t
+ *   - functions only enqueue work (no sync, no allocation) and are CUDA-graph capturable
+ *   - return 0 = OK, < 0 = argument / shape / alignment error (unsupported configurations fail loudly,
+ *     there is no CPU or library fallback), > 0 = cudaError_t of the failed launch
+ *   - sblk_last_error() returns a thread-local description of the last failure
+ *   - activations are bf16 NHWC / row-major, accumulation and normalisation are fp32
+ */
+#ifndef SBLK_H_
+#define SBLK_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBLK_VERSION 100
+
+int sblk_version(void);
+const char* sblk_last_error(void);
+/* Number of SMs of the current device (>0) or a negative error. Also performs the one-time per-device setup. */
+int sblk_init(void);
+/* Device-side pipeline watchdog word (0 = never fired); survives a trapped launch. */
+unsigned int sblk_watchdog_code(void);
+/* Enable (1) / disable (0) programmatic dependent launch between consecutive kernels. Returns previous value. */
+int sblk_set_pdl(int enable);
+/* Number of kernels launched by this library since load (all threads). */
+long long sblk_launch_count(void);
+
+/* ---- packers (one-time, per weight version) ------------------------------------------------------- */
+/* Conv3d(1,64,(5,7,7)) weight [64,1,5,7,7] fp32 + BatchNorm3d(eval) -> bf16 [64][320] + fp32 bias[64].
+ * replaces: nn.Conv3d / nn.BatchNorm3d parameters, transformer/video_frontend.py:100-101 */
+int sblk_pack_conv3d(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                     float eps, void* w_packed_bf16, float* bias, void* stream);
+/* Conv2d weight [Co,Ci,R,S] fp32 + BatchNorm2d(eval) -> bf16 [Co][R][S][Ci] + fp32 bias[Co].
+ * gamma == NULL packs without folding (bias, if given, is zero-filled).
+ * replaces: conv3x3 / downsample conv + bn parameters, transformer/video_frontend.py:10-12,20-24,68-72 */
+int sblk_pack_conv2d(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
+                     float eps, void* w_packed_bf16, float* bias, int Co, int Ci, int R, int S, void* stream);
+/* fp32 -> bf16 cast of n elements (n % 4 == 0). Linear weights [out,in] are already K-major. */
+int sblk_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+
+/* ---- visual frontend ------------------------------------------------------------------------------ */
+/* x fp32 [N,1,T,88,88] -> bf16 [N,T+4,94,96], zero temporal (2) and spatial (3) borders.
+ * replaces: the implicit zero padding of nn.Conv3d(padding=(2,3,3)), transformer/video_frontend.py:100 */
+int sblk_prep_clip(const float* x, void* x_prepped_bf16, int N, int T, void* stream);
+/* Conv3d + BN3d(eval) + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) + transpose(1,2).contiguous().view:
+ * prepped clip -> bf16 NHWC [N*T,22,22,64].
+ * replaces: Lipreading.frontend3D and _frontend_forward's relayout, transformer/video_frontend.py:99-104,111-115 */
+int sblk_conv3d_bn_relu_pool_fwd(const void* x_prepped_bf16, const void* w_packed_bf16, const float* bias,
+                                 void* out_bf16, int N, int T, void* stream);
+/* Implicit-GEMM Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) over bf16 NHWC [F,H,W,Cin] with folded BN:
+ * out = act(conv(x, w) + bias (+ residual)), bf16 NHWC [F,P,Q,Cout].  Cin % 64 == 0, Cout % 64 == 0.
+ * replaces: BasicBlock.forward conv1/bn1/relu, conv2/bn2/+=residual/relu and the downsample branch,
+ * transformer/video_frontend.py:28-41,68-72 */
+int sblk_conv2d_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const float* bias,
+                          const void* residual_bf16, void* out_bf16, int F, int H, int W, int Cin, int Cout,
+                          int R, int S, int stride, int pad, int relu, void* stream);
+/* bf16 NHWC [F,HW,C] -> mean over HW: fp32 [F,C] and/or bf16 [F,C] (either may be NULL).
+ * replaces: nn.AdaptiveAvgPool2d(1) + view, transformer/video_frontend.py:87-88 */
+int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);
+
+/* ---- transformer encoder -------------------------------------------------------------------------- */
+/* out = act(A[M,K] * W[N,K]^T + bias (+ residual_bf16)); bf16 operands, fp32 accumulate; writes bf16 and/or fp32.
+ * K % 64 == 0, N % 64 == 0.
+ * replaces: nn.Linear call sites, transformer/attention.py:41-43,57 ; module.py:49 ; encoder.py:53 */
+int sblk_gemm_fwd(const void* a_bf16, const void* w_bf16, const float* bias, const void* residual_bf16,
+                  void* out_bf16, float* out_f32, int M, int N, int K, int relu, void* stream);
+/* y = LayerNorm(x + residual) * gamma + beta (+ pe[m % T]) (* (m % T < lengths[m / T])), D must be 512.
+ * residual, pe, lengths, out_f32, out_bf16 may be NULL.
+ * replaces: nn.LayerNorm call sites attention.py:58, module.py:51, encoder.py:53-55 (+PositionalEncoding,
+ * module.py:26-32) and the non_pad_mask multiplies, encoder.py:86,89 + utils.py:98-113 */
+int sblk_add_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
+                           const float* pe, const int* lengths, float* out_f32, void* out_bf16, int M, int T,
+                           int D, float eps, void* stream);
+/* Fused self-attention on a packed projection qkv bf16 [N*T, 3*H*64] (q|k|v): softmax(QK^T * scale, keys >=
+ * lengths[b] masked) V -> bf16 [N*T, H*64].  probs (optional) fp32 [H*N, T, T] with batch index h*N + b.
+ * d_k must be 64, T <= 128.
+ * replaces: ScaledDotProductAttention.forward + head split/merge, transformer/attention.py:45-55,72-83 and
+ * get_attn_pad_mask, transformer/utils.py:140-147 */
+int sblk_attention_fwd(const void* qkv_bf16, void* out_bf16, float* probs, const int* lengths, int N, int T,
+                       int H, int d_k, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBLK_H_ */

@@ -1,0 +1,74 @@
+"""ctypes binding of libsblk.so (C ABI declared in include/sblk.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a RuntimeError
+is raised.  PyTorch is used by callers only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsblk.so")
+
+_lock = threading.Lock()
+_lib = None
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_ll = ctypes.c_longlong
+
+# name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).
+SIGNATURES = {
+    "sblk_version": (_i, []),
+    "sblk_last_error": (ctypes.c_char_p, []),
+    "sblk_init": (_i, []),
+    "sblk_watchdog_code": (ctypes.c_uint, []),
+    "sblk_set_pdl": (_i, [_i]),
+    "sblk_launch_count": (_ll, []),
+    "sblk_pack_conv3d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
+    "sblk_pack_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sblk_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "sblk_prep_clip": (_i, [_vp, _vp, _i, _i, _vp]),
+    "sblk_conv3d_bn_relu_pool_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "sblk_conv2d_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "sblk_avgpool_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sblk_gemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sblk_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "sblk_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
+}
+
+
+def load():
+    """Load libsblk.so once; raise loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU / PyTorch fallback for the visual-encoder path.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def last_error() -> str:
+    return load().sblk_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        lib = load()
+        wd = lib.sblk_watchdog_code()
+        extra = f" [pipeline watchdog 0x{wd:08x}]" if wd else ""
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}{extra}")

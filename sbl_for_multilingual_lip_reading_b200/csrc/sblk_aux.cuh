@@ -1,0 +1,230 @@
+// sblk_aux.cuh — the memory-bound kernels of the visual encoder (HBM roofline, not tensor):
+//   clip prep (fp32 -> padded bf16), weight packers (BN fold), global average pool,
+//   residual + LayerNorm (+ positional encoding, + pad mask), fp32 -> bf16 cast.
+#pragma once
+#include "sblk_common.cuh"
+#include "sblk_conv3d.cuh"
+
+namespace sblk {
+
+// --------------------------------------------------------------------------------------------
+// Clip prep: x fp32 [N,1,T,88,88] -> bf16 [N, T+4, 94, 96] with zero borders (2 frames each side in
+// time = Conv3d temporal padding; 3 px spatial padding).  Lets the Conv3d loader fetch its 5x51x96
+// patch with ONE un-predicated TMA.  Reference: input layout of Lipreading.forward,
+// SBL/transformer/video_frontend.py:119-121 (+ Conv3d padding=(2,3,3), :100).
+// One thread per 8 output pixels (16-B store).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_clip_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int T) {
+  using namespace c3d;
+  const int TP = T + 2 * TPAD;
+  const long long total = static_cast<long long>(N) * TP * HP * (WP / 8);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cx = static_cast<int>(i % (WP / 8));
+    long long r = i / (WP / 8);
+    const int py = static_cast<int>(r % HP);
+    r /= HP;
+    const int tp = static_cast<int>(r % TP);
+    const int n = static_cast<int>(r / TP);
+    const int t = tp - TPAD;
+    const int y = py - 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+    if (t >= 0 && t < T && y >= 0 && y < IN_HW) {
+      const float* src = x + ((static_cast<long long>(n) * T + t) * IN_HW + y) * IN_HW;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int xx = cx * 8 + e - 3;
+        if (xx >= 0 && xx < IN_HW) v[e] = __ldg(src + xx);
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Weight packers.  Eval-mode BatchNorm y = (x - mean) * gamma / sqrt(var + eps) + beta is folded:
+//   w' = w * gamma / sqrt(var + eps)   (per output channel), bias' = beta - mean * gamma / sqrt(var + eps)
+// Reference BN call sites: video_frontend.py:21,24,71,101 (eps = 1e-5 PyTorch default).
+// --------------------------------------------------------------------------------------------
+// Conv2d weight fp32 [Co,Ci,R,S] -> bf16 [Co][R][S][Ci] (K-major for the implicit GEMM), bias fp32 [Co].
+__global__ void __launch_bounds__(256)
+pack_conv2d_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                   __nv_bfloat16* __restrict__ wp, float* __restrict__ bias, int Co, int Ci, int R, int S) {
+  const int total = Co * Ci * R * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ci = i % Ci;
+    int r = i / Ci;
+    const int s = r % S;
+    r /= S;
+    const int rr = r % R;
+    const int co = r / R;
+    const float scale = (gamma != nullptr) ? gamma[co] / sqrtf(var[co] + eps) : 1.0f;
+    wp[i] = __float2bfloat16_rn(w[((co * Ci + ci) * R + rr) * S + s] * scale);
+    if (ci == 0 && s == 0 && rr == 0 && bias != nullptr) {
+      bias[co] = (gamma != nullptr) ? beta[co] - mean[co] * scale : 0.0f;
+    }
+  }
+}
+
+// Conv3d stem weight fp32 [64,1,5,7,7] -> bf16 [64][320]: k = (dt*7 + r)*8 + s, s == 7 and k >= 280 are zero.
+__global__ void __launch_bounds__(256)
+pack_conv3d_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                   __nv_bfloat16* __restrict__ wp, float* __restrict__ bias) {
+  const int total = c3d::COUT * c3d::KPAD;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % c3d::KPAD;
+    const int co = i / c3d::KPAD;
+    const float scale = gamma[co] / sqrtf(var[co] + eps);
+    float v = 0.0f;
+    const int s = k & 7;
+    const int c = k >> 3;
+    if (c < 35 && s < 7) {
+      const int dt = c / 7;
+      const int r = c - dt * 7;
+      v = w[((co * 5 + dt) * 7 + r) * 7 + s] * scale;
+    }
+    wp[i] = __float2bfloat16_rn(v);
+    if (k == 0) bias[co] = beta[co] - mean[co] * scale;
+  }
+}
+
+// fp32 -> bf16 cast (Linear weights, encoder input).  n must be a multiple of 4.
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Global average pool: bf16 NHWC [F, HW, C] -> fp32 [F, C] (+ optional bf16 copy).
+// Reference: ResNet.avgpool + view, SBL/transformer/video_frontend.py:87-88.
+// One thread per (frame, channel pair).
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out_f32,
+               __nv_bfloat16* __restrict__ out_bf16, int F, int HW, int C) {
+  const int C2 = C >> 1;
+  const long long total = static_cast<long long>(F) * C2;
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c2 = static_cast<int>(i % C2);
+    const long long f = i / C2;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(x) + f * HW * C2 + c2;
+    float a = 0.0f, b = 0.0f;
+    for (int q = 0; q < HW; ++q) {
+      const uint32_t u = __ldg(src + static_cast<long long>(q) * C2);
+      a += bf16_lo(u);
+      b += bf16_hi(u);
+    }
+    a *= inv;
+    b *= inv;
+    if (out_f32 != nullptr) reinterpret_cast<float2*>(out_f32)[i] = make_float2(a, b);
+    if (out_bf16 != nullptr) reinterpret_cast<uint32_t*>(out_bf16)[i] = pack_bf16x2(a, b);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// y = LayerNorm(x + residual) * gamma + beta  (+ pe[t])  (* pad_mask[b,t]),  D = 512, eps = 1e-5.
+// Reference: attention.py:58, module.py:51, encoder.py:53-55 (+PE), encoder.py:86,89 (mask).
+// One warp per row; the row lives in registers (16 values per lane); two-pass mean / variance in fp32.
+// Writes the fp32 residual stream and the bf16 copy the next GEMM consumes.
+// --------------------------------------------------------------------------------------------
+struct LnParams {
+  const float* x;         // [M, 512] GEMM output (bias already added)
+  const float* residual;  // [M, 512] or nullptr
+  const float* gamma;     // [512]
+  const float* beta;      // [512]
+  const float* pe;        // [>=T, 512] or nullptr ; row t = m % T
+  const int* lengths;     // [M / T] or nullptr ; rows with t >= lengths[b] are zeroed
+  float* out_f32;         // [M, 512] or nullptr
+  __nv_bfloat16* out_bf16;  // [M, 512] or nullptr
+  int M;
+  int T;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256)
+add_layernorm512_kernel(const LnParams p) {
+  grid_dep_wait();
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int m = blockIdx.x * warps_per_block + (threadIdx.x >> 5); m < p.M; m += gridDim.x * warps_per_block) {
+    const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<size_t>(m) * 512);
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = __ldg(xr + j * 32 + lane);
+      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+    }
+    if (p.residual != nullptr) {
+      const float4* rr = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * 512);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = __ldg(rr + j * 32 + lane);
+        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+      }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += v[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / 512.0f);
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float d = v[j] - mean;
+      q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / 512.0f) + p.eps);
+    const int t = m % p.T;
+    float keep = 1.0f;
+    if (p.lengths != nullptr && t >= __ldg(p.lengths + m / p.T)) keep = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col4 = j * 32 + lane;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + col4);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + col4);
+      float4 y;
+      y.x = (v[4 * j] - mean) * rstd * g.x + b.x;
+      y.y = (v[4 * j + 1] - mean) * rstd * g.y + b.y;
+      y.z = (v[4 * j + 2] - mean) * rstd * g.z + b.z;
+      y.w = (v[4 * j + 3] - mean) * rstd * g.w + b.w;
+      if (p.pe != nullptr) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(p.pe + static_cast<size_t>(t) * 512) + col4);
+        y.x += e.x; y.y += e.y; y.z += e.z; y.w += e.w;
+      }
+      y.x *= keep; y.y *= keep; y.z *= keep; y.w *= keep;
+      if (p.out_f32 != nullptr)
+        reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * 512)[col4] = y;
+      if (p.out_bf16 != nullptr) {
+        uint2 o;
+        o.x = pack_bf16x2(y.x, y.y);
+        o.y = pack_bf16x2(y.z, y.w);
+        reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(m) * 512)[col4] = o;
+      }
+    }
+  }
+  grid_dep_launch();
+}
+
+}  // namespace sblk

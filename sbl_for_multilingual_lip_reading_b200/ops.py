@@ -1,0 +1,186 @@
+"""Thin tensor-level wrappers over the libsblk C ABI.
+
+Each function validates dtype / device / contiguity, allocates the output with torch (device memory is
+torch's job, arithmetic is not) and enqueues the kernel on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (no CPU fallback exists), got {t.device}")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor")
+
+
+def init() -> int:
+    """Per-device setup; returns the SM count."""
+    n = _lib.load().sblk_init()
+    if n <= 0:
+        raise RuntimeError(f"sblk_init failed (rc={n}): {_lib.last_error()}")
+    return n
+
+
+def set_pdl(enable: bool) -> bool:
+    return bool(_lib.load().sblk_set_pdl(1 if enable else 0))
+
+
+def launch_count() -> int:
+    return int(_lib.load().sblk_launch_count())
+
+
+# ------------------------------------------------------------------------------------ packers
+def pack_conv3d(w, gamma, beta, mean, var, eps=1e-5):
+    for t, n in ((w, "w"), (gamma, "gamma"), (beta, "beta"), (mean, "mean"), (var, "var")):
+        _req(t, F32, n)
+    if tuple(w.shape) != (64, 1, 5, 7, 7):
+        raise RuntimeError(f"pack_conv3d: weight shape {tuple(w.shape)} != (64,1,5,7,7)")
+    wp = torch.empty((64, 320), dtype=BF16, device=w.device)
+    bias = torch.empty((64,), dtype=F32, device=w.device)
+    _lib.check(_lib.load().sblk_pack_conv3d(_p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
+                                            _stream()), "sblk_pack_conv3d")
+    return wp, bias
+
+
+def pack_conv2d(w, gamma=None, beta=None, mean=None, var=None, eps=1e-5):
+    _req(w, F32, "w")
+    for t, n in ((gamma, "gamma"), (beta, "beta"), (mean, "mean"), (var, "var")):
+        _req(t, F32, n)
+    co, ci, r, s = w.shape
+    wp = torch.empty((co, r, s, ci), dtype=BF16, device=w.device)
+    bias = torch.empty((co,), dtype=F32, device=w.device)
+    _lib.check(_lib.load().sblk_pack_conv2d(_p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
+                                            co, ci, r, s, _stream()), "sblk_pack_conv2d")
+    return wp, bias
+
+
+def cast_bf16(x, out=None):
+    _req(x, F32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _req(out, BF16, "out")
+    _lib.check(_lib.load().sblk_cast_f32_bf16(_p(x), _p(out), x.numel(), _stream()), "sblk_cast_f32_bf16")
+    return out
+
+
+# ------------------------------------------------------------------------------------ frontend
+def prep_clip(x, out=None):
+    """x fp32 [N,1,T,88,88] (or [N,T,88,88]) -> bf16 [N,T+4,94,96] zero-bordered."""
+    _req(x, F32, "x")
+    if x.dim() == 5:
+        n, c, t, h, w = x.shape
+        if c != 1:
+            raise RuntimeError("prep_clip: expected one (gray) channel")
+    else:
+        n, t, h, w = x.shape
+    if (h, w) != (88, 88):
+        raise RuntimeError(f"prep_clip: frames must be 88x88, got {h}x{w}")
+    if out is None:
+        out = torch.empty((n, t + 4, 94, 96), dtype=BF16, device=x.device)
+    _req(out, BF16, "out")
+    _lib.check(_lib.load().sblk_prep_clip(_p(x), _p(out), n, t, _stream()), "sblk_prep_clip")
+    return out
+
+
+def conv3d_bn_relu_pool(xp, wp, bias, out=None):
+    """prepped clip bf16 [N,T+4,94,96] -> bf16 NHWC [N*T,22,22,64]."""
+    _req(xp, BF16, "xp"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
+    n, tp = xp.shape[0], xp.shape[1]
+    t = tp - 4
+    if out is None:
+        out = torch.empty((n * t, 22, 22, 64), dtype=BF16, device=xp.device)
+    _req(out, BF16, "out")
+    _lib.check(_lib.load().sblk_conv3d_bn_relu_pool_fwd(_p(xp), _p(wp), _p(bias), _p(out), n, t, _stream()),
+               "sblk_conv3d_bn_relu_pool_fwd")
+    return out
+
+
+def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
+    """x bf16 NHWC [F,H,W,Cin], wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout]."""
+    _req(x, BF16, "x"); _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
+    f, h, w, cin = x.shape
+    cout, r, s, cin2 = wp.shape
+    if cin2 != cin:
+        raise RuntimeError(f"conv2d: Cin mismatch {cin} vs {cin2}")
+    pad = 1 if r == 3 else 0
+    p = (h + 2 * pad - r) // stride + 1
+    q = (w + 2 * pad - s) // stride + 1
+    if out is None:
+        out = torch.empty((f, p, q, cout), dtype=BF16, device=x.device)
+    _req(out, BF16, "out")
+    if residual is not None and residual.numel() != out.numel():
+        raise RuntimeError("conv2d: residual shape mismatch")
+    _lib.check(_lib.load().sblk_conv2d_igemm_fwd(_p(x), _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout,
+                                                 r, s, stride, pad, 1 if relu else 0, _stream()),
+               "sblk_conv2d_igemm_fwd")
+    return out
+
+
+def avgpool(x, want_f32=True, want_bf16=False):
+    _req(x, BF16, "x")
+    f, c = x.shape[0], x.shape[-1]
+    hw = x.numel() // (f * c)
+    o32 = torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None
+    o16 = torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None
+    _lib.check(_lib.load().sblk_avgpool_fwd(_p(x), _p(o32), _p(o16), f, hw, c, _stream()), "sblk_avgpool_fwd")
+    return o32, o16
+
+
+# ------------------------------------------------------------------------------------ encoder
+def gemm(a, w, bias=None, residual=None, relu=False, out_bf16=False, out_f32=False):
+    """a bf16 [M,K], w bf16 [N,K] -> (bf16 [M,N] | None, fp32 [M,N] | None)."""
+    _req(a, BF16, "a"); _req(w, BF16, "w"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
+    m, k = a.shape
+    n, k2 = w.shape
+    if k2 != k:
+        raise RuntimeError(f"gemm: K mismatch {k} vs {k2}")
+    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if out_bf16 else None
+    o32 = torch.empty((m, n), dtype=F32, device=a.device) if out_f32 else None
+    _lib.check(_lib.load().sblk_gemm_fwd(_p(a), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), m, n, k,
+                                         1 if relu else 0, _stream()), "sblk_gemm_fwd")
+    return o16, o32
+
+
+def add_layernorm(x, gamma, beta, residual=None, pe=None, lengths=None, T=1, eps=1e-5, want_f32=True,
+                  want_bf16=True):
+    _req(x, F32, "x"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta"); _req(residual, F32, "residual")
+    _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths")
+    m, d = x.shape
+    o32 = torch.empty((m, d), dtype=F32, device=x.device) if want_f32 else None
+    o16 = torch.empty((m, d), dtype=BF16, device=x.device) if want_bf16 else None
+    _lib.check(_lib.load().sblk_add_layernorm_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths),
+                                                  _p(o32), _p(o16), m, T, d, eps, _stream()),
+               "sblk_add_layernorm_fwd")
+    return o32, o16
+
+
+def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
+    _req(qkv, BF16, "qkv"); _req(lengths, torch.int32, "lengths")
+    if tuple(qkv.shape) != (n * t, 3 * h * d_k):
+        raise RuntimeError(f"attention: qkv shape {tuple(qkv.shape)} != {(n * t, 3 * h * d_k)}")
+    out = torch.empty((n * t, h * d_k), dtype=BF16, device=qkv.device)
+    probs = torch.empty((h * n, t, t), dtype=F32, device=qkv.device) if want_probs else None
+    if scale is None:
+        scale = 1.0 / (d_k ** 0.5)
+    _lib.check(_lib.load().sblk_attention_fwd(_p(qkv), _p(out), _p(probs), _p(lengths), n, t, h, d_k, scale,
+                                              _stream()), "sblk_attention_fwd")
+    return out, probs

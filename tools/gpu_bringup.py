@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""GPU bring-up diagnostics for libsblk (run on a B200 via gpurun).
+
+    python tools/gpu_bringup.py <section>      sections: aux gemm conv probe conv3d
+
+Each section runs in its own process (a trapped kernel kills the CUDA context) and compares the
+hand-written kernels against torch fp32 ops evaluated on the SAME bf16-rounded operands.
+torch is the checker here, never the product path.
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+import torch.nn.functional as F
+
+from sbl_for_multilingual_lip_reading_b200 import ops, _lib
+
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+DEV = "cuda"
+FAILS = []
+
+
+def report(name, got, ref, tol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    diff = (got - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    rel_max = diff.max().item() / denom
+    fro = (diff.norm() / (ref.norm() + 1e-12)).item()
+    bad = (diff > tol * denom).float().mean().item()
+    ok = fro < tol and bad < 1e-3 and bool(torch.isfinite(got).all())
+    print(f"[{'OK ' if ok else 'BAD'}] {name}: rel_fro={fro:.3e} max_rel={rel_max:.3e} bad_frac={bad:.3e} "
+          f"shape={tuple(got.shape)}", flush=True)
+    if not ok:
+        FAILS.append(name)
+    return ok
+
+
+def pattern(name, got, ref, rows_mod=128):
+    """Where are the errors? Per row-in-tile and per column block."""
+    got = got.float().reshape(-1, got.shape[-1])
+    ref = ref.float().reshape(-1, ref.shape[-1])
+    err = (got - ref).abs() > 0.05 * (ref.abs().max() + 1e-9)
+    m, n = err.shape
+    rows = err.any(dim=1)
+    print(f"   {name}: bad rows {int(rows.sum())}/{m}; bad cols {int(err.any(dim=0).sum())}/{n}")
+    idx = torch.nonzero(rows).flatten()[:24].tolist()
+    print(f"   first bad rows: {idx}")
+    rim = torch.zeros(rows_mod)
+    for r in torch.nonzero(rows).flatten().tolist()[:100000]:
+        rim[r % rows_mod] += 1
+    print(f"   bad rows by (row % {rows_mod}) [8-bins]: {rim.reshape(8, -1).sum(1).tolist()}")
+    cb = err.any(dim=0).reshape(-1, min(n, 16)).any(dim=1).int().tolist() if n % 16 == 0 else []
+    print(f"   bad col blocks(16): {cb}")
+    if len(idx):
+        r0 = idx[0]
+        print(f"   row {r0} got[:8]={got[r0, :8].tolist()}\n   row {r0} ref[:8]={ref[r0, :8].tolist()}")
+
+
+def bf(x):
+    return x.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+def sec_aux():
+    g = torch.Generator(device="cpu").manual_seed(0)
+    # prep
+    x = torch.randn(2, 1, 5, 88, 88, generator=g).to(DEV)
+    xp = ops.prep_clip(x)
+    ref = torch.zeros(2, 9, 94, 96, device=DEV)
+    ref[:, 2:7, 3:91, 3:91] = x[:, 0]
+    report("prep_clip", xp, bf(ref))
+    # pack conv2d
+    w = torch.randn(128, 64, 3, 3, generator=g).to(DEV)
+    gam = (torch.rand(128, generator=g) + 0.5).to(DEV)
+    bet = torch.randn(128, generator=g).to(DEV) * 0.1
+    mu = torch.randn(128, generator=g).to(DEV) * 0.1
+    var = (torch.rand(128, generator=g) + 0.5).to(DEV)
+    wp, b = ops.pack_conv2d(w, gam, bet, mu, var)
+    sc = gam / torch.sqrt(var + 1e-5)
+    report("pack_conv2d.w", wp, bf((w * sc[:, None, None, None]).permute(0, 2, 3, 1)))
+    report("pack_conv2d.b", b, bet - mu * sc, tol=1e-5)
+    # pack conv3d
+    w3 = torch.randn(64, 1, 5, 7, 7, generator=g).to(DEV)
+    wp3, b3 = ops.pack_conv3d(w3, gam[:64].contiguous(), bet[:64].contiguous(), mu[:64].contiguous(),
+                              var[:64].contiguous())
+    sc3 = gam[:64] / torch.sqrt(var[:64] + 1e-5)
+    ref3 = torch.zeros(64, 40, 8, device=DEV)
+    ref3[:, :35, :7] = (w3[:, 0] * sc3[:, None, None, None]).reshape(64, 35, 7)
+    report("pack_conv3d.w", wp3, bf(ref3.reshape(64, 320)))
+    # cast
+    a = torch.randn(1000, 512, generator=g).to(DEV)
+    report("cast", ops.cast_bf16(a), bf(a))
+    # avgpool
+    t = bf(torch.randn(37, 3, 3, 512, generator=g)).to(DEV)
+    o32, o16 = ops.avgpool(t, True, True)
+    report("avgpool.f32", o32, t.float().mean(dim=(1, 2)), tol=1e-5)
+    report("avgpool.bf16", o16, bf(t.float().mean(dim=(1, 2))))
+    # layernorm
+    M, T = 29 * 6, 29
+    xx = torch.randn(M, 512, generator=g).to(DEV)
+    rr = torch.randn(M, 512, generator=g).to(DEV)
+    gm = torch.randn(512, generator=g).to(DEV)
+    bt = torch.randn(512, generator=g).to(DEV)
+    pe = torch.randn(40, 512, generator=g).to(DEV)
+    lens = torch.tensor([29, 20, 1, 29, 0, 15], dtype=torch.int32, device=DEV)
+    o32, o16 = ops.add_layernorm(xx, gm, bt, residual=rr, pe=pe, lengths=lens, T=T)
+    ref = F.layer_norm(xx + rr, (512,), gm, bt, 1e-5) + pe[:T].repeat(6, 1)
+    mask = (torch.arange(T, device=DEV)[None, :] < lens[:, None]).reshape(-1, 1).float()
+    report("layernorm(res,pe,mask).f32", o32, ref * mask, tol=1e-4)
+    report("layernorm.bf16", o16, bf(ref * mask))
+    o32, _ = ops.add_layernorm(xx, gm, bt, T=T, want_bf16=False)
+    report("layernorm(plain)", o32, F.layer_norm(xx, (512,), gm, bt, 1e-5), tol=1e-4)
+    # attention
+    for (N, T, lens) in [(4, 29, None), (3, 40, [40, 17, 1]), (2, 100, [100, 64]), (2, 31, None)]:
+        H = 8
+        qkv = bf(torch.randn(N * T, 3 * H * 64, generator=g)).to(DEV)
+        lt = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=DEV)
+        out, probs = ops.attention(qkv, N, T, H, lengths=lt, want_probs=True)
+        q, k, v = [z.float().reshape(N, T, H, 64).permute(2, 0, 1, 3).reshape(H * N, T, 64)
+                   for z in qkv.split(H * 64, dim=1)]
+        att = torch.bmm(q, k.transpose(1, 2)) / 8.0
+        if lens is not None:
+            km = (torch.arange(T, device=DEV)[None, :] >= lt[:, None])  # [N,T] True = masked key
+            att = att.masked_fill(km[:, None, :].expand(N, T, T).repeat(H, 1, 1), float("-inf"))
+        pr = torch.softmax(att, dim=2)
+        o = torch.bmm(pr, v).reshape(H, N, T, 64).permute(1, 2, 0, 3).reshape(N * T, H * 64)
+        report(f"attention N{N} T{T} lens={lens}", out, bf(o))
+        report(f"attention.probs N{N} T{T}", probs, pr, tol=1e-3)
+
+
+def sec_gemm():
+    g = torch.Generator(device="cpu").manual_seed(1)
+    cases = [(128, 64, 64), (128, 128, 128), (256, 256, 64), (928, 512, 512), (928, 1536, 512), (928, 2048, 512),
+             (928, 512, 2048), (300, 192, 192), (29, 512, 512), (40000, 64, 576), (20000, 512, 1024)]
+    for i, (M, N, K) in enumerate(cases):
+        a = bf(torch.randn(M, K, generator=g)).to(DEV)
+        w = bf(torch.randn(N, K, generator=g) / (K ** 0.5)).to(DEV)
+        bias = torch.randn(N, generator=g).to(DEV)
+        res = bf(torch.randn(M, N, generator=g)).to(DEV)
+        ref0 = a.float() @ w.float().t()
+        o16, o32 = ops.gemm(a, w, out_bf16=True, out_f32=True)
+        torch.cuda.synchronize()
+        ok = report(f"gemm plain M{M} N{N} K{K} f32", o32, ref0, tol=1e-4)
+        report(f"gemm plain M{M} N{N} K{K} bf16", o16, bf(ref0))
+        if not ok:
+            pattern("gemm", o32, ref0)
+        o16, o32 = ops.gemm(a, w, bias=bias, residual=res, relu=True, out_bf16=True, out_f32=True)
+        ref1 = torch.relu(ref0 + bias + res.float())
+        ok = report(f"gemm bias+res+relu M{M} N{N} K{K} f32", o32, ref1, tol=1e-4)
+        if not ok:
+            pattern("gemm.epi", o32, ref1)
+    # error path: unsupported K
+    try:
+        ops.gemm(bf(torch.zeros(8, 48)).to(DEV), bf(torch.zeros(64, 48)).to(DEV), out_f32=True)
+        print("[BAD] gemm K=48 did not raise")
+        FAILS.append("gemm-raise")
+    except RuntimeError as e:
+        print("[OK ] gemm K=48 raises:", str(e)[:100])
+
+
+def conv_ref(x, wp, bias, stride, relu, residual):
+    # x NHWC bf16, wp [Co,R,S,Ci] bf16
+    xr = x.float().permute(0, 3, 1, 2)
+    wr = wp.float().permute(0, 3, 1, 2)
+    pad = 1 if wp.shape[1] == 3 else 0
+    y = F.conv2d(xr, wr, bias, stride=stride, padding=pad)
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2)
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def sec_conv():
+    g = torch.Generator(device="cpu").manual_seed(2)
+    cases = [  # F, H, Cin, Cout, R, stride
+        (3, 22, 64, 64, 3, 1), (29, 22, 64, 64, 3, 1), (5, 22, 64, 128, 3, 2), (5, 22, 64, 128, 1, 2),
+        (7, 11, 128, 128, 3, 1), (7, 11, 128, 256, 3, 2), (7, 11, 128, 256, 1, 2), (9, 6, 256, 256, 3, 1),
+        (9, 6, 256, 512, 3, 2), (9, 6, 256, 512, 1, 2), (40, 3, 512, 512, 3, 1), (300, 22, 64, 64, 3, 1),
+        (1, 22, 64, 64, 3, 1), (2, 3, 512, 512, 3, 1),
+    ]
+    for (Fr, H, Ci, Co, R, st) in cases:
+        x = bf(torch.randn(Fr, H, H, Ci, generator=g)).to(DEV)
+        wp = bf(torch.randn(Co, R, R, Ci, generator=g) / ((R * R * Ci) ** 0.5)).to(DEV)
+        bias = torch.randn(Co, generator=g).to(DEV)
+        out = ops.conv2d(x, wp, bias, stride=st, relu=False)
+        torch.cuda.synchronize()
+        ref = conv_ref(x, wp, bias, st, False, None)
+        name = f"conv F{Fr} H{H} {Ci}->{Co} k{R} s{st}"
+        ok = report(name, out, bf(ref))
+        if not ok:
+            pattern(name, out, ref)
+        res = bf(torch.randn(*ref.shape, generator=g)).to(DEV)
+        out = ops.conv2d(x, wp, bias, stride=st, relu=True, residual=res)
+        ok = report(name + " +res+relu", out, bf(conv_ref(x, wp, bias, st, True, res)))
+
+
+def sec_probe():
+    """Identity-tap probe: which input pixel does each (r,s) tap of the im2col TMA actually fetch?"""
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for (Fr, H, st, R) in [(2, 22, 1, 3), (2, 22, 2, 3), (2, 11, 2, 1), (3, 6, 1, 3)]:
+        Ci = Co = 64
+        x = bf(torch.randn(Fr, H, H, Ci, generator=g)).to(DEV)
+        pad = 1 if R == 3 else 0
+        P = (H + 2 * pad - R) // st + 1
+        xpad = F.pad(x.float(), (0, 0, 4, 4, 4, 4))  # generous zero border for shift search
+        for r in range(R):
+            for s in range(R):
+                wp = torch.zeros(Co, R, R, Ci)
+                wp[torch.arange(Co), r, s, torch.arange(Ci)] = 1.0
+                out = ops.conv2d(x, bf(wp).to(DEV), torch.zeros(Co, device=DEV), stride=st, relu=False).float()
+                torch.cuda.synchronize()
+                best = None
+                for dy in range(-4, 5):
+                    for dx in range(-4, 5):
+                        ys = torch.arange(P) * st + dy + 4
+                        xs = torch.arange(P) * st + dx + 4
+                        if ys.min() < 0 or xs.min() < 0 or ys.max() >= H + 8 or xs.max() >= H + 8:
+                            continue
+                        cand = xpad[:, ys][:, :, xs]
+                        e = (cand - out).abs().max().item()
+                        if best is None or e < best[0]:
+                            best = (e, dy, dx)
+                exp = (r - pad, s - pad)
+                ok = best[0] < 1e-6 and (best[1], best[2]) == exp
+                print(f"[{'OK ' if ok else 'BAD'}] probe H{H} s{st} k{R} tap(r={r},s={s}): best shift (dy,dx)="
+                      f"({best[1]},{best[2]}) err={best[0]:.3e} expected {exp}", flush=True)
+                if not ok:
+                    FAILS.append(f"probe H{H} s{st} tap{r}{s}")
+
+
+def conv3d_ref(x, w3, gam, bet, mu, var):
+    # bf16-rounded operands, fp32 math: conv3d + folded BN + relu + maxpool, output NHWC per frame
+    sc = gam / torch.sqrt(var + 1e-5)
+    wf = bf(w3 * sc[:, None, None, None, None]).float()
+    xb = bf(x).float()
+    y = F.conv3d(xb, wf, None, stride=(1, 2, 2), padding=(2, 3, 3)) + (bet - mu * sc)[None, :, None, None, None]
+    y = torch.relu(y)
+    y = bf(y).float()  # the kernel rounds conv outputs to bf16 before pooling
+    y = F.max_pool3d(y, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    n, c, t, h, w = y.shape
+    return y.permute(0, 2, 3, 4, 1).reshape(n * t, h, w, c)
+
+
+def sec_conv3d():
+    g = torch.Generator(device="cpu").manual_seed(4)
+    w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / (245 ** 0.5)).to(DEV)
+    gam = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    bet = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    mu = (torch.randn(64, generator=g) * 0.1).to(DEV)
+    var = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    wp, bias = ops.pack_conv3d(w3, gam, bet, mu, var)
+    for (N, T) in [(1, 3), (1, 29), (3, 29), (2, 40), (8, 29)]:
+        x = torch.randn(N, 1, T, 88, 88, generator=g).to(DEV)
+        xp = ops.prep_clip(x)
+        out = ops.conv3d_bn_relu_pool(xp, wp, bias)
+        torch.cuda.synchronize()
+        ref = conv3d_ref(x, w3, gam, bet, mu, var)
+        name = f"conv3d N{N} T{T}"
+        ok = report(name, out, bf(ref))
+        if not ok:
+            d = (out.float() - ref).abs().reshape(N * T, 22, 22, 64)
+            thr = 0.05 * ref.abs().max()
+            print("   bad by frame:", (d > thr).float().mean(dim=(1, 2, 3)).tolist()[:12])
+            print("   bad by pooled row:", (d > thr).float().mean(dim=(0, 2, 3)).tolist())
+            print("   bad by pooled col:", (d > thr).float().mean(dim=(0, 1, 3)).tolist())
+            print("   bad by channel[:16]:", (d > thr).float().mean(dim=(0, 1, 2)).tolist()[:16])
+
+
+def sec_perf():
+    """Quick per-layer timing at the C2 shape (F = 928) to see where the time goes."""
+    g = torch.Generator(device="cpu").manual_seed(5)
+    Fr = 928
+
+    def timeit(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    layers = [(22, 64, 64, 3, 1), (22, 64, 128, 3, 2), (11, 128, 128, 3, 1), (22, 64, 128, 1, 2),
+              (11, 128, 256, 3, 2), (6, 256, 256, 3, 1), (6, 256, 512, 3, 2), (3, 512, 512, 3, 1)]
+    for (H, Ci, Co, R, st) in layers:
+        x = bf(torch.randn(Fr, H, H, Ci, generator=g)).to(DEV)
+        wp = bf(torch.randn(Co, R, R, Ci, generator=g) / ((R * R * Ci) ** 0.5)).to(DEV)
+        bias = torch.zeros(Co, device=DEV)
+        pad = 1 if R == 3 else 0
+        P = (H + 2 * pad - R) // st + 1
+        out = torch.empty(Fr, P, P, Co, dtype=torch.bfloat16, device=DEV)
+        ms = timeit(lambda: ops.conv2d(x, wp, bias, stride=st, relu=True, out=out))
+        fl = 2.0 * Fr * P * P * Co * R * R * Ci
+        print(f"perf conv H{H} {Ci}->{Co} k{R} s{st}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for (M, N, K) in [(928, 1536, 512), (928, 512, 512), (928, 2048, 512), (928, 512, 2048)]:
+        a = bf(torch.randn(M, K, generator=g)).to(DEV)
+        w = bf(torch.randn(N, K, generator=g)).to(DEV)
+        ms = timeit(lambda: ops.gemm(a, w, out_bf16=True))
+        print(f"perf gemm M{M} N{N} K{K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / 16).to(DEV)
+    one = torch.ones(64, device=DEV)
+    zero = torch.zeros(64, device=DEV)
+    wp3, b3 = ops.pack_conv3d(w3, one, zero, zero, one)
+    x = torch.randn(32, 1, 29, 88, 88, generator=g).to(DEV)
+    xp = ops.prep_clip(x)
+    out = torch.empty(928, 22, 22, 64, dtype=torch.bfloat16, device=DEV)
+    ms = timeit(lambda: ops.conv3d_bn_relu_pool(xp, wp3, b3, out=out))
+    print(f"perf conv3d N32 T29: {ms * 1e3:.1f} us  {2.0 * 928 * 44 * 44 * 64 * 245 / ms / 1e9:.1f} TFLOP/s")
+    ms = timeit(lambda: ops.prep_clip(x, out=xp))
+    print(f"perf prep N32 T29: {ms * 1e3:.1f} us")
+
+
+if __name__ == "__main__":
+    sec = sys.argv[1]
+    t0 = time.time()
+    print(f"=== section {sec}: SMs={ops.init()} torch={torch.__version__} dev={torch.cuda.get_device_name(0)}",
+          flush=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "pdl":
+        ops.set_pdl(True)
+        print("PDL enabled")
+    try:
+        {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d,
+         "perf": sec_perf}[sec]()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc()
+        print(f"EXCEPTION in section {sec}: {e}; watchdog=0x{_lib.load().sblk_watchdog_code():08x}", flush=True)
+        FAILS.append(f"exception:{sec}")
+    print(f"=== section {sec} done in {time.time() - t0:.1f}s; failures: {FAILS}", flush=True)
+    sys.exit(1 if FAILS else 0)
