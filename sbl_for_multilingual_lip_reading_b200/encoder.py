@@ -1,0 +1,201 @@
+"""Drop-in replacement for the reference transformer encoder (transformer/encoder.py + the parts of
+attention.py / module.py / utils.py it uses).
+
+`Encoder` has the reference constructor signature, attributes, state-dict keys and return convention
+((enc_output,) 1-tuple, or (enc_output, [attn]*n_layers) with return_attns=True — callers unpack with
+`enc_out, *_ = self.encoder(...)`, transformer/transformer.py:38).  Submodules are parameter holders with the
+reference's names and initialisation; the forward pass runs libsblk kernels only:
+
+    cast -> linear_in (tcgen05 GEMM) -> LayerNorm + PE  -> n_layers x {
+        packed QKV GEMM (tcgen05) -> fused softmax attention -> fc GEMM -> residual + LayerNorm (+pad mask)
+        w_1 GEMM + ReLU -> w_2 GEMM -> residual + LayerNorm (+pad mask) }
+
+The residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation.
+Masks are never materialised: `input_lengths` goes to the kernels as an int32 vector
+(reference builds them with a Python loop twice per call, transformer/utils.py:98-113,140-147).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class PositionalEncoding(nn.Module):
+    """Holder of the reference sin/cos table buffer `pe` [1,max_len,d_model] (transformer/module.py:8-32)."""
+
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model, requires_grad=False)
+        position = torch.arange(0, max_len).unsqueeze(1).float()
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer('pe', pe.unsqueeze(0))
+
+    def forward(self, input):
+        return self.pe[:, :input.size(1)]
+
+
+class _SelfAttentionParams(nn.Module):
+    """Parameter holder mirroring reference MultiHeadAttention.__init__ (transformer/attention.py:9-30)."""
+
+    def __init__(self, n_head, d_model, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.n_head, self.d_k, self.d_v = n_head, d_k, d_v
+        self.w_qs = nn.Linear(d_model, n_head * d_k)
+        self.w_ks = nn.Linear(d_model, n_head * d_k)
+        self.w_vs = nn.Linear(d_model, n_head * d_v)
+        nn.init.normal_(self.w_qs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_ks.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_vs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_v)))
+        self.temperature = float(np.power(d_k, 0.5))
+        self.layer_norm = nn.LayerNorm(d_model)
+        self.fc = nn.Linear(n_head * d_v, d_model)
+        nn.init.xavier_normal_(self.fc.weight)
+        self.dropout = nn.Dropout(dropout)
+
+
+class _FeedForwardParams(nn.Module):
+    """Parameter holder mirroring reference PositionwiseFeedForward.__init__ (transformer/module.py:40-45)."""
+
+    def __init__(self, d_model, d_ff, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, d_ff)
+        self.w_2 = nn.Linear(d_ff, d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model)
+
+
+class EncoderLayer(nn.Module):
+    """Holder with the reference EncoderLayer attribute names (transformer/encoder.py:70-81)."""
+
+    def __init__(self, d_model, d_inner, n_head, d_k, d_v, dropout=0.1):
+        super().__init__()
+        self.slf_attn = _SelfAttentionParams(n_head, d_model, d_k, d_v, dropout=dropout)
+        self.pos_ffn = _FeedForwardParams(d_model, d_inner, dropout=dropout)
+
+
+class _PackedEncoder:
+    __slots__ = ("key", "w_in", "layers")
+
+
+class Encoder(nn.Module):
+    """Drop-in for reference Encoder (transformer/encoder.py:8-67)."""
+
+    def __init__(self, d_input, n_layers, n_head, d_k, d_v, d_model, d_inner, dropout=0.1, pe_maxlen=5000):
+        super().__init__()
+        self.d_input = d_input
+        self.n_layers = n_layers
+        self.n_head = n_head
+        self.d_k = d_k
+        self.d_v = d_v
+        self.d_model = d_model
+        self.d_inner = d_inner
+        self.dropout_rate = dropout
+        self.pe_maxlen = pe_maxlen
+
+        self.linear_in = nn.Linear(d_input, d_model)
+        self.layer_norm_in = nn.LayerNorm(d_model)
+        self.positional_encoding = PositionalEncoding(d_model, max_len=pe_maxlen)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_stack = nn.ModuleList([
+            EncoderLayer(d_model, d_inner, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
+        self._packed = None
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_packed"] = None
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    def _check_config(self):
+        if self.d_model != 512 or self.d_k != 64 or self.d_v != 64:
+            raise RuntimeError(f"Encoder (libsblk): only d_model=512, d_k=d_v=64 are implemented "
+                               f"(got d_model={self.d_model}, d_k={self.d_k}, d_v={self.d_v}); no fallback path")
+        if self.d_input % 64 or self.d_inner % 64 or (self.n_head * self.d_k) % 64:
+            raise RuntimeError("Encoder (libsblk): d_input, d_inner and n_head*d_k must be multiples of 64")
+
+    def _cache_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _get_packed(self):
+        key = self._cache_key()
+        pk = self._packed
+        if pk is not None and pk.key == key:
+            return pk
+        pk = _PackedEncoder()
+        pk.key = key
+        pk.w_in = ops.cast_bf16(self.linear_in.weight.detach().contiguous())
+        pk.layers = []
+        for lyr in self.layer_stack:
+            a, f = lyr.slf_attn, lyr.pos_ffn
+            hk = self.n_head * self.d_k
+            wqkv = torch.empty((3 * hk, self.d_model), dtype=torch.bfloat16, device=a.w_qs.weight.device)
+            ops.cast_bf16(a.w_qs.weight.detach().contiguous(), out=wqkv[0:hk])
+            ops.cast_bf16(a.w_ks.weight.detach().contiguous(), out=wqkv[hk:2 * hk])
+            ops.cast_bf16(a.w_vs.weight.detach().contiguous(), out=wqkv[2 * hk:3 * hk])
+            bqkv = torch.cat([a.w_qs.bias.detach(), a.w_ks.bias.detach(), a.w_vs.bias.detach()]).contiguous()
+            pk.layers.append(dict(
+                wqkv=wqkv, bqkv=bqkv,
+                wfc=ops.cast_bf16(a.fc.weight.detach().contiguous()),
+                w1=ops.cast_bf16(f.w_1.weight.detach().contiguous()),
+                w2=ops.cast_bf16(f.w_2.weight.detach().contiguous())))
+        self._packed = pk
+        return pk
+
+    def forward(self, padded_input, input_lengths, return_attns=False):
+        """padded_input: N x T x d_input (fp32, CUDA); input_lengths: N ints -> (enc_output N x T x d_model,)"""
+        self._check_config()
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("Encoder (libsblk): training-mode forward/backward is not implemented yet; "
+                               "call .eval() / torch.no_grad()")
+        if not padded_input.is_cuda:
+            raise RuntimeError("Encoder (libsblk) runs on a B200 CUDA device only; no CPU fallback exists")
+        n, t, d_in = padded_input.shape
+        if d_in != self.d_input:
+            raise RuntimeError(f"Encoder: last dim {d_in} != d_input {self.d_input}")
+        if t > self.pe_maxlen:
+            raise RuntimeError(f"Encoder: T={t} exceeds pe_maxlen={self.pe_maxlen}")
+        lens = [int(v) for v in input_lengths]
+        if len(lens) != n:
+            raise RuntimeError(f"Encoder: {len(lens)} input_lengths for batch {n}")
+        m = n * t
+        x = padded_input.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous().view(m, d_in)
+        with torch.cuda.device(x.device):
+            pk = self._get_packed()
+            lengths = None
+            if any(v < t for v in lens):  # all-keep masks (every reference call site) cost nothing
+                lengths = torch.tensor(lens, dtype=torch.int32, device=x.device)
+            pe = self.positional_encoding.pe[0]
+            attns = []
+            x16 = ops.cast_bf16(x)
+            _, h32 = ops.gemm(x16, pk.w_in, bias=self.linear_in.bias.detach(), out_f32=True)
+            # encoder.py:53-55 — LN(linear_in(x)) + PE ; no pad mask at this point
+            x32, x16 = ops.add_layernorm(h32, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
+                                         pe=pe, T=t, eps=self.layer_norm_in.eps)
+            for lyr, w in zip(self.layer_stack, pk.layers):
+                a, f = lyr.slf_attn, lyr.pos_ffn
+                qkv16, _ = ops.gemm(x16, w["wqkv"], bias=w["bqkv"], out_bf16=True)
+                att16, probs = ops.attention(qkv16, n, t, self.n_head, self.d_k, lengths=lengths,
+                                             want_probs=return_attns, scale=1.0 / a.temperature)
+                _, o32 = ops.gemm(att16, w["wfc"], bias=a.fc.bias.detach(), out_f32=True)
+                x32, x16 = ops.add_layernorm(o32, a.layer_norm.weight.detach(), a.layer_norm.bias.detach(),
+                                             residual=x32, lengths=lengths, T=t, eps=a.layer_norm.eps)
+                h16, _ = ops.gemm(x16, w["w1"], bias=f.w_1.bias.detach(), relu=True, out_bf16=True)
+                _, o32 = ops.gemm(h16, w["w2"], bias=f.w_2.bias.detach(), out_f32=True)
+                x32, x16 = ops.add_layernorm(o32, f.layer_norm.weight.detach(), f.layer_norm.bias.detach(),
+                                             residual=x32, lengths=lengths, T=t, eps=f.layer_norm.eps)
+                if return_attns:
+                    attns.append(probs)
+        enc_output = x32.view(n, t, self.d_model)
+        if return_attns:
+            return enc_output, attns
+        return enc_output,

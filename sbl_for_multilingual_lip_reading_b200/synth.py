@@ -1,0 +1,100 @@
+"""Deterministic synthetic weights and clips for tests, smoke and bench (there is no network for real
+checkpoints or LRW data).  Keys/shapes follow the reference state dict exactly, so the same
+dict loads into the reference modules, the oracle and the drop-in modules.
+
+Distributions follow SURVEY.md §8d: xavier-uniform-like matrices / conv kernels (what Transformer.__init__
+leaves behind, transformer/transformer.py:18-20) and randomised BatchNorm statistics, so that the BN fold is
+actually exercised (default gamma=1, beta=0, mean=0, var=1 would make it an identity).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def _xavier(gen, shape):
+    """xavier_uniform_ bound for a weight of `shape` ([out, in, *kernel])."""
+    rf = 1
+    for s in shape[2:]:
+        rf *= s
+    fan_in, fan_out = shape[1] * rf, shape[0] * rf
+    bound = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
+
+
+def _bn(gen, sd, prefix, c):
+    sd[prefix + ".weight"] = torch.rand(c, generator=gen) + 0.5          # U(0.5,1.5)
+    sd[prefix + ".bias"] = torch.randn(c, generator=gen) * 0.1
+    sd[prefix + ".running_mean"] = torch.randn(c, generator=gen) * 0.1
+    sd[prefix + ".running_var"] = torch.rand(c, generator=gen) + 0.5
+    sd[prefix + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def frontend_state_dict(seed=1, prefix=""):
+    """State dict of reference `Lipreading` (transformer/video_frontend.py:91-109)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    sd[prefix + "frontend3D.0.weight"] = _xavier(gen, (64, 1, 5, 7, 7))
+    _bn(gen, sd, prefix + "frontend3D.1", 64)
+    inplanes = 64
+    for li, planes in ((1, 64), (2, 128), (3, 256), (4, 512)):
+        for bi in range(2):
+            p = f"{prefix}resnet18.layer{li}.{bi}"
+            cin = inplanes if bi == 0 else planes
+            sd[p + ".conv1.weight"] = _xavier(gen, (planes, cin, 3, 3))
+            _bn(gen, sd, p + ".bn1", planes)
+            sd[p + ".conv2.weight"] = _xavier(gen, (planes, planes, 3, 3))
+            _bn(gen, sd, p + ".bn2", planes)
+            if bi == 0 and li != 1:
+                sd[p + ".downsample.0.weight"] = _xavier(gen, (planes, cin, 1, 1))
+                _bn(gen, sd, p + ".downsample.1", planes)
+        inplanes = planes
+    return sd
+
+
+def encoder_state_dict(seed=2, n_layers=6, d_input=512, d_model=512, d_inner=2048, n_head=8, d_k=64, d_v=64,
+                       pe_maxlen=5000, prefix=""):
+    """State dict of reference `Encoder` (transformer/encoder.py:12-34)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+
+    def linear(name, out_f, in_f):
+        sd[name + ".weight"] = _xavier(gen, (out_f, in_f))
+        sd[name + ".bias"] = (torch.rand(out_f, generator=gen) * 2 - 1) / math.sqrt(in_f)
+
+    def ln(name):
+        sd[name + ".weight"] = torch.rand(d_model, generator=gen) + 0.5
+        sd[name + ".bias"] = torch.randn(d_model, generator=gen) * 0.1
+
+    linear(prefix + "linear_in", d_model, d_input)
+    ln(prefix + "layer_norm_in")
+    pe = torch.zeros(pe_maxlen, d_model)
+    position = torch.arange(0, pe_maxlen).unsqueeze(1).float()
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    sd[prefix + "positional_encoding.pe"] = pe.unsqueeze(0)
+    for i in range(n_layers):
+        p = f"{prefix}layer_stack.{i}"
+        linear(p + ".slf_attn.w_qs", n_head * d_k, d_model)
+        linear(p + ".slf_attn.w_ks", n_head * d_k, d_model)
+        linear(p + ".slf_attn.w_vs", n_head * d_v, d_model)
+        ln(p + ".slf_attn.layer_norm")
+        linear(p + ".slf_attn.fc", d_model, n_head * d_v)
+        linear(p + ".pos_ffn.w_1", d_inner, d_model)
+        linear(p + ".pos_ffn.w_2", d_model, d_inner)
+        ln(p + ".pos_ffn.layer_norm")
+    return sd
+
+
+def synthetic_clips(n, t, seed=7, pad_frames=0):
+    """LRW-shaped normalised gray clips [N,1,T,88,88] fp32: u8 ~ U{0..255} -> (u8/255 - 0.413621)/0.1700239
+    (cvtransforms.py:44-48); the last `pad_frames` frames are all-zero like the reference's zero padding
+    (data_gen.py:294-296)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    u8 = torch.randint(0, 256, (n, 1, t, 88, 88), generator=gen, dtype=torch.int32)
+    x = (u8.float() / 255.0 - 0.413621) / 0.1700239
+    if pad_frames:
+        x[:, :, t - pad_frames:] = 0.0
+    return x

@@ -1,0 +1,163 @@
+"""CPU-only checks of the host side: C-ABI surface, state-dict contract, init parity, pickling,
+loud failure without a GPU."""
+import io
+import json
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/SBL_Multilingual_Lip_reading"
+
+from sbl_for_multilingual_lip_reading_b200 import _lib, synth  # noqa: E402
+from sbl_for_multilingual_lip_reading_b200.encoder import Encoder  # noqa: E402
+from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading, visual_frontend  # noqa: E402
+
+
+def _contract():
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_contract.json")) as f:
+        return json.load(f)
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "sblk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sblk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sblk.h but not exported by libsblk.so"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.sblk_version() == 100
+
+
+def test_library_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    rc = lib.sblk_init()
+    assert rc < 0
+    assert "cuda" in _lib.last_error().lower()
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05 / TMA / TMEM instructions must be in the shipped binary (B200_PROFILING.md evidence table)."""
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    except FileNotFoundError:
+        pytest.skip("cuobjdump not available")
+    assert "UTCHMMA" in sass, "no tcgen05.mma in libsblk.so"
+    assert "UTMALDG" in sass and "IM2COL" in sass, "no TMA (im2col) loads in libsblk.so"
+    assert "LDTM" in sass, "no tcgen05.ld in libsblk.so"
+    assert " HMMA" not in sass, "legacy mma.sync path present"
+
+
+def test_state_dict_contract_frontend():
+    c = _contract()["Lipreading"]
+    sd = Lipreading().state_dict()
+    assert list(sd.keys()) == list(c.keys()) or sorted(sd.keys()) == sorted(c.keys())
+    for k, (shape, dtype) in c.items():
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+
+
+def test_state_dict_contract_encoder():
+    c = _contract()["Encoder6"]
+    sd = Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000).state_dict()
+    assert sorted(sd.keys()) == sorted(c.keys())
+    for k, (shape, dtype) in c.items():
+        assert list(sd[k].shape) == shape and str(sd[k].dtype) == dtype, k
+
+
+def test_synth_state_dicts_load():
+    fe = Lipreading()
+    fe.load_state_dict(synth.frontend_state_dict(1))
+    enc = Encoder(512, 3, 8, 64, 64, 512, 2048)
+    enc.load_state_dict(synth.encoder_state_dict(3, 3))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_init_parity_with_reference_under_same_seed():
+    """Same torch seed -> bit-identical initial weights as the reference constructors, and the reference
+    Transformer assembles with the drop-in classes patched in (transformer/transformer.py:9-20)."""
+    sys.path.insert(0, REF)
+    try:
+        from transformer.encoder import Encoder as RefEncoder
+        from transformer.video_frontend import Lipreading as RefLipreading
+        torch.manual_seed(7)
+        a = RefLipreading().state_dict()
+        torch.manual_seed(7)
+        b = Lipreading().state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+        torch.manual_seed(7)
+        a = RefEncoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000).state_dict()
+        torch.manual_seed(7)
+        b = Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000).state_dict()
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    finally:
+        sys.path.remove(REF)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_reference_transformer_assembles_on_dropins():
+    from sbl_for_multilingual_lip_reading_b200 import dropin
+    with dropin.patched_reference(REF) as mods:
+        from transformer.decoder import Decoder
+        from transformer.transformer import Transformer
+        enc = mods["transformer.encoder"].Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+        dec = Decoder(0, 1, 58, 512, 6, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1,
+                      pe_maxlen=5000)
+        model = Transformer(enc, dec, None)
+        assert type(model.visual_frontend).__module__.startswith("sbl_for_multilingual_lip_reading_b200")
+        assert type(model.encoder).__module__.startswith("sbl_for_multilingual_lip_reading_b200")
+        c = _contract()
+        assert len(model.state_dict()) == c["Transformer_num_keys"]
+        hot = sorted(k for k in model.state_dict() if k.startswith(("visual_frontend.", "encoder.")))
+        assert hot == c["Transformer_hot_path_keys"]
+
+
+def test_modules_pickle_roundtrip():
+    """Checkpoints are whole pickled modules in the reference (utils.py:22-33)."""
+    fe = visual_frontend(None)
+    enc = Encoder(512, 2, 8, 64, 64, 512, 2048)
+    buf = io.BytesIO()
+    torch.save({"fe": fe, "enc": enc}, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    for k, v in fe.state_dict().items():
+        assert torch.equal(v, back["fe"].state_dict()[k])
+    assert pickle.loads(pickle.dumps(enc)).n_layers == 2
+
+
+def test_cpu_input_is_rejected_loudly():
+    fe = Lipreading().eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        fe(torch.zeros(1, 1, 2, 88, 88))
+    enc = Encoder(512, 1, 8, 64, 64, 512, 2048).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(1, 4, 512), [4])
+
+
+def test_unsupported_encoder_config_is_rejected():
+    enc = Encoder(512, 1, 4, 32, 32, 256, 1024).eval()
+    with torch.no_grad(), pytest.raises(RuntimeError, match="only d_model=512"):
+        enc(torch.zeros(1, 4, 512), [4])
+
+
+def test_training_mode_is_rejected():
+    fe = Lipreading().train()
+    with pytest.raises(RuntimeError, match="training-mode"):
+        fe(torch.zeros(1, 1, 2, 88, 88))

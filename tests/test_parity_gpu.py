@@ -1,0 +1,251 @@
+"""GPU parity tests (run with -m gpu on a B200): the libsblk path, called through the drop-in modules and
+the C ABI, against (1) the golden outputs of the reference itself, (2) the CPU oracle on seeded inputs at
+small sizes, and (3) size-independent properties at the BASELINE config sizes.
+
+Tolerance (BASELINE.json north_star): encoder outputs within 1e-2 relative error (bf16 operands, fp32
+accumulation) — measured as relative Frobenius error; features of the frontend get the same bar.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-2
+
+
+def rel_fro(a, b):
+    a = torch.as_tensor(a).float().cpu()
+    b = torch.as_tensor(b).float().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert torch.isfinite(a).all()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    assert ops.init() > 0
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def frontend(dev):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading
+    m = Lipreading()
+    m.load_state_dict(synth.frontend_state_dict(1))
+    m.always_on_dropout = False
+    return m.to(dev).eval()
+
+
+@pytest.fixture(scope="module")
+def encoder6(dev):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    m = Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+    m.load_state_dict(synth.encoder_state_dict(2, 6))
+    return m.to(dev).eval()
+
+
+# ------------------------------------------------------------------ golden vectors (reference outputs)
+def test_golden_frontend_config1(frontend, dev, golden):
+    """BASELINE config 1: one 29x88x88 clip, Conv3d frontend + ResNet-18 trunk."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(1, 29, seed=7).to(dev)
+    with torch.no_grad():
+        feat = frontend._frontend_forward(x)
+        out = frontend(x)
+    assert out.shape == (1, 29, 512) and out.dtype == torch.float32
+    assert rel_fro(feat, golden["frontend_c1"]) < REL_TOL
+
+
+def test_golden_frontend_zero_padded_frames(frontend, dev, golden):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(2, 6, seed=8, pad_frames=1).to(dev)
+    with torch.no_grad():
+        assert rel_fro(frontend._frontend_forward(x), golden["frontend_N2_T6_pad1"]) < REL_TOL
+
+
+def test_golden_stem(frontend, dev, golden):
+    """Conv3d + BN + ReLU + MaxPool3d kernel alone vs the reference's frontend3D output."""
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    x = synth.synthetic_clips(1, 2, seed=11).to(dev)
+    pk = frontend._get_packed()
+    out = ops.conv3d_bn_relu_pool(ops.prep_clip(x), pk.c3w, pk.c3b)            # [F,22,22,64] NHWC
+    ref = torch.from_numpy(golden["frontend3d_T2"])[0].permute(1, 2, 3, 0)     # [64,T,22,22] -> [T,22,22,64]
+    assert rel_fro(out, ref) < REL_TOL
+
+
+def test_golden_encoder(encoder6, dev, golden, golden_inputs):
+    with torch.no_grad():
+        out = encoder6(torch.from_numpy(golden_inputs["xin"]).to(dev), [29])
+        assert isinstance(out, tuple) and len(out) == 1
+        assert rel_fro(out[0], golden["encoder6_N1_T29"]) < REL_TOL
+        out40, = encoder6(torch.from_numpy(golden_inputs["xin40"]).to(dev), [40])
+        assert rel_fro(out40, golden["encoder6_N1_T40"]) < REL_TOL
+
+
+def test_golden_encoder_three_layers(dev, golden, golden_inputs):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    enc3 = Encoder(512, 3, 8, 64, 64, 512, 2048)
+    enc3.load_state_dict(synth.encoder_state_dict(3, 3))
+    enc3 = enc3.to(dev).eval()
+    with torch.no_grad():
+        out, = enc3(torch.from_numpy(golden_inputs["xin3"]).to(dev), [31, 31])
+    assert rel_fro(out, golden["encoder3_N2_T31"]) < REL_TOL
+
+
+def test_golden_encoder_ragged_lengths_and_attns(encoder6, dev, golden, golden_inputs):
+    with torch.no_grad():
+        out, attns = encoder6(torch.from_numpy(golden_inputs["xin_r"]).to(dev), [12, 7, 1], return_attns=True)
+    assert rel_fro(out, golden["encoder6_ragged_out"]) < REL_TOL
+    assert len(attns) == 6 and attns[0].shape == (24, 12, 12)
+    assert rel_fro(attns[0], golden["encoder6_ragged_attn0"]) < REL_TOL
+    assert rel_fro(attns[5], golden["encoder6_ragged_attn5"]) < REL_TOL
+    assert float(out[1, 7:].abs().max()) == 0.0 and float(out[2, 1:].abs().max()) == 0.0
+
+
+def test_golden_whole_hot_path(frontend, encoder6, dev, golden):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(2, 6, seed=8, pad_frames=1).to(dev)
+    with torch.no_grad():
+        feat = frontend(x)
+        out, = encoder6(feat, [6, 6])
+    assert rel_fro(out, golden["visual_encoder_N2_T6"]) < REL_TOL
+
+
+# ------------------------------------------------------------------ oracle on seeded inputs
+@pytest.mark.parametrize("n,t", [(1, 1), (1, 5), (3, 7), (2, 29), (1, 40)])
+def test_oracle_whole_path(frontend, encoder6, dev, n, t):
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    sd = {}
+    sd.update(synth.frontend_state_dict(1, prefix="visual_frontend."))
+    sd.update(synth.encoder_state_dict(2, 6, prefix="encoder."))
+    x = synth.synthetic_clips(n, t, seed=100 + n * 50 + t)
+    with torch.no_grad():
+        ref_feat = O.lipreading_forward(x, sd, "visual_frontend.")
+        ref = O.visual_encoder_forward(x, sd)
+        feat = frontend(x.to(dev))
+        out, = encoder6(feat, [t] * n)
+    assert rel_fro(feat, ref_feat) < REL_TOL
+    assert rel_fro(out, ref) < REL_TOL
+
+
+def test_oracle_basic_block_chain(frontend, dev):
+    """Every ResNet stage boundary against the oracle (catches a wrong layer that later layers would blur)."""
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    sd = synth.frontend_state_dict(1)
+    x = synth.synthetic_clips(1, 3, seed=5)
+    with torch.no_grad():
+        y = O.frontend3d(x, sd).transpose(1, 2).contiguous().view(-1, 64, 22, 22)
+        pk = frontend._get_packed()
+        a = ops.conv3d_bn_relu_pool(ops.prep_clip(x.to(dev)), pk.c3w, pk.c3b)
+        assert rel_fro(a.permute(0, 3, 1, 2), y) < REL_TOL
+        bi = 0
+        for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
+            for b in range(2):
+                y = O.basic_block(y, sd, f"resnet18.layer{li}.{b}", stride if b == 0 else 1, b == 0 and li != 1)
+                (st, w1, b1, w2, b2, ds) = pk.blocks[bi]
+                h = ops.conv2d(a, w1, b1, stride=st, relu=True)
+                res = a if ds is None else ops.conv2d(a, ds[0], ds[1], stride=st, relu=False)
+                a = ops.conv2d(h, w2, b2, stride=1, relu=True, residual=res)
+                assert rel_fro(a.permute(0, 3, 1, 2), y) < REL_TOL, f"layer{li}.{b}"
+                bi += 1
+
+
+# ------------------------------------------------------------------ edge cases and error behaviour
+def test_dropout_always_on_like_reference(dev):
+    """Reference quirk (video_frontend.py:122): dropout(0.5) is active in eval mode; same torch RNG call."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading
+    m = Lipreading()
+    m.load_state_dict(synth.frontend_state_dict(1))
+    m = m.to(dev).eval()
+    x = synth.synthetic_clips(1, 4, seed=9).to(dev)
+    with torch.no_grad():
+        torch.manual_seed(3)
+        a = m(x)
+        torch.manual_seed(3)
+        b = m(x)
+        c = m(x)
+        feat = m._frontend_forward(x)
+        torch.manual_seed(3)
+        expect = torch.nn.functional.dropout(feat, p=0.5).view(1, 4, 512)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert torch.equal(a, expect)
+    zeros = (a == 0).float().mean().item()
+    assert 0.4 < zeros < 0.7
+
+
+def test_state_dict_reload_invalidates_packed_weights(dev):
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    enc = Encoder(512, 1, 8, 64, 64, 512, 2048)
+    enc.load_state_dict(synth.encoder_state_dict(5, 1))
+    enc = enc.to(dev).eval()
+    x = torch.randn(2, 9, 512, device=dev)
+    with torch.no_grad():
+        a, = enc(x, [9, 9])
+        enc.load_state_dict(synth.encoder_state_dict(6, 1))
+        b, = enc(x, [9, 9])
+        enc.load_state_dict(synth.encoder_state_dict(5, 1))
+        c, = enc(x, [9, 9])
+    assert not torch.allclose(a, b) and torch.equal(a, c)
+
+
+def test_c_abi_rejects_bad_arguments(dev):
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.gemm(torch.zeros(8, 48, dtype=torch.bfloat16, device=dev),
+                 torch.zeros(64, 48, dtype=torch.bfloat16, device=dev), out_f32=True)
+    with pytest.raises(RuntimeError, match="only 512"):
+        ops.add_layernorm(torch.zeros(4, 256, device=dev), torch.ones(256, device=dev), torch.zeros(256, device=dev))
+    with pytest.raises(RuntimeError, match="T=200"):
+        ops.attention(torch.zeros(200, 1536, dtype=torch.bfloat16, device=dev), 1, 200, 8)
+    with pytest.raises(RuntimeError, match="expected dtype"):
+        ops.conv2d(torch.zeros(1, 22, 22, 64, device=dev), torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device=dev),
+                   torch.zeros(64, device=dev))
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+def test_config2_batch_independence_and_determinism(frontend, encoder6, dev):
+    """Config 2 (32 x 29 x 88 x 88): clips are independent in eval mode, so clip i of the
+    batch-32 run must equal the same clip run alone; and two runs must be bit-identical."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(32, 29, seed=7).to(dev)
+    with torch.no_grad():
+        out, = encoder6(frontend(x), [29] * 32)
+        out2, = encoder6(frontend(x), [29] * 32)
+        single, = encoder6(frontend(x[5:6].contiguous()), [29])
+        part, = encoder6(frontend(x[16:].contiguous()), [29] * 16)
+    assert out.shape == (32, 29, 512)
+    assert torch.equal(out, out2)
+    assert rel_fro(out[5:6], single) < 1e-6
+    assert rel_fro(out[16:], part) < 1e-6
+
+
+def test_config2_linearity_of_conv_stage(frontend, dev):
+    """conv(a*x) = a*conv(x) for a power-of-two a (exact in bf16/fp32 without bias/ReLU clipping):
+    checks the implicit GEMM at the full layer-1 size M = 928*22*22."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(928, 22, 22, 64, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(64, 3, 3, 64, generator=g) / 24).to(torch.bfloat16).to(dev)
+    zero = torch.zeros(64, device=dev)
+    a = ops.conv2d(x, w, zero, relu=False)
+    b = ops.conv2d(x * 4, w, zero, relu=False)
+    assert torch.equal(a.float() * 4, b.float())
+    # spot-check 4096 random outputs against an fp64 dot product
+    idx = torch.randint(0, 928 * 22 * 22, (4096,), generator=g)
+    f, yy, xx = idx // 484, (idx % 484) // 22, idx % 22
+    xp = torch.nn.functional.pad(x.float().cpu(), (0, 0, 1, 1, 1, 1))
+    patches = torch.stack([xp[f, yy + r, xx + s] for r in range(3) for s in range(3)], dim=1)  # [4096,9,64]
+    ref = torch.einsum("ptc,otc->po", patches.double(), w.float().cpu().reshape(64, 9, 64).double())
+    got = a.reshape(-1, 64)[idx.to(dev)].float().cpu().double()
+    assert ((got - ref).norm() / ref.norm()).item() < 5e-3

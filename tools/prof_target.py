@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Small fixed workloads for ncu: python tools/prof_target.py <conv3d|l1conv|l4conv|forward> [iters]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from sbl_for_multilingual_lip_reading_b200 import ops, synth
+
+dev = "cuda"
+what = sys.argv[1]
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+ops.init()
+g = torch.Generator().manual_seed(0)
+bf = torch.bfloat16
+if what == "conv3d":
+    w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / 16).to(dev)
+    one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    wp, b = ops.pack_conv3d(w3, one, zero, zero, one)
+    x = synth.synthetic_clips(32, 29, seed=7).to(dev)
+    xp = ops.prep_clip(x)
+    out = torch.empty(928, 22, 22, 64, dtype=bf, device=dev)
+    for _ in range(iters):
+        ops.conv3d_bn_relu_pool(xp, wp, b, out=out)
+elif what in ("l1conv", "l2conv", "l3conv", "l4conv"):
+    H, C = {"l1conv": (22, 64), "l2conv": (11, 128), "l3conv": (6, 256), "l4conv": (3, 512)}[what]
+    x = torch.randn(928, H, H, C, generator=g).to(bf).to(dev)
+    w = (torch.randn(C, 3, 3, C, generator=g) / (9 * C) ** 0.5).to(bf).to(dev)
+    bias = torch.zeros(C, device=dev)
+    out = torch.empty(928, H, H, C, dtype=bf, device=dev)
+    for _ in range(iters):
+        ops.conv2d(x, w, bias, relu=True, residual=x, out=out)
+torch.cuda.synchronize()
+print("done", what)
