@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — visual-encoder clips/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus 1 --steps K --warmup W            # this repo's sm_100a path (libsblk)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+  torchrun --nproc-per-node N ... bench.py --gpus N ...    # one rank per GPU, clip batch sharded (weak scaling)
+
+A step = one forward of the hot path (Conv3d frontend -> ResNet-18 trunk -> 6-layer transformer Encoder,
+always-on dropout included, exactly what `Transformer.forward` runs before the decoder,
+SBL_Multilingual_Lip_reading/transformer/transformer.py:34-38) over one synthetic LRW-shaped batch
+(BASELINE.json configs[1]: 32 clips x 29 frames x 88 x 88 per GPU).
+
+  value   device-timed (CUDA events on the launching stream), inputs resident in HBM, L2 flushed between steps
+  e2e     same metric through the host-facing call: pinned host fp32 clips in, H2D + forward + D2H of the encoder
+          output every step (double-buffered), wall clock bracketed by synchronize
+  roofline        dominant kernel: algorithmic FLOPs per launch / CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline    the CPU oracle (port of the reference algorithm; same torch primitives) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "visual_encoder_clips_per_sec"
+UNIT = "clips/s"
+FALLBACK_PEAKS = {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0}
+
+
+def flops_per_clip(t, layers):
+    """SURVEY.md §8d / BASELINE.md §3: 2*MACs of Conv3d + 20 ResNet convs + linear_in + per-layer linears + bmm."""
+    return t * (60712960 + 571604992 + 524288 + layers * 6291456) + layers * 2048 * t * t
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            if "bf16_tflops" in d and "hbm_gbs" in d:
+                d["_source"] = "measured"
+                return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons through NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self.nv is not None:
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (port of the reference algorithm) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_setup(layers):
+    import torch
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {}
+    sd.update(synth.frontend_state_dict(1, prefix="visual_frontend."))
+    sd.update(synth.encoder_state_dict(2, layers, prefix="encoder."))
+    return O, sd, cores
+
+
+def cpu_oracle_step(O, sd, x):
+    import torch
+    with torch.no_grad():
+        gen = torch.Generator().manual_seed(0)
+        n, t = x.shape[0], x.shape[2]
+        mask = (torch.rand((n * t, 512), generator=gen) >= 0.5).float() * 2.0  # always-on dropout(0.5), x2 scaling
+        return O.visual_encoder_forward(x, sd, dropout_mask=mask)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    O, sd, cores = cpu_oracle_setup(args.layers)
+    sample = args.ref_clips if args.ref_clips > 0 else (4 if args.steps <= 100 else 2 if args.steps <= 300 else 1)
+    x = synth.synthetic_clips(sample, args.frames, seed=7)
+    for _ in range(max(args.warmup, 1)):
+        cpu_oracle_step(O, sd, x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_step(O, sd, x)
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    desc = f"{sample} clips x {args.frames} frames per step (bounded sample of the {args.batch}-clip batch)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, world):
+    return {
+        "workload": (f"BASELINE configs[1]: full visual encoder forward (Conv3d frontend + ResNet-18 trunk + "
+                     f"{args.layers}-layer transformer Encoder), LRW-shaped {args.frames}x88x88 gray clips, "
+                     f"batch {args.batch} per B200"),
+        "clips_per_gpu": args.batch, "frames": args.frames, "encoder_layers": args.layers,
+        "global_batch": args.batch * world, "parallelism": f"dp{world}",
+        "l2": "L2 flushed (256 MiB write) between timed steps; e2e inputs stream from pinned host memory",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    from sbl_for_multilingual_lip_reading_b200.runner import VisualEncoderPlan
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import visual_frontend
+
+    ops.init()
+    B, T, L = args.batch, args.frames, args.layers
+    fe = visual_frontend(None)
+    fe.load_state_dict(synth.frontend_state_dict(1))
+    enc = Encoder(512, L, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+    enc.load_state_dict(synth.encoder_state_dict(2, L))
+    fe, enc = fe.to(dev).eval(), enc.to(dev).eval()
+    torch.manual_seed(1234 + rank)
+
+    plan = VisualEncoderPlan(fe, enc, B, T, device=dev, slots=2, pdl=not args.no_pdl)
+
+    # synthetic inputs: a pool of distinct batches (host pinned for e2e; device copies for the device-timed run)
+    pool_n = 4
+    host_pool = [synth.synthetic_clips(B, T, seed=100 + 17 * rank + i).pin_memory() for i in range(pool_n)]
+    dev_pool = [h.to(dev) for h in host_pool]
+    out_host = [torch.empty((B, T, 512), dtype=torch.float32).pin_memory() for _ in range(2)]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world * B, T, 512), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def one_device_step(i, timed):
+        """inputs already in HBM; L2 flushed before the timed part; returns (start, end) events."""
+        s = i % plan.slots
+        with torch.cuda.stream(plan.compute):
+            plan.x[s].copy_(dev_pool[i % pool_n])
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(plan.compute)
+            plan.graphs[s].replay()
+            if gathered is not None:
+                # output gathering (the DataParallel `gather` of the reference, train.py:115) over NCCL/NVLink
+                dist.all_gather_into_tensor(gathered, plan.out[s])
+            e1.record(plan.compute)
+        return e0, e1
+
+    sampler = ClockSampler(local_rank)
+
+    # ---- device-timed run -------------------------------------------------------------------
+    for i in range(args.warmup):
+        one_device_step(i, False)
+    barrier()
+    sampler.start()
+    evs = [one_device_step(args.warmup + i, True) for i in range(args.steps)]
+    barrier()
+    sampler.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = world * B * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end run (host buffers, H2D + D2H inside the timed region) --------------------
+    def e2e_steps(k):
+        for i in range(k):
+            plan.submit_host(host_pool[i % pool_n], out_host[i % 2])
+        plan.synchronize()
+
+    e2e_steps(max(args.warmup, 3))
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    e2e_steps(args.steps)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    sampler.stop()
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+    checksum = float(out_host[(args.steps - 1) % 2].double().abs().mean())  # the D2H result is really read
+
+    # ---- per-kernel roofline (rank 0): eager traced passes, PDL off so every launch is timed alone --------
+    line_extra = {}
+    if rank == 0:
+        peaks = load_peaks()
+        prev_pdl = ops.set_pdl(False)
+        agg = {}
+        passes = 5
+        with torch.no_grad():
+            for rep in range(passes + 1):
+                sink = []
+                flush.zero_()
+                with ops.trace(sink):
+                    out, = enc(fe(dev_pool[rep % pool_n]), [T] * B)
+                torch.cuda.synchronize(dev)
+                if rep == 0:
+                    continue  # warm-up pass
+                for r in sink:
+                    key = (r["name"], r["tag"])
+                    a = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": r["flops"], "bytes": r["bytes"]})
+                    a["ms"] += r["start"].elapsed_time(r["end"])
+                    a["launches"] += 1
+        ops.set_pdl(bool(prev_pdl))
+        total_ms = sum(a["ms"] for a in agg.values()) / passes
+        rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
+        breakdown = []
+        for (name, tag), a in rows[:12]:
+            per = a["ms"] / a["launches"]
+            breakdown.append({"kernel": name, "case": tag, "launches_per_step": a["launches"] // passes,
+                              "avg_us": round(per * 1e3, 2), "share": round(a["ms"] / passes / total_ms, 4),
+                              "tflops": round(a["flops"] / (per * 1e-3) / 1e12, 1) if a["flops"] else None,
+                              "gbs": round(a["bytes"] / (per * 1e-3) / 1e9, 1)})
+        (name, tag), a = rows[0]
+        per_s = a["ms"] / a["launches"] * 1e-3
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                with open(tp) as f:
+                    traffic = json.load(f).get(f"{name}|{tag}")
+            except Exception:
+                traffic = None
+        if a["flops"]:
+            ach, peak = a["flops"] / per_s / 1e12, float(peaks["bf16_tflops"])
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        else:
+            ach, peak = a["bytes"] / per_s / 1e9, float(peaks["hbm_gbs"])
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+        roof.update({"traffic": traffic, "kernel": name, "case": tag, "avg_launch_us": per_s * 1e6,
+                     "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json burst figure: kernel timed alone)"})
+        fpc = flops_per_clip(T, L)
+        path_tf = value / world * fpc / 1e12
+        line_extra["roofline"] = roof
+        line_extra["path"] = {"flops_per_clip": fpc, "achieved_tflops_per_gpu": path_tf,
+                              "frac_of_bf16_peak": path_tf / float(peaks["bf16_tflops"]),
+                              "frac_of_bf16_sustained": path_tf / float(peaks.get("bf16_tflops_sustained",
+                                                                                  peaks["bf16_tflops"])),
+                              "eager_traced_ms_per_step": total_ms}
+        line_extra["breakdown"] = breakdown
+
+        # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample of the same workload --------------
+        if world == 1 and not args.no_cpu_baseline:
+            O, sd, cores = cpu_oracle_setup(L)
+            sample = 4
+            xs = host_pool[0][:sample].clone()
+            cpu_oracle_step(O, sd, xs)
+            reps, t0 = 0, time.perf_counter()
+            while True:
+                cpu_oracle_step(O, sd, xs)
+                reps += 1
+                if time.perf_counter() - t0 > args.cpu_seconds or reps >= 200:
+                    break
+            dt = time.perf_counter() - t0
+            line_extra["cpu_baseline"] = {
+                "value": sample * reps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{reps} forwards of {sample} clips x {T} frames (first {sample} clips of the batch), "
+                          f"oracle/visual_encoder_oracle.py, fp32, torch {torch.__version__} CPU, {dt:.1f} s"}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 88 * 88 * 4,
+                    "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "timing": "wall clock, synchronize on both sides, double-buffered H2D/compute/D2H",
+                    "result_checksum": checksum},
+            "gpu_launches": plan.launches_per_forward * args.steps,
+            "gpu_launches_per_step": plan.launches_per_forward,
+        }
+        line.update(line_extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="clips per GPU (BASELINE configs[1]: 32)")
+    ap.add_argument("--frames", type=int, default=29)
+    ap.add_argument("--layers", type=int, default=6)
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-clips", type=int, default=0, help="clips per reference-arm step (0 = auto)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "b200" and args.gpus != world:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit(f"bench.py --gpus {args.gpus}: launch with torch.distributed.run "
+                             f"--nproc-per-node {args.gpus} (one rank per GPU)")
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -106,10 +106,12 @@ class Encoder(nn.Module):
         self.layer_stack = nn.ModuleList([
             EncoderLayer(d_model, d_inner, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
         self._packed = None
+        self._len_cache = {}
 
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"] = None
+        st["_len_cache"] = {}
         return st
 
     # ------------------------------------------------------------------------------------------
@@ -173,7 +175,13 @@ class Encoder(nn.Module):
             pk = self._get_packed()
             lengths = None
             if any(v < t for v in lens):  # all-keep masks (every reference call site) cost nothing
-                lengths = torch.tensor(lens, dtype=torch.int32, device=x.device)
+                ck = (x.device, tuple(lens))  # staged once per distinct lengths vector (CUDA-graph capturable)
+                lengths = self._len_cache.get(ck)
+                if lengths is None:
+                    if len(self._len_cache) > 64:
+                        self._len_cache.clear()
+                    lengths = torch.tensor(lens, dtype=torch.int32, device=x.device)
+                    self._len_cache[ck] = lengths
             pe = self.positional_encoding.pe[0]
             attns = []
             x16 = ops.cast_bf16(x)

@@ -32,6 +32,41 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name}: expected a contiguous tensor")
 
 
+# Optional per-launch trace (bench.py / profiling): when a list is installed with `trace(list)`, every wrapper
+# brackets its launch with CUDA events on the launching stream and appends
+# {"name", "tag", "flops", "bytes", "start", "end"}; algorithmic flops/bytes are the figures DESIGN.md states.
+_TRACE = None
+
+
+class trace:
+    def __init__(self, sink):
+        self.sink = sink
+
+    def __enter__(self):
+        global _TRACE
+        self._prev, _TRACE = _TRACE, self.sink
+        return self.sink
+
+    def __exit__(self, *exc):
+        global _TRACE
+        _TRACE = self._prev
+        return False
+
+
+def _call(name, tag, flops, nbytes, *args):
+    fn = getattr(_lib.load(), name)
+    tr = _TRACE
+    if tr is None:
+        _lib.check(fn(*args), name)
+        return
+    s = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(s)
+    _lib.check(fn(*args), name)
+    e1.record(s)
+    tr.append(dict(name=name, tag=tag, flops=flops, bytes=nbytes, start=e0, end=e1))
+
+
 def init() -> int:
     """Per-device setup; returns the SM count."""
     n = _lib.load().sblk_init()
@@ -56,8 +91,8 @@ def pack_conv3d(w, gamma, beta, mean, var, eps=1e-5):
         raise RuntimeError(f"pack_conv3d: weight shape {tuple(w.shape)} != (64,1,5,7,7)")
     wp = torch.empty((64, 320), dtype=BF16, device=w.device)
     bias = torch.empty((64,), dtype=F32, device=w.device)
-    _lib.check(_lib.load().sblk_pack_conv3d(_p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
-                                            _stream()), "sblk_pack_conv3d")
+    _call("sblk_pack_conv3d", "pack", 0, 0, _p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
+          _stream())
     return wp, bias
 
 
@@ -68,8 +103,8 @@ def pack_conv2d(w, gamma=None, beta=None, mean=None, var=None, eps=1e-5):
     co, ci, r, s = w.shape
     wp = torch.empty((co, r, s, ci), dtype=BF16, device=w.device)
     bias = torch.empty((co,), dtype=F32, device=w.device)
-    _lib.check(_lib.load().sblk_pack_conv2d(_p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
-                                            co, ci, r, s, _stream()), "sblk_pack_conv2d")
+    _call("sblk_pack_conv2d", "pack", 0, 0, _p(w), _p(gamma), _p(beta), _p(mean), _p(var), eps, _p(wp), _p(bias),
+          co, ci, r, s, _stream())
     return wp, bias
 
 
@@ -78,7 +113,7 @@ def cast_bf16(x, out=None):
     if out is None:
         out = torch.empty(x.shape, dtype=BF16, device=x.device)
     _req(out, BF16, "out")
-    _lib.check(_lib.load().sblk_cast_f32_bf16(_p(x), _p(out), x.numel(), _stream()), "sblk_cast_f32_bf16")
+    _call("sblk_cast_f32_bf16", f"cast n={x.numel()}", 0, 6 * x.numel(), _p(x), _p(out), x.numel(), _stream())
     return out
 
 
@@ -97,7 +132,7 @@ def prep_clip(x, out=None):
     if out is None:
         out = torch.empty((n, t + 4, 94, 96), dtype=BF16, device=x.device)
     _req(out, BF16, "out")
-    _lib.check(_lib.load().sblk_prep_clip(_p(x), _p(out), n, t, _stream()), "sblk_prep_clip")
+    _call("sblk_prep_clip", f"prep N={n} T={t}", 0, 4 * x.numel() + 2 * out.numel(), _p(x), _p(out), n, t, _stream())
     return out
 
 
@@ -109,8 +144,8 @@ def conv3d_bn_relu_pool(xp, wp, bias, out=None):
     if out is None:
         out = torch.empty((n * t, 22, 22, 64), dtype=BF16, device=xp.device)
     _req(out, BF16, "out")
-    _lib.check(_lib.load().sblk_conv3d_bn_relu_pool_fwd(_p(xp), _p(wp), _p(bias), _p(out), n, t, _stream()),
-               "sblk_conv3d_bn_relu_pool_fwd")
+    _call("sblk_conv3d_bn_relu_pool_fwd", f"conv3d N={n} T={t}", 2 * 64 * 44 * 44 * 245 * n * t,
+          2 * xp.numel() + 2 * out.numel(), _p(xp), _p(wp), _p(bias), _p(out), n, t, _stream())
     return out
 
 
@@ -129,9 +164,10 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     _req(out, BF16, "out")
     if residual is not None and residual.numel() != out.numel():
         raise RuntimeError("conv2d: residual shape mismatch")
-    _lib.check(_lib.load().sblk_conv2d_igemm_fwd(_p(x), _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout,
-                                                 r, s, stride, pad, 1 if relu else 0, _stream()),
-               "sblk_conv2d_igemm_fwd")
+    _call("sblk_conv2d_igemm_fwd", f"conv{r}x{s} H={h} {cin}->{cout} s{stride}", 2 * f * p * q * cout * r * s * cin,
+          2 * (x.numel() + wp.numel() + out.numel() + (0 if residual is None else residual.numel())),
+          _p(x), _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout, r, s, stride, pad, 1 if relu else 0,
+          _stream())
     return out
 
 
@@ -141,7 +177,8 @@ def avgpool(x, want_f32=True, want_bf16=False):
     hw = x.numel() // (f * c)
     o32 = torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None
     o16 = torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None
-    _lib.check(_lib.load().sblk_avgpool_fwd(_p(x), _p(o32), _p(o16), f, hw, c, _stream()), "sblk_avgpool_fwd")
+    _call("sblk_avgpool_fwd", f"avgpool HW={hw} C={c}", 0, 2 * x.numel() + (4 if want_f32 else 0) * f * c +
+          (2 if want_bf16 else 0) * f * c, _p(x), _p(o32), _p(o16), f, hw, c, _stream())
     return o32, o16
 
 
@@ -155,8 +192,9 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_bf16=False, out_f32=Fal
         raise RuntimeError(f"gemm: K mismatch {k} vs {k2}")
     o16 = torch.empty((m, n), dtype=BF16, device=a.device) if out_bf16 else None
     o32 = torch.empty((m, n), dtype=F32, device=a.device) if out_f32 else None
-    _lib.check(_lib.load().sblk_gemm_fwd(_p(a), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), m, n, k,
-                                         1 if relu else 0, _stream()), "sblk_gemm_fwd")
+    _call("sblk_gemm_fwd", f"gemm N={n} K={k}", 2 * m * n * k,
+          2 * (m * k + n * k) + m * n * ((2 if out_bf16 else 0) + (4 if out_f32 else 0)),
+          _p(a), _p(w), _p(bias), _p(residual), _p(o16), _p(o32), m, n, k, 1 if relu else 0, _stream())
     return o16, o32
 
 
@@ -167,9 +205,9 @@ def add_layernorm(x, gamma, beta, residual=None, pe=None, lengths=None, T=1, eps
     m, d = x.shape
     o32 = torch.empty((m, d), dtype=F32, device=x.device) if want_f32 else None
     o16 = torch.empty((m, d), dtype=BF16, device=x.device) if want_bf16 else None
-    _lib.check(_lib.load().sblk_add_layernorm_fwd(_p(x), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths),
-                                                  _p(o32), _p(o16), m, T, d, eps, _stream()),
-               "sblk_add_layernorm_fwd")
+    _call("sblk_add_layernorm_fwd", "add_layernorm", 0,
+          m * d * (4 + (4 if residual is not None else 0) + (4 if want_f32 else 0) + (2 if want_bf16 else 0)),
+          _p(x), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths), _p(o32), _p(o16), m, T, d, eps, _stream())
     return o32, o16
 
 
@@ -181,6 +219,6 @@ def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
     probs = torch.empty((h * n, t, t), dtype=F32, device=qkv.device) if want_probs else None
     if scale is None:
         scale = 1.0 / (d_k ** 0.5)
-    _lib.check(_lib.load().sblk_attention_fwd(_p(qkv), _p(out), _p(probs), _p(lengths), n, t, h, d_k, scale,
-                                              _stream()), "sblk_attention_fwd")
+    _call("sblk_attention_fwd", f"attention T={t}", 4 * n * h * t * t * d_k, 2 * qkv.numel() + 2 * out.numel(),
+          _p(qkv), _p(out), _p(probs), _p(lengths), n, t, h, d_k, scale, _stream())
     return out, probs

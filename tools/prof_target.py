@@ -30,5 +30,20 @@ elif what in ("l1conv", "l2conv", "l3conv", "l4conv"):
     out = torch.empty(928, H, H, C, dtype=bf, device=dev)
     for _ in range(iters):
         ops.conv2d(x, w, bias, relu=True, residual=x, out=out)
+if what == "forward":
+    # whole hot path, eager (one launch per kernel), BASELINE configs[1] shape: 32 clips x 29 frames
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import visual_frontend
+    fe = visual_frontend(None)
+    fe.load_state_dict(synth.frontend_state_dict(1))
+    enc = Encoder(512, 6, 8, 64, 64, 512, 2048)
+    enc.load_state_dict(synth.encoder_state_dict(2, 6))
+    fe, enc = fe.to(dev).eval(), enc.to(dev).eval()
+    x = synth.synthetic_clips(32, 29, seed=7).to(dev)
+    with torch.no_grad():
+        for _ in range(iters):
+            out, = enc(fe(x), [29] * 32)
+    torch.cuda.synchronize()
+    print("done forward", float(out.abs().mean()))
 torch.cuda.synchronize()
 print("done", what)
