@@ -32,7 +32,8 @@ int sblk_set_pdl(int enable);
 long long sblk_launch_count(void);
 
 /* ---- packers (one-time, per weight version) ------------------------------------------------------- */
-/* Conv3d(1,64,(5,7,7)) weight [64,1,5,7,7] fp32 + BatchNorm3d(eval) -> bf16 [64][320] + fp32 bias[64].
+/* Conv3d(1,64,(5,7,7)) weight [64,1,5,7,7] fp32 + BatchNorm3d(eval) -> bf16 [64][320] (k = dt*64 + (r/2)*16 +
+ * (r%2)*8 + s, zero elsewhere) + fp32 bias[64].
  * replaces: nn.Conv3d / nn.BatchNorm3d parameters, transformer/video_frontend.py:100-101 */
 int sblk_pack_conv3d(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,
                      float eps, void* w_packed_bf16, float* bias, void* stream);
@@ -45,8 +46,12 @@ int sblk_pack_conv2d(const float* w, const float* gamma, const float* beta, cons
 int sblk_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
 
 /* ---- visual frontend ------------------------------------------------------------------------------ */
-/* x fp32 [N,1,T,88,88] -> bf16 [N,T+4,94,96], zero temporal (2) and spatial (3) borders.
- * replaces: the implicit zero padding of nn.Conv3d(padding=(2,3,3)), transformer/video_frontend.py:100 */
+/* Number of bf16 elements the prepped clip of sblk_prep_clip needs (includes the over-read slack). */
+long long sblk_prep_clip_elems(int N, int T);
+/* x fp32 [N,1,T,88,88] -> bf16 row-Toeplitz entries [N][T+4][2][47][44][8] (zero temporal (2) and spatial (3)
+ * borders materialised; entry (pl,yy,x) = the 8 input pixels 2x-3.. of padded row 2yy+pl).
+ * replaces: the implicit zero padding / stride-2 window walk of nn.Conv3d(stride=(1,2,2), padding=(2,3,3)),
+ * transformer/video_frontend.py:100 */
 int sblk_prep_clip(const float* x, void* x_prepped_bf16, int N, int T, void* stream);
 /* Conv3d + BN3d(eval) + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) + transpose(1,2).contiguous().view:
  * prepped clip -> bf16 NHWC [N*T,22,22,64].

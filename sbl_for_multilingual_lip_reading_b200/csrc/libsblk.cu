@@ -254,16 +254,21 @@ int sblk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
                 static_cast<__nv_bfloat16*>(dst), n / 4);
 }
 
+long long sblk_prep_clip_elems(int N, int T) {
+  using namespace sblk::c3d;
+  if (N <= 0 || T <= 0) return -1;
+  return (static_cast<long long>(N) * (T + 2 * TPAD) * FRAME_ENTRIES + TAIL_PAD_ENTRIES) * 8;
+}
+
 int sblk_prep_clip(const float* x, void* out, int N, int T, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !out) return fail(-1, "sblk_prep_clip: null pointer");
   if (N <= 0 || T <= 0) return fail(-1, "sblk_prep_clip: bad shape N=%d T=%d", N, T);
   if (!aligned16(out)) return fail(-1, "sblk_prep_clip: output must be 16-byte aligned");
-  const long long items = static_cast<long long>(N) * (T + 2 * sblk::c3d::TPAD) * sblk::c3d::HP * (sblk::c3d::WP / 8);
+  const long long items = static_cast<long long>(N) * (T + 2 * sblk::c3d::TPAD) * sblk::c3d::FRAME_ENTRIES;
   return launch(sblk::prep_clip_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "prep_clip_kernel", x, static_cast<__nv_bfloat16*>(out), N,
-                T);
+                static_cast<cudaStream_t>(stream), false, "prep_clip_kernel", x, static_cast<uint4*>(out), N, T);
 }
 
 int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bias, void* out, int N, int T,
@@ -275,14 +280,7 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   if (N <= 0 || T <= 0) return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: bad shape N=%d T=%d", N, T);
   if (!aligned16(xp) || !aligned16(wp) || !aligned16(out))
     return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: pointers must be 16-byte aligned");
-  CUtensorMap tmX, tmW;
-  {
-    cuuint64_t dims[3] = {static_cast<cuuint64_t>(WP), static_cast<cuuint64_t>(HP),
-                          static_cast<cuuint64_t>(N) * (T + 2 * TPAD)};
-    cuuint64_t strides[2] = {static_cast<cuuint64_t>(WP) * 2, static_cast<cuuint64_t>(WP) * HP * 2};
-    cuuint32_t box[3] = {WP, PATCH_ROWS, PATCH_FRAMES};
-    if ((rc = encode_tiled(&tmX, xp, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-  }
+  CUtensorMap tmW;
   {
     cuuint64_t dims[2] = {KPAD, COUT};
     cuuint64_t strides[1] = {KPAD * 2};
@@ -292,12 +290,13 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   sblk::Conv3dParams p;
   p.frames = N * T;
   p.T = T;
+  p.x8 = static_cast<const uint4*>(xp);
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
   const int units = p.frames * 2;
   const int grid = units < sms ? units : sms;
   return launch(sblk::conv3d_bn_relu_pool_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES,
-                static_cast<cudaStream_t>(stream), true, "conv3d_bn_relu_pool_kernel", tmX, tmW, p);
+                static_cast<cudaStream_t>(stream), true, "conv3d_bn_relu_pool_kernel", tmW, p);
 }
 
 int sblk_conv2d_igemm_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,

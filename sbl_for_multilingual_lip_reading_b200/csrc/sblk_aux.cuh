@@ -8,27 +8,30 @@
 namespace sblk {
 
 // --------------------------------------------------------------------------------------------
-// Clip prep: x fp32 [N,1,T,88,88] -> bf16 [N, T+4, 94, 96] with zero borders (2 frames each side in
-// time = Conv3d temporal padding; 3 px spatial padding).  Lets the Conv3d loader fetch its 5x51x96
-// patch with ONE un-predicated TMA.  Reference: input layout of Lipreading.forward,
-// SBL/transformer/video_frontend.py:119-121 (+ Conv3d padding=(2,3,3), :100).
-// One thread per 8 output pixels (16-B store).
+// Clip prep: x fp32 [N,1,T,88,88] -> row-Toeplitz bf16 entries X8[N][T+4][2][47][44][8] (layout: sblk_conv3d.cuh):
+//   X8[n][tp][pl][yy][x][j] = xpad[n][tp - 2][2*yy + pl - 3][2*x + j - 3]   (zero outside the clip)
+// i.e. the Conv3d zero padding (2 frames, 3 px) is materialised and every 16-byte entry already holds the 8
+// consecutive input pixels one (dt, r) filter row multiplies for conv pixel x, so the stem kernel streams its A
+// operand with plain bulk copies.  Reference: input layout of Lipreading.forward, SBL/transformer/video_frontend.py:
+// 119-121 (+ Conv3d padding=(2,3,3), stride (1,2,2), :100).  One thread per entry (16-B store).
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-prep_clip_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int T) {
+prep_clip_kernel(const float* __restrict__ x, uint4* __restrict__ out, int N, int T) {
   using namespace c3d;
   const int TP = T + 2 * TPAD;
-  const long long total = static_cast<long long>(N) * TP * HP * (WP / 8);
+  const long long total = static_cast<long long>(N) * TP * FRAME_ENTRIES;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cx = static_cast<int>(i % (WP / 8));
-    long long r = i / (WP / 8);
-    const int py = static_cast<int>(r % HP);
-    r /= HP;
+    const int cx = static_cast<int>(i % CONV_HW);
+    long long r = i / CONV_HW;
+    const int yy = static_cast<int>(r % PLANE_ROWS);
+    r /= PLANE_ROWS;
+    const int pl = static_cast<int>(r & 1);
+    r >>= 1;
     const int tp = static_cast<int>(r % TP);
     const int n = static_cast<int>(r / TP);
     const int t = tp - TPAD;
-    const int y = py - 3;
+    const int y = 2 * yy + pl - 3;
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.0f;
@@ -36,7 +39,7 @@ prep_clip_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
       const float* src = x + ((static_cast<long long>(n) * T + t) * IN_HW + y) * IN_HW;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int xx = cx * 8 + e - 3;
+        const int xx = cx * 2 + e - 3;
         if (xx >= 0 && xx < IN_HW) v[e] = __ldg(src + xx);
       }
     }
@@ -45,7 +48,7 @@ prep_clip_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
     o.y = pack_bf16x2(v[2], v[3]);
     o.z = pack_bf16x2(v[4], v[5]);
     o.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(out)[i] = o;
+    out[i] = o;
   }
 }
 
@@ -75,7 +78,8 @@ pack_conv2d_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
   }
 }
 
-// Conv3d stem weight fp32 [64,1,5,7,7] -> bf16 [64][320]: k = (dt*7 + r)*8 + s, s == 7 and k >= 280 are zero.
+// Conv3d stem weight fp32 [64,1,5,7,7] -> bf16 [64][320] in the MMA order of sblk_conv3d.cuh:
+//   k = dt*64 + q*16 + h*8 + s  with filter row r = 2q + h ; r == 7 and s == 7 are zero.
 __global__ void __launch_bounds__(256)
 pack_conv3d_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ mean, const float* __restrict__ var, float eps,
@@ -86,13 +90,10 @@ pack_conv3d_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
     const int co = i / c3d::KPAD;
     const float scale = gamma[co] / sqrtf(var[co] + eps);
     float v = 0.0f;
+    const int dt = k >> 6;
+    const int r = ((k >> 4) & 3) * 2 + ((k >> 3) & 1);
     const int s = k & 7;
-    const int c = k >> 3;
-    if (c < 35 && s < 7) {
-      const int dt = c / 7;
-      const int r = c - dt * 7;
-      v = w[((co * 5 + dt) * 7 + r) * 7 + s] * scale;
-    }
+    if (r < 7 && s < 7) v = w[((co * 5 + dt) * 7 + r) * 7 + s] * scale;
     wp[i] = __float2bfloat16_rn(v);
     if (k == 0) bias[co] = beta[co] - mean[co] * scale;
   }

@@ -4,15 +4,21 @@
 // Reference: Lipreading.frontend3D + the transpose/contiguous/view that follows it,
 //            SBL/transformer/video_frontend.py:99-104,111-115.
 //
-// Implicit GEMM on tcgen05: M = conv output pixels, N = 64 channels, K = (dt, r, s8) = 5*7*8 = 280 -> 288.
-// Cin = 1, so TMA im2col cannot build the A operand.  Instead one CTA owns a half frame (22/23 conv rows):
-//   * loader thread: ONE 3-D TMA brings the bf16 input patch (5 frames x 51 rows x 96 cols) into smem
-//   * 8 producer warps expand it into SWIZZLE_128B A tiles (128 pixels x 64 K per ring stage); each 16-B
-//     chunk of a row is 8 consecutive input pixels of one (dt, r) filter row — the 8th multiplies a zero weight
-//   * 1 MMA thread: 18 x tcgen05.mma (M128 N64 K16) per 128-pixel tile into a 2-deep TMEM ring
-//   * 4 epilogue warps: TMEM -> +bias, ReLU -> bf16 -> swizzled smem ring of conv pixels, then the 3x3/s2
-//     max-pool is taken straight out of that ring and stored coalesced.  The 7.2 MB/clip un-pooled
-//     activation never reaches HBM.
+// Implicit GEMM on tcgen05 with NO per-CTA operand expansion.  Cin = 1, so TMA im2col cannot build the A operand.
+// Instead prep_clip (sblk_aux.cuh) writes the clip once as a row-Toeplitz array of 16-byte entries
+//     X8[n][tp][pl][yy][x][j] = xpad[n][tp][2*yy + pl][2*x + j],  j = 0..7      (pl = row parity, 47x44 entries/plane)
+// so that the K-chunk (dt, r) of conv pixel m = y*44 + x is the entry at flat index  m + (r>>1)*44  of plane
+// (tp = t + dt, pl = r & 1): the A operand of every (dt, r) is the SAME flat entry array at a shifted start.  A
+// SWIZZLE_NONE K-major UMMA descriptor reads 8 consecutive entries as one core matrix (SBO = 128 B) and takes the
+// second K-chunk of an MMA at an arbitrary byte distance (LBO), so one M128 x N64 x K16 tcgen05.mma consumes the
+// filter rows (r, r+1) = (plane 0, plane 1) straight out of the staged entries.
+//
+// Per CTA (persistent over half frames):
+//   * loader thread: per (group of 4 tiles, dt) two bulk copies (plane 0 / plane 1, 644 entries each) into a 4-stage ring
+//   * MMA thread:    per stage 4 tiles x 4 MMAs (r pairs 01, 23, 45, 6+zero) into 4 TMEM accumulators; 2 accumulator sets
+//   * 8 epilogue warps: TMEM -> +bias, ReLU -> bf16 -> swizzled smem ring of conv pixels, then the 3x3/s2 max-pool is
+//     taken straight out of that ring with 16-byte loads and stored coalesced.  The 7.2 MB/clip un-pooled activation
+//     never reaches HBM.
 #pragma once
 #include "sblk_common.cuh"
 
@@ -20,42 +26,66 @@ namespace sblk {
 
 namespace c3d {
 constexpr int IN_HW = 88;
-constexpr int HP = 94;          // padded rows of the prepped frame (3 + 88 + 3)
-constexpr int WP = 96;          // padded cols (3 + 88 + 5)
-constexpr int TPAD = 2;         // zero frames before/after each clip
+constexpr int TPAD = 2;              // zero frames before/after each clip
 constexpr int CONV_HW = 44;
 constexpr int POOL_HW = 22;
 constexpr int COUT = 64;
-constexpr int KPAD = 320;       // packed weight row length (5 K-blocks of 64); taps live in [0, 288)
-constexpr int PATCH_ROWS = 51;
-constexpr int PATCH_FRAMES = 5;
-constexpr int PATCH_BYTES = PATCH_FRAMES * PATCH_ROWS * WP * 2;  // 48960
+constexpr int PLANE_ROWS = 47;       // (3 + 88 + 3) / 2 row pairs
+constexpr int PLANE_ENTRIES = PLANE_ROWS * CONV_HW;  // 2068 entries of 16 B
+constexpr int FRAME_ENTRIES = 2 * PLANE_ENTRIES;     // two row-parity planes
+constexpr int TAIL_PAD_ENTRIES = 256;                // over-read slack at the very end of X8
+constexpr int KPAD = 320;            // packed weight row: 5 dt x 4 MMAs x 16
+constexpr int TILES_PER_GROUP = 4;
+constexpr int GROUP_PIX = TILES_PER_GROUP * 128;     // 512 conv pixels
+constexpr int HALO_ENTRIES = 3 * CONV_HW;            // filter rows 2..6 reach 1..3 entry-rows further
+constexpr int STAGE_PLANE_ENTRIES = GROUP_PIX + HALO_ENTRIES;   // 644
+constexpr int STAGE_PLANE_BYTES = STAGE_PLANE_ENTRIES * 16;     // 10304
+constexpr int A_STAGE_BYTES = 2 * STAGE_PLANE_BYTES;            // 20608
 constexpr int A_STAGES = 4;
-constexpr int A_STAGE_BYTES = 128 * 128;                          // 128 pixels x 64 bf16
-constexpr int B_BYTES = 5 * COUT * 128;                           // 40960
-constexpr int RING_PIX = 512;
-constexpr int RING_BYTES = RING_PIX * 128;
-constexpr int OFF_A = 0;
-constexpr int OFF_B = OFF_A + A_STAGES * A_STAGE_BYTES;           // 65536
-constexpr int OFF_RING = OFF_B + B_BYTES;                         // 106496
-constexpr int OFF_PATCH = OFF_RING + RING_BYTES;                  // 172032
-constexpr int SMEM_BYTES = OFF_PATCH + PATCH_BYTES + 1024;        // 222016
-constexpr int TILES_PER_UNIT = 8;
-constexpr int NUM_PRODUCERS = 256;
-constexpr int THREADS = 32 * 14;  // loader, mma, 4 epilogue, 8 producer warps
-constexpr int TMEM_COLS = 128;    // 2 accumulator stages x 64 columns
+constexpr int B_BYTES = 5 * COUT * 128;                         // 40960
+constexpr int RING_PIX = 768;
+constexpr int RING_BYTES = RING_PIX * 128;                      // 98304
+constexpr int OFF_B = 0;
+constexpr int OFF_RING = OFF_B + B_BYTES;                       // 40960
+constexpr int OFF_A = OFF_RING + RING_BYTES;                    // 139264
+constexpr int SMEM_BYTES = OFF_A + A_STAGES * A_STAGE_BYTES + 1024;  // 222720
+constexpr int GROUPS_PER_UNIT = 2;   // a half frame = 22/23 conv rows <= 1024 pixels
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int THREADS = 64 + EPI_THREADS;  // loader warp, mma warp, 8 epilogue warps
+constexpr int TMEM_COLS = 512;       // 2 sets x 4 tiles x 64 columns
 }  // namespace c3d
+
+// SWIZZLE_NONE K-major smem descriptor: core matrix = 8 rows x 16 B contiguous; SBO = byte distance between
+// M-adjacent core matrices, LBO = byte distance between the two K-adjacent core matrices of one K16 MMA.
+__device__ __forceinline__ uint64_t make_desc_kmajor_noswizzle(uint32_t smem_addr_bytes, uint32_t lbo_bytes,
+                                                               uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr_bytes & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); layout type 0 = SWIZZLE_NONE
+  return d;
+}
+
+// global -> shared bulk copy (contiguous bytes, multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 struct Conv3dParams {
   int frames;                 // F = N*T
   int T;                      // frames per clip
+  const uint4* x8;            // row-Toeplitz clip [N][T+4][2][47][44] entries of 8 bf16
   const float* bias;          // [64] folded BN shift
   __nv_bfloat16* out;         // [F,22,22,64]
 };
 
 __global__ void __launch_bounds__(c3d::THREADS, 1)
-conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                           const Conv3dParams p) {
+conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3dParams p) {
   using namespace c3d;
   constexpr uint32_t IDESC = make_idesc_bf16(128, COUT);
 
@@ -64,8 +94,6 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   __shared__ uint64_t empty_bar[A_STAGES];
   __shared__ uint64_t tfull_bar[2];
   __shared__ uint64_t tempty_bar[2];
-  __shared__ uint64_t patch_full_bar;
-  __shared__ uint64_t patch_free_bar;
   __shared__ uint64_t weights_bar;
   __shared__ uint32_t tmem_base_slot;
 
@@ -78,19 +106,16 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   const int num_units = p.frames * 2;
 
   if (threadIdx.x == 0) {
-    tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
 #pragma unroll
     for (int i = 0; i < A_STAGES; ++i) {
-      mbar_init(&full_bar[i], NUM_PRODUCERS);
+      mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], 4);
-    mbar_init(&tempty_bar[1], 4);
-    mbar_init(&patch_full_bar, 1);
-    mbar_init(&patch_free_bar, NUM_PRODUCERS);
+    mbar_init(&tempty_bar[0], EPI_WARPS);
+    mbar_init(&tempty_bar[1], EPI_WARPS);
     mbar_init(&weights_bar, 1);
     fence_barrier_init();
   }
@@ -103,22 +128,33 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   grid_dep_wait();
 
   if (warp == 0) {
-    // ------------------------------------------------ loader: weights once, then one patch per unit
+    // ------------------------------------------------ loader: weights once, then (group, dt) stages
     if (lane == 0) {
       mbar_arrive_expect_tx(&weights_bar, B_BYTES);
 #pragma unroll
       for (int j = 0; j < 5; ++j) tma_load_2d(smem + OFF_B + j * (COUT * 128), &tmW, &weights_bar, j * 64, 0);
+      int stage = 0;
       uint32_t phase = 0;
+      const int TP = p.T + 2 * TPAD;
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
         const int f = u >> 1;
         const int half = u & 1;
         const int n = f / p.T;
         const int t = f - n * p.T;
-        mbar_wait(&patch_free_bar, phase ^ 1u, 0x0201);
-        mbar_arrive_expect_tx(&patch_full_bar, PATCH_BYTES);
-        // padded-time frames t .. t+4 hold real frames t-2 .. t+2; rows start at 0 (half 0) or 42 (half 1)
-        tma_load_3d(smem + OFF_PATCH, &tmX, &patch_full_bar, 0, half ? 42 : 0, n * (p.T + 2 * TPAD) + t);
-        phase ^= 1u;
+        const int m_start = half ? 21 * CONV_HW : 0;
+        for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
+          const int m0 = m_start + g * GROUP_PIX;
+#pragma unroll 1
+          for (int dt = 0; dt < 5; ++dt) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0201);
+            uint8_t* dst = smem + OFF_A + stage * A_STAGE_BYTES;
+            const uint4* src = p.x8 + static_cast<size_t>(n * TP + t + dt) * FRAME_ENTRIES + m0;
+            mbar_arrive_expect_tx(&full_bar[stage], A_STAGE_BYTES);
+            bulk_load(dst, src, STAGE_PLANE_BYTES, &full_bar[stage]);
+            bulk_load(dst + STAGE_PLANE_BYTES, src + PLANE_ENTRIES, STAGE_PLANE_BYTES, &full_bar[stage]);
+            if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -127,43 +163,49 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       mbar_wait(&weights_bar, 0, 0x0202);
       int stage = 0;
       uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      int set = 0;
+      uint32_t set_phase = 0;
       const uint64_t db0 = make_desc_sw128(smem_base + OFF_B);
       for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        for (int tile = 0; tile < TILES_PER_UNIT; ++tile) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x0203);
+        for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
+          mbar_wait(&tempty_bar[set], set_phase ^ 1u, 0x0203);
           tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * COUT);
 #pragma unroll 1
-          for (int j = 0; j < 5; ++j) {
+          for (int dt = 0; dt < 5; ++dt) {
             mbar_wait(&full_bar[stage], phase, 0x0204);
             tc_fence_after_sync();
-            const uint64_t da = make_desc_sw128(smem_base + OFF_A + stage * A_STAGE_BYTES);
-            const uint64_t db = db0 + static_cast<uint64_t>((j * COUT * 128) >> 4);
-            const int nk = (j < 4) ? 4 : 2;  // K = 288 = 4*64 + 32
-            for (int k = 0; k < nk; ++k) {
-              umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), IDESC,
-                        (j > 0 || k > 0) ? 1u : 0u);
+            const uint32_t a_base = smem_base + OFF_A + stage * A_STAGE_BYTES;
+            const uint64_t db = db0 + static_cast<uint64_t>((dt * COUT * 128) >> 4);
+#pragma unroll
+            for (int j = 0; j < TILES_PER_GROUP; ++j) {
+              const uint32_t d_tmem = tmem_base + static_cast<uint32_t>((set * TILES_PER_GROUP + j) * COUT);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                // filter rows (2q, 2q+1): plane 0 / plane 1 entries at flat offset q*44 ; q == 3: row 6 + zero weights
+                const uint64_t da = make_desc_kmajor_noswizzle(a_base + j * 2048 + q * (CONV_HW * 16),
+                                                               STAGE_PLANE_BYTES, 128);
+                umma_bf16(d_tmem, da, db + static_cast<uint64_t>(2 * q), IDESC, (dt > 0 || q > 0) ? 1u : 0u);
+              }
             }
             umma_commit(&empty_bar[stage]);
             if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
           }
-          umma_commit(&tfull_bar[acc]);
-          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          umma_commit(&tfull_bar[set]);
+          if (++set == 2) { set = 0; set_phase ^= 1u; }
         }
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------ epilogue + fused max-pool (warps 2..5)
-    const int quarter = warp & 3;
-    const int ew = warp - 2;           // 0..3, pooling work split
-    const int row = quarter * 32 + lane;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    float bias_r[COUT];
+  } else {
+    // ------------------------------------------------ epilogue + fused max-pool (warps 2..9, 256 threads)
+    const int ew = warp - 2;              // 0..7
+    const int quarter = warp & 3;         // TMEM lane quarter this warp may read
+    const int chalf = ew >> 2;            // which 32 of the 64 channels
+    const int etid = threadIdx.x - 64;    // 0..255
+    int set = 0;
+    uint32_t set_phase = 0;
+    float bias_r[32];
 #pragma unroll
-    for (int j = 0; j < COUT; ++j) bias_r[j] = __ldg(p.bias + j);
+    for (int j = 0; j < 32; ++j) bias_r[j] = __ldg(p.bias + chalf * 32 + j);
     uint8_t* ring = smem + OFF_RING;
 
     for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
@@ -173,112 +215,77 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
       const int nrows = half ? 23 : 22;
       const int py_end = half ? 22 : 11;
       int py_next = half ? 11 : 0;
-      for (int tile = 0; tile < TILES_PER_UNIT; ++tile) {
-        mbar_wait(&tfull_bar[acc], acc_phase, 0x0205);
+      for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
+        mbar_wait(&tfull_bar[set], set_phase, 0x0205);
         tc_fence_after_sync();
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * COUT);
-        const int pm = tile * 128 + row;
-        const int slot = pm & (RING_PIX - 1);
-        uint8_t* dst_row = ring + slot * 128;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        for (int j = 0; j < TILES_PER_GROUP; ++j) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                                 static_cast<uint32_t>((set * TILES_PER_GROUP + j) * COUT + chalf * 32);
           uint32_t v[32];
-          __syncwarp();
-          tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_32x32b_x32(taddr, v);
           tmem_ld_wait();
+          const int pm = g * GROUP_PIX + j * 128 + quarter * 32 + lane;  // conv pixel index local to the unit
+          const int slot = (pm >= RING_PIX) ? pm - RING_PIX : pm;
+          uint8_t* dst_row = ring + slot * 128;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            float g[8];
+            float gq[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-              g[e] = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_r[c * 32 + q * 8 + e], 0.0f);
+            for (int e = 0; e < 8; ++e) gq[e] = fmaxf(__uint_as_float(v[q * 8 + e]) + bias_r[q * 8 + e], 0.0f);
             uint4 o;
-            o.x = pack_bf16x2(g[0], g[1]);
-            o.y = pack_bf16x2(g[2], g[3]);
-            o.z = pack_bf16x2(g[4], g[5]);
-            o.w = pack_bf16x2(g[6], g[7]);
-            const int chunk = c * 4 + q;
+            o.x = pack_bf16x2(gq[0], gq[1]);
+            o.y = pack_bf16x2(gq[2], gq[3]);
+            o.z = pack_bf16x2(gq[4], gq[5]);
+            o.w = pack_bf16x2(gq[6], gq[7]);
+            const int chunk = chalf * 4 + q;
             *reinterpret_cast<uint4*>(dst_row + ((chunk ^ (slot & 7)) << 4)) = o;
           }
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (lane == 0) mbar_arrive(&tempty_bar[set]);
+        if (++set == 2) { set = 0; set_phase ^= 1u; }
 
-        // conv pixels of this tile are now in the ring; pool every pooled row that just completed
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int rows_done = (tile == TILES_PER_UNIT - 1) ? nrows : min(nrows, (128 * (tile + 1)) / CONV_HW);
-        while (py_next < py_end) {
-          const int gy_lo = max(2 * py_next - 1, 0);
-          const int gy_hi = min(2 * py_next + 1, CONV_HW - 1);
-          if (gy_hi - y_base >= rows_done) break;
-          for (int px = ew; px < POOL_HW; px += 4) {
-            const int gx_lo = max(2 * px - 1, 0);
-            const int gx_hi = min(2 * px + 1, CONV_HW - 1);
-            __nv_bfloat162 best = __floats2bfloat162_rn(0.0f, 0.0f);  // post-ReLU values are >= 0
-            for (int gy = gy_lo; gy <= gy_hi; ++gy) {
-              for (int gx = gx_lo; gx <= gx_hi; ++gx) {
-                const int s2 = ((gy - y_base) * CONV_HW + gx) & (RING_PIX - 1);
-                const uint32_t w = *reinterpret_cast<const uint32_t*>(
-                    ring + s2 * 128 + (((lane >> 2) ^ (s2 & 7)) << 4) + ((lane & 3) << 2));
-                best = __hmax2(best, *reinterpret_cast<const __nv_bfloat162*>(&w));
-              }
-            }
-            __nv_bfloat16* op = p.out + ((static_cast<size_t>(f) * POOL_HW + py_next) * POOL_HW + px) * COUT;
-            reinterpret_cast<__nv_bfloat162*>(op)[lane] = best;
-          }
-          ++py_next;
-        }
-      }
-    }
-  } else {
-    // ------------------------------------------------ A-operand producers (warps 6..13, 256 threads)
-    const int ptid = threadIdx.x - 6 * 32;
-    const int m = ptid & 127;
-    const int hsel = ptid >> 7;
-    const uint8_t* patch = smem + OFF_PATCH;
-    int stage = 0;
-    uint32_t phase = 0;
-    uint32_t patch_phase = 0;
-    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-      mbar_wait(&patch_full_bar, patch_phase, 0x0206);
-      patch_phase ^= 1u;
-      for (int tile = 0; tile < TILES_PER_UNIT; ++tile) {
-        const int pm = tile * 128 + m;
-        int yl = pm / CONV_HW;
-        const int x = pm - yl * CONV_HW;
-        yl = min(yl, 22);  // rows past the unit are never pooled; keep their reads inside the patch
-        const uint8_t* src_px = patch + ((2 * yl) * WP + 2 * x) * 2;
-        uint8_t* dst_row = smem + OFF_A + m * 128;
-        const int sw = m & 7;
-#pragma unroll 1
-        for (int j = 0; j < 5; ++j) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0207);
-          uint8_t* dst = dst_row + stage * A_STAGE_BYTES;
-          if (j < 4 || hsel == 0) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int cc = hsel * 4 + q;   // chunk inside this 64-wide K block
-              const int c = j * 8 + cc;      // global chunk = dt*7 + r
-              uint4 val = make_uint4(0u, 0u, 0u, 0u);
-              if (c < 35) {
-                const int dt = c / 7;
-                const int r = c - dt * 7;
-                const uint32_t* sp =
-                    reinterpret_cast<const uint32_t*>(src_px + ((dt * PATCH_ROWS + r) * WP) * 2);
-                val.x = sp[0]; val.y = sp[1]; val.z = sp[2]; val.w = sp[3];
-              }
-              *reinterpret_cast<uint4*>(dst + ((cc ^ sw) << 4)) = val;
+        // conv pixels of this group are in the ring; pool every pooled row whose 3 conv rows are complete
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int rows_done = (g == GROUPS_PER_UNIT - 1) ? nrows : min(nrows, (GROUP_PIX * (g + 1)) / CONV_HW);
+        int py_stop = py_next;
+        while (py_stop < py_end && min(2 * py_stop + 1, CONV_HW - 1) - y_base < rows_done) ++py_stop;
+        const int items = (py_stop - py_next) * (POOL_HW * 8);
+        for (int it = etid; it < items; it += EPI_THREADS) {
+          const int c = it & 7;                  // 8-channel chunk
+          const int pp = it >> 3;
+          const int pyo = pp / POOL_HW;
+          const int px = pp - pyo * POOL_HW;
+          const int py = py_next + pyo;
+          const int gy_lo = max(2 * py - 1, 0), gy_hi = min(2 * py + 1, CONV_HW - 1);
+          const int gx_lo = max(2 * px - 1, 0), gx_hi = min(2 * px + 1, CONV_HW - 1);
+          __nv_bfloat162 b0 = __floats2bfloat162_rn(0.0f, 0.0f);  // post-ReLU values are >= 0
+          __nv_bfloat162 b1 = b0, b2 = b0, b3 = b0;
+          for (int gy = gy_lo; gy <= gy_hi; ++gy) {
+            for (int gx = gx_lo; gx <= gx_hi; ++gx) {
+              int s2 = (gy - y_base) * CONV_HW + gx;
+              if (s2 >= RING_PIX) s2 -= RING_PIX;
+              const uint4 w = *reinterpret_cast<const uint4*>(ring + s2 * 128 + ((c ^ (s2 & 7)) << 4));
+              b0 = __hmax2(b0, *reinterpret_cast<const __nv_bfloat162*>(&w.x));
+              b1 = __hmax2(b1, *reinterpret_cast<const __nv_bfloat162*>(&w.y));
+              b2 = __hmax2(b2, *reinterpret_cast<const __nv_bfloat162*>(&w.z));
+              b3 = __hmax2(b3, *reinterpret_cast<const __nv_bfloat162*>(&w.w));
             }
           }
-          fence_proxy_async_smem();
-          mbar_arrive(&full_bar[stage]);
-          if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
+          uint4 o;
+          o.x = *reinterpret_cast<uint32_t*>(&b0);
+          o.y = *reinterpret_cast<uint32_t*>(&b1);
+          o.z = *reinterpret_cast<uint32_t*>(&b2);
+          o.w = *reinterpret_cast<uint32_t*>(&b3);
+          __nv_bfloat16* op = p.out + ((static_cast<size_t>(f) * POOL_HW + py) * POOL_HW + px) * COUT + c * 8;
+          *reinterpret_cast<uint4*>(op) = o;
         }
+        py_next = py_stop;
+        // the next group's ring writes may overwrite pixels this group's pooling just read
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
-      mbar_arrive(&patch_free_bar);  // this thread no longer reads the patch
     }
   }
 

@@ -119,7 +119,7 @@ def cast_bf16(x, out=None):
 
 # ------------------------------------------------------------------------------------ frontend
 def prep_clip(x, out=None):
-    """x fp32 [N,1,T,88,88] (or [N,T,88,88]) -> bf16 [N,T+4,94,96] zero-bordered."""
+    """x fp32 [N,1,T,88,88] (or [N,T,88,88]) -> (flat bf16 row-Toeplitz clip, N, T) for conv3d_bn_relu_pool."""
     _req(x, F32, "x")
     if x.dim() == 5:
         n, c, t, h, w = x.shape
@@ -129,18 +129,20 @@ def prep_clip(x, out=None):
         n, t, h, w = x.shape
     if (h, w) != (88, 88):
         raise RuntimeError(f"prep_clip: frames must be 88x88, got {h}x{w}")
+    elems = int(_lib.load().sblk_prep_clip_elems(n, t))
     if out is None:
-        out = torch.empty((n, t + 4, 94, 96), dtype=BF16, device=x.device)
+        out = torch.empty((elems,), dtype=BF16, device=x.device)
     _req(out, BF16, "out")
-    _call("sblk_prep_clip", f"prep N={n} T={t}", 0, 4 * x.numel() + 2 * out.numel(), _p(x), _p(out), n, t, _stream())
-    return out
+    if out.numel() < elems:
+        raise RuntimeError(f"prep_clip: output needs {elems} bf16 elements, got {out.numel()}")
+    _call("sblk_prep_clip", f"prep N={n} T={t}", 0, 4 * x.numel() + 2 * elems, _p(x), _p(out), n, t, _stream())
+    return out, n, t
 
 
 def conv3d_bn_relu_pool(xp, wp, bias, out=None):
-    """prepped clip bf16 [N,T+4,94,96] -> bf16 NHWC [N*T,22,22,64]."""
+    """prepped clip (out, N, T) of prep_clip -> bf16 NHWC [N*T,22,22,64]."""
+    xp, n, t = xp
     _req(xp, BF16, "xp"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
-    n, tp = xp.shape[0], xp.shape[1]
-    t = tp - 4
     if out is None:
         out = torch.empty((n * t, 22, 22, 64), dtype=BF16, device=xp.device)
     _req(out, BF16, "out")

@@ -70,10 +70,13 @@ def sec_aux():
     g = torch.Generator(device="cpu").manual_seed(0)
     # prep
     x = torch.randn(2, 1, 5, 88, 88, generator=g).to(DEV)
-    xp = ops.prep_clip(x)
-    ref = torch.zeros(2, 9, 94, 96, device=DEV)
-    ref[:, 2:7, 3:91, 3:91] = x[:, 0]
-    report("prep_clip", xp, bf(ref))
+    xp, _, _ = ops.prep_clip(x)
+    pad = torch.zeros(2, 9, 94, 104, device=DEV)
+    pad[:, 2:7, 3:91, 3:91] = x[:, 0]
+    # X8[n][tp][pl][yy][x][j] = pad[n][tp][2yy+pl][2x+j]
+    ref = pad.unfold(3, 8, 2)[:, :, :, :44]                      # [2,9,94,44,8]
+    ref = ref.reshape(2, 9, 47, 2, 44, 8).permute(0, 1, 3, 2, 4, 5).contiguous()
+    report("prep_clip", xp[:ref.numel()].reshape(ref.shape), bf(ref))
     # pack conv2d
     w = torch.randn(128, 64, 3, 3, generator=g).to(DEV)
     gam = (torch.rand(128, generator=g) + 0.5).to(DEV)
@@ -89,8 +92,8 @@ def sec_aux():
     wp3, b3 = ops.pack_conv3d(w3, gam[:64].contiguous(), bet[:64].contiguous(), mu[:64].contiguous(),
                               var[:64].contiguous())
     sc3 = gam[:64] / torch.sqrt(var[:64] + 1e-5)
-    ref3 = torch.zeros(64, 40, 8, device=DEV)
-    ref3[:, :35, :7] = (w3[:, 0] * sc3[:, None, None, None]).reshape(64, 35, 7)
+    ref3 = torch.zeros(64, 5, 8, 8, device=DEV)                   # [co][dt][r (2q+h)][s]
+    ref3[:, :, :7, :7] = w3[:, 0] * sc3[:, None, None, None]
     report("pack_conv3d.w", wp3, bf(ref3.reshape(64, 320)))
     # cast
     a = torch.randn(1000, 512, generator=g).to(DEV)
@@ -315,7 +318,7 @@ def sec_perf():
     out = torch.empty(928, 22, 22, 64, dtype=torch.bfloat16, device=DEV)
     ms = timeit(lambda: ops.conv3d_bn_relu_pool(xp, wp3, b3, out=out))
     print(f"perf conv3d N32 T29: {ms * 1e3:.1f} us  {2.0 * 928 * 44 * 44 * 64 * 245 / ms / 1e9:.1f} TFLOP/s")
-    ms = timeit(lambda: ops.prep_clip(x, out=xp))
+    ms = timeit(lambda: ops.prep_clip(x, out=xp[0]))
     print(f"perf prep N32 T29: {ms * 1e3:.1f} us")
 
 
