@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -110,9 +111,9 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(sblk::attention_kernel<1>, 100 * 1024))) return rc;
-    if ((rc = set_smem(sblk::attention_kernel<2>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<4>, 100 * 1024))) return rc;
+    if ((rc = set_smem(sblk::attention_kernel<8>, 100 * 1024))) return rc;
+    if ((rc = set_smem(sblk::attention_kernel<16>, 100 * 1024))) return rc;
     st.ready = true;
   }
   if (num_sms_out != nullptr) *num_sms_out = st.num_sms;
@@ -293,6 +294,10 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   p.x8 = static_cast<const uint4*>(xp);
   p.bias = bias;
   p.out = static_cast<__nv_bfloat16*>(out);
+  {
+    const char* dm = getenv("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    p.debug_mode = dm ? atoi(dm) : 0;
+  }
   const int units = p.frames * 2;
   const int grid = units < sms ? units : sms;
   return launch(sblk::conv3d_bn_relu_pool_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES,
@@ -440,12 +445,17 @@ int sblk_attention_fwd(const void* qkv, void* out, float* probs, const int* leng
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.probs = probs; p.lengths = lengths; p.N = N; p.T = T; p.H = H; p.scale = scale;
-  const size_t smem = static_cast<size_t>(T) * (65 + 65 + 64) * sizeof(float);
-  const dim3 grid(N * H), block(128);
+  const int pairs = N * H;
+  const dim3 grid((pairs + sblk::ATTN_WARPS - 1) / sblk::ATTN_WARPS), block(sblk::ATTN_WARPS * 32);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (T <= 32) return launch(sblk::attention_kernel<1>, grid, block, smem, s, true, "attention_kernel<1>", p);
-  if (T <= 64) return launch(sblk::attention_kernel<2>, grid, block, smem, s, true, "attention_kernel<2>", p);
-  return launch(sblk::attention_kernel<4>, grid, block, smem, s, true, "attention_kernel<4>", p);
+  if (T <= 32)
+    return launch(sblk::attention_kernel<4>, grid, block, sblk::ATTN_WARPS * 3 * 32 * 128, s, true,
+                  "attention_kernel<4>", p);
+  if (T <= 64)
+    return launch(sblk::attention_kernel<8>, grid, block, sblk::ATTN_WARPS * 3 * 64 * 128, s, true,
+                  "attention_kernel<8>", p);
+  return launch(sblk::attention_kernel<16>, grid, block, sblk::ATTN_WARPS * 3 * 128 * 128, s, true,
+                "attention_kernel<16>", p);
 }
 
 }  // extern "C"

@@ -2,9 +2,10 @@
 // Reference: ScaledDotProductAttention.forward, SBL/transformer/attention.py:72-83 and the head
 // split / merge around it in MultiHeadAttention.forward, attention.py:41-55:
 //   attn = softmax(Q K^T / sqrt(d_k) masked_fill(key >= length, -inf)) ; out = attn V
-// One CTA per (clip, head); K and V of the head live in shared memory as fp32; one warp per query row:
-// each lane owns keys {lane, lane+32, ...}, max / sum are warp-shuffle reductions, everything fp32.
-// 0.05 % of the encoder's FLOPs -> latency bound; no tensor cores on purpose.
+// One WARP per (clip, head): Q, K, V of the head are staged in (warp-private, XOR-swizzled) shared memory, S = Q K^T
+// and O = P V run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate; 0.05 % of the encoder's FLOPs, far
+// too small for a tcgen05 tile), the softmax lives in the accumulator registers (fp32, quad-shuffle max / sum), and P is
+// fed to the second MMA as a bf16 hi + lo pair so the probabilities keep fp32-level accuracy.
 #pragma once
 #include "sblk_common.cuh"
 
@@ -19,102 +20,187 @@ struct AttnParams {
   float scale;               // 1 / temperature
 };
 
-template <int KPL>  // keys per lane: supports T <= 32*KPL
-__global__ void __launch_bounds__(128)
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                                  uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+constexpr int ATTN_WARPS = 2;
+
+// NT = number of 8-key tiles (T <= 8*NT); rows padded to TP = 8*NT (multiple of 16).
+template <int NT>
+__global__ void __launch_bounds__(ATTN_WARPS * 32)
 attention_kernel(const AttnParams p) {
   constexpr int D = 64;
-  constexpr int LDK = D + 1;  // padded fp32 row -> conflict-free column walks
-  extern __shared__ float sm[];
-  float* sK = sm;                      // [T][65]
-  float* sV = sK + p.T * LDK;          // [T][65]
-  float* sQ = sV + p.T * LDK;          // [T][64]
+  constexpr int TP = 8 * NT;
+  constexpr int KT = NT / 2;             // 16-key tiles for P V
+  extern __shared__ __align__(128) uint8_t attn_smem[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int pair = blockIdx.x * ATTN_WARPS + warp;    // (clip, head) index
+  uint8_t* sQ = attn_smem + warp * (3 * TP * 128);
+  uint8_t* sK = sQ + TP * 128;
+  uint8_t* sV = sK + TP * 128;
 
+  grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
   grid_dep_wait();
+  if (pair >= p.N * p.H) return;
 
-  const int b = blockIdx.x / p.H;
-  const int h = blockIdx.x - b * p.H;
+  const int b = pair / p.H;
+  const int h = pair - b * p.H;
   const int T = p.T;
   const int ld = 3 * p.H * D;
   const int len = (p.lengths != nullptr) ? min(max(__ldg(p.lengths + b), 0), T) : T;
 
-  // cooperative load: T rows x 3 x 64 bf16, 8 values (16 B) per thread-iteration
+  // stage Q | K | V rows of this head (bf16, 128 B per row, 16-B chunk c stored at c ^ (row & 7)); pad rows are zero
   const __nv_bfloat16* base = p.qkv + static_cast<size_t>(b) * T * ld + h * D;
-  for (int i = threadIdx.x; i < T * 3 * (D / 8); i += blockDim.x) {
-    const int c8 = i % (D / 8);
-    int r = i / (D / 8);
-    const int which = r % 3;
-    const int t = r / 3;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * ld + which * p.H * D) + c8);
-    float* dst = (which == 0) ? (sQ + t * D + c8 * 8) : ((which == 1 ? sK : sV) + t * LDK + c8 * 8);
-    dst[0] = bf16_lo(u.x); dst[1] = bf16_hi(u.x);
-    dst[2] = bf16_lo(u.y); dst[3] = bf16_hi(u.y);
-    dst[4] = bf16_lo(u.z); dst[5] = bf16_hi(u.z);
-    dst[6] = bf16_lo(u.w); dst[7] = bf16_hi(u.w);
+  for (int i = lane; i < 3 * TP * 8; i += 32) {
+    const int c = i & 7;
+    const int row = (i >> 3) % TP;
+    const int which = (i >> 3) / TP;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (row < T)
+      u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(row) * ld + which * p.H * D) + c);
+    *reinterpret_cast<uint4*>(sQ + which * (TP * 128) + row * 128 + ((c ^ (row & 7)) << 4)) = u;
   }
-  __syncthreads();
+  __syncwarp();
 
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  for (int q = warp; q < T; q += (blockDim.x >> 5)) {
-    const float* qrow = sQ + q * D;
-    float s[KPL];
+  const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+  const int g = lane >> 2;       // fragment row within an 8-row group
+  const int tq = lane & 3;       // fragment column pair
+  const int mt_count = (T + 15) >> 4;
+
+  for (int mt = 0; mt < mt_count; ++mt) {
+    // ---- S = Q K^T for 16 query rows
+    float s[NT][4];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) s[i] = 0.0f;
-#pragma unroll 8
-    for (int d = 0; d < D; ++d) {
-      const float qd = qrow[d];
+    for (int j = 0; j < NT; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f; }
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int j = lane + 32 * i;
-        if (j < T) s[i] = fmaf(qd, sK[j * LDK + d], s[i]);
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t a0, a1, a2, a3;
+      {
+        const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = 2 * kk + (lane >> 4);
+        ldmatrix_x4(sQ_u + row * 128 + ((c ^ (row & 7)) << 4), a0, a1, a2, a3);
+      }
+#pragma unroll
+      for (int j2 = 0; j2 < NT / 2; ++j2) {
+        // two key tiles per ldmatrix.x4: matrices (keys 16*j2.., chunk 2kk), (.., chunk 2kk+1), (keys +8, ..), (..)
+        const int row = j2 * 16 + (lane & 7) + (lane >> 4) * 8;
+        const int c = 2 * kk + ((lane >> 3) & 1);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4(sK_u + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * j2], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(s[2 * j2 + 1], a0, a1, a2, a3, b2, b3);
       }
     }
-    float mx = -INFINITY;
+    // ---- masked softmax over keys (rows g and g + 8 of this tile), fp32
+    float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int j = lane + 32 * i;
-      s[i] = (j < len) ? s[i] * p.scale : -INFINITY;
-      mx = fmaxf(mx, s[i]);
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = (j * 8 + 2 * tq + e) < len;
+        s[j][e] = ok ? s[j][e] * p.scale : -INFINITY;
+        s[j][2 + e] = ok ? s[j][2 + e] * p.scale : -INFINITY;
+        mx0 = fmaxf(mx0, s[j][e]);
+        mx1 = fmaxf(mx1, s[j][2 + e]);
+      }
     }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.0f, sum1 = 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.0f;
+    for (int j = 0; j < NT; ++j) {
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      s[i] = __expf(s[i] - mx);  // all-masked row: exp(-inf - -inf) = NaN, as in the reference softmax
-      sum += s[i];
+      for (int e = 0; e < 2; ++e) {
+        // all-masked row: exp(-inf - -inf) = NaN, as in the reference softmax
+        s[j][e] = __expf(s[j][e] - mx0);
+        s[j][2 + e] = __expf(s[j][2 + e] - mx1);
+        sum0 += s[j][e];
+        sum1 += s[j][2 + e];
+      }
     }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) s[i] *= inv;
-
+    for (int j = 0; j < NT; ++j) {
+      s[j][0] *= inv0; s[j][1] *= inv0; s[j][2] *= inv1; s[j][3] *= inv1;
+    }
+    const int q0 = mt * 16 + g, q1 = q0 + 8;
     if (p.probs != nullptr) {
-      float* pr = p.probs + (static_cast<size_t>(h) * p.N + b) * T * T + static_cast<size_t>(q) * T;
+      float* pr = p.probs + (static_cast<size_t>(h) * p.N + b) * T * T;
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int j = lane + 32 * i;
-        if (j < T) pr[j] = s[i];
+      for (int j = 0; j < NT; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = j * 8 + 2 * tq + e;
+          if (key < T) {
+            if (q0 < T) pr[static_cast<size_t>(q0) * T + key] = s[j][e];
+            if (q1 < T) pr[static_cast<size_t>(q1) * T + key] = s[j][2 + e];
+          }
+        }
       }
     }
-
-    float o0 = 0.0f, o1 = 0.0f;  // output dims lane and lane + 32
+    // ---- O = P V with P as bf16 hi + lo
+    float o[8][4];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int jmax = min(32, T - 32 * i);
-      for (int jj = 0; jj < jmax; ++jj) {
-        const float pj = __shfl_sync(0xffffffffu, s[i], jj);
-        const float* vr = sV + (32 * i + jj) * LDK;
-        o0 = fmaf(pj, vr[lane], o0);
-        o1 = fmaf(pj, vr[lane + 32], o1);
+    for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        // A-fragment register r: (row g | g+8, keys 16kt + 2tq.. | +8) == accumulator regs of key tiles 2kt, 2kt+1
+        const float x = s[2 * kt + (r >> 1)][(r & 1) * 2 + 0];
+        const float y = s[2 * kt + (r >> 1)][(r & 1) * 2 + 1];
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
+        const float2 hf = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+        hi[r] = *reinterpret_cast<const uint32_t*>(&hh);
+        lo[r] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+#pragma unroll
+      for (int n2 = 0; n2 < 4; ++n2) {
+        // V^T fragments for d-chunks 2*n2 and 2*n2+1: matrices (keys 16kt.., chunk), (keys +8, chunk), (.., chunk+1), (..)
+        const int row = kt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int c = 2 * n2 + (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldmatrix_x4_trans(sV_u + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * n2], hi[0], hi[1], hi[2], hi[3], b0, b1);
+        mma_bf16_16816(o[2 * n2], lo[0], lo[1], lo[2], lo[3], b0, b1);
+        mma_bf16_16816(o[2 * n2 + 1], hi[0], hi[1], hi[2], hi[3], b2, b3);
+        mma_bf16_16816(o[2 * n2 + 1], lo[0], lo[1], lo[2], lo[3], b2, b3);
       }
     }
-    __nv_bfloat16* orow = p.out + (static_cast<size_t>(b) * T + q) * (p.H * D) + h * D;
-    orow[lane] = __float2bfloat16_rn(o0);
-    orow[lane + 32] = __float2bfloat16_rn(o1);
+    // ---- store: out[(b*T + q), h*64 + d]; thread holds d = 8n + 2tq, +1 for rows q0 / q1
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (q0 < T)
+        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(b) * T + q0) * (p.H * D) + h * D + n * 8 + 2 * tq) =
+            pack_bf16x2(o[n][0], o[n][1]);
+      if (q1 < T)
+        *reinterpret_cast<uint32_t*>(p.out + (static_cast<size_t>(b) * T + q1) * (p.H * D) + h * D + n * 8 + 2 * tq) =
+            pack_bf16x2(o[n][2], o[n][3]);
+    }
   }
-  grid_dep_launch();
 }
 
 }  // namespace sblk

@@ -22,10 +22,10 @@ prep_clip_kernel(const float* __restrict__ x, uint4* __restrict__ out, int N, in
   const long long total = static_cast<long long>(N) * TP * FRAME_ENTRIES;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cx = static_cast<int>(i % CONV_HW);
-    long long r = i / CONV_HW;
-    const int yy = static_cast<int>(r % PLANE_ROWS);
-    r /= PLANE_ROWS;
+    const int e_in_plane = static_cast<int>(i % PLANE_ENTRIES);  // entries >= 47*44 are zero padding
+    long long r = i / PLANE_ENTRIES;
+    const int yy = e_in_plane / CONV_HW;
+    const int cx = e_in_plane - yy * CONV_HW;
     const int pl = static_cast<int>(r & 1);
     r >>= 1;
     const int tp = static_cast<int>(r % TP);
@@ -35,7 +35,7 @@ prep_clip_kernel(const float* __restrict__ x, uint4* __restrict__ out, int N, in
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-    if (t >= 0 && t < T && y >= 0 && y < IN_HW) {
+    if (t >= 0 && t < T && y >= 0 && y < IN_HW && yy < PLANE_ROWS) {
       const float* src = x + ((static_cast<long long>(n) * T + t) * IN_HW + y) * IN_HW;
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
@@ -163,6 +163,7 @@ struct LnParams {
 
 __global__ void __launch_bounds__(256)
 add_layernorm512_kernel(const LnParams p) {
+  grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
   grid_dep_wait();
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -225,7 +226,6 @@ add_layernorm512_kernel(const LnParams p) {
       }
     }
   }
-  grid_dep_launch();
 }
 
 }  // namespace sblk

@@ -97,6 +97,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = tmem_base_slot;
 
   // Everything above overlaps the tail of the previous kernel under PDL; inputs are read below.
+  grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
   grid_dep_wait();
 
   if (warp == 0) {
@@ -245,7 +246,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
-  grid_dep_launch();
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {

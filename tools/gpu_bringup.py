@@ -75,7 +75,8 @@ def sec_aux():
     pad[:, 2:7, 3:91, 3:91] = x[:, 0]
     # X8[n][tp][pl][yy][x][j] = pad[n][tp][2yy+pl][2x+j]
     ref = pad.unfold(3, 8, 2)[:, :, :, :44]                      # [2,9,94,44,8]
-    ref = ref.reshape(2, 9, 47, 2, 44, 8).permute(0, 1, 3, 2, 4, 5).contiguous()
+    ref = ref.reshape(2, 9, 47, 2, 44, 8).permute(0, 1, 3, 2, 4, 5).reshape(2, 9, 2, 47 * 44 * 8)
+    ref = F.pad(ref, (0, 32)).contiguous()                       # 4 zero entries per plane
     report("prep_clip", xp[:ref.numel()].reshape(ref.shape), bf(ref))
     # pack conv2d
     w = torch.randn(128, 64, 3, 3, generator=g).to(DEV)
