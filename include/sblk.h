@@ -54,17 +54,30 @@ long long sblk_prep_clip_elems(int N, int T);
  * transformer/video_frontend.py:100 */
 int sblk_prep_clip(const float* x, void* x_prepped_bf16, int N, int T, void* stream);
 /* Conv3d + BN3d(eval) + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) + transpose(1,2).contiguous().view:
- * prepped clip -> bf16 NHWC [N*T,22,22,64].
+ * prepped clip -> bf16 NHWC [N*T,22,22,64] (flat_out = 0) or the flat layout below (flat_out = 1).
  * replaces: Lipreading.frontend3D and _frontend_forward's relayout, transformer/video_frontend.py:99-104,111-115 */
 int sblk_conv3d_bn_relu_pool_fwd(const void* x_prepped_bf16, const void* w_packed_bf16, const float* bias,
-                                 void* out_bf16, int N, int T, void* stream);
+                                 void* out_bf16, int N, int T, int flat_out, void* stream);
+/* Rows of the zero-haloed flat activation layout for F frames of H x W pixels:
+ * pixel (f,y,x) -> row (f*(H+1) + 1 + y)*(W+2) + 1 + x of a [rows, C] bf16 matrix; all other rows are zero. */
+long long sblk_flat_rows(int F, int H, int W);
+/* Stride-1 3x3 / pad 1 Conv2d (C -> C, C == 64) + folded BN (+ residual) (+ ReLU) over the flat layout
+ * (flat_out of sblk_conv3d_bn_relu_pool_fwd or a previous call); output is again flat with zero halos.
+ * w_packed_bf16 is [C][10*C]: the 9 taps of sblk_pack_conv2d's [C][3][3][C] followed by a CxC identity
+ * (the residual is accumulated by the tensor core as R*I).
+ * replaces: the four 64->64 convs of ResNet layer1, transformer/video_frontend.py:10-12,28-41 */
+int sblk_flatconv3x3_fwd(const void* x_flat, const void* w_packed_bf16, const float* bias, const void* residual_flat,
+                         void* out_flat, int F, int H, int W, int C, int relu, void* stream);
 /* Implicit-GEMM Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) over bf16 NHWC [F,H,W,Cin] with folded BN:
  * out = act(conv(x, w) + bias (+ residual)), bf16 NHWC [F,P,Q,Cout].  Cin % 64 == 0, Cout % 64 == 0.
+ * in_row_pitch / in_frame_pitch (pixels, 0 = dense) let x point at pixel (0,0,0) of a pitched layout such as the
+ * flat one (pass x_flat + (W+3)*Cin elements, W+2, (H+1)*(W+2)).
  * replaces: BasicBlock.forward conv1/bn1/relu, conv2/bn2/+=residual/relu and the downsample branch,
  * transformer/video_frontend.py:28-41,68-72 */
 int sblk_conv2d_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const float* bias,
                           const void* residual_bf16, void* out_bf16, int F, int H, int W, int Cin, int Cout,
-                          int R, int S, int stride, int pad, int relu, void* stream);
+                          int R, int S, int stride, int pad, int relu, int in_row_pitch, int in_frame_pitch,
+                          void* stream);
 /* bf16 NHWC [F,HW,C] -> mean over HW: fp32 [F,C] and/or bf16 [F,C] (either may be NULL).
  * replaces: nn.AdaptiveAvgPool2d(1) + view, transformer/video_frontend.py:87-88 */
 int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);

@@ -33,8 +33,10 @@ SIGNATURES = {
     "sblk_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "sblk_prep_clip_elems": (_ll, [_i, _i]),
     "sblk_prep_clip": (_i, [_vp, _vp, _i, _i, _vp]),
-    "sblk_conv3d_bn_relu_pool_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
-    "sblk_conv2d_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "sblk_conv3d_bn_relu_pool_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sblk_flat_rows": (_ll, [_i, _i, _i]),
+    "sblk_flatconv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sblk_conv2d_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_avgpool_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "sblk_gemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),

@@ -32,6 +32,17 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// Warp-uniform helpers.  tcgen05.mma / TMA take their operands from uniform registers; if the issuing code sits in a
+// lane-divergent region (`if (lane == 0)`) the compiler wraps every MMA in an ELECT + R2UR.BROADCAST loop (~13
+// instructions, ~100 cycles per MMA).  Role code therefore runs warp-uniformly (all lanes compute the same
+// descriptors) and only the issue itself is predicated on one elected lane.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------- mbarrier -------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -144,6 +155,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr_bytes) {
   d |= static_cast<uint64_t>(1) << 46;            // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
   return d;
+}
+
+// Descriptor arithmetic for single-thread MMA issue loops: the issuing thread is one instruction stream, so per-MMA
+// 64-bit descriptor construction caps the issue rate (measured: ~100 cycles per N=64 MMA instead of 48).  Keep the
+// constant high word and add byte offsets (>> 4) to the low word only; valid smem addresses never carry out of the
+// 14-bit start-address field.
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t desc, uint32_t lo) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(static_cast<uint32_t>(desc >> 32)));
+  return r;
 }
 
 // Instruction descriptor, kind::f16: BF16 x BF16 -> FP32, both operands K-major, dense.

@@ -83,7 +83,8 @@ struct Conv3dParams {
   int T;                      // frames per clip
   const uint4* x8;            // row-Toeplitz clip [N][T+4][2][47][44] entries of 8 bf16
   const float* bias;          // [64] folded BN shift
-  __nv_bfloat16* out;         // [F,22,22,64]
+  __nv_bfloat16* out;         // [F,22,22,64], or the zero-haloed flat layout of sblk_flatconv.cuh when flat_out
+  int flat_out;               // 1: pixel (f,y,x) -> row (f*23 + 1 + y)*24 + 1 + x, halo rows/columns written as zeros
   int debug_mode;             // 0 = normal; timing experiments only: 1 = no MMAs, 2 = no loads
 };
 
@@ -183,7 +184,10 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
             mbar_wait(&full_bar[stage], phase, 0x0204);
             tc_fence_after_sync();
             const uint32_t a_base = smem_base + OFF_A + stage * A_STAGE_BYTES;
-            const uint64_t db = db0 + static_cast<uint64_t>((dt * COUT * 128) >> 4);
+            // descriptors differ only in the low word (start address >> 4): one 32-bit add per operand per MMA
+            const uint64_t da0 = make_desc_kmajor_noswizzle(a_base, STAGE_PLANE_BYTES, 128);
+            const uint32_t da0_lo = static_cast<uint32_t>(da0);
+            const uint32_t db_lo = static_cast<uint32_t>(db0) + static_cast<uint32_t>((dt * COUT * 128) >> 4);
 #pragma unroll
             for (int j = 0; j < TILES_PER_GROUP; ++j) {
               if (p.debug_mode == 1) break;
@@ -191,9 +195,8 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 // filter rows (2q, 2q+1): plane 0 / plane 1 entries at flat offset q*44 ; q == 3: row 6 + zero weights
-                const uint64_t da = make_desc_kmajor_noswizzle(a_base + j * 2048 + q * (CONV_HW * 16),
-                                                               STAGE_PLANE_BYTES, 128);
-                umma_bf16(d_tmem, da, db + static_cast<uint64_t>(2 * q), IDESC, (dt > 0 || q > 0) ? 1u : 0u);
+                umma_bf16(d_tmem, desc_with_lo(da0, da0_lo + static_cast<uint32_t>((j * 2048 + q * (CONV_HW * 16)) >> 4)),
+                          desc_with_lo(db0, db_lo + static_cast<uint32_t>(2 * q)), IDESC, (dt > 0 || q > 0) ? 1u : 0u);
               }
             }
             umma_commit(&empty_bar[stage]);
@@ -268,49 +271,62 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
             (g == GROUPS_PER_UNIT - 1) ? nrows : min(nrows, (GROUP_PIX * (g + 1) - pix_off) / CONV_HW);
         int py_stop = py_next;
         while (py_stop < py_end && min(2 * py_stop + 1, CONV_HW - 1) - y_base < rows_done) ++py_stop;
-        const int items = (py_stop - py_next) * (POOL_HW * 8);
+        const int wcols = p.flat_out ? POOL_HW + 2 : POOL_HW;   // flat layout: zero halo column on each side
+        const int items = (py_stop - py_next) * (wcols * 8);
         for (int it = etid; it < items; it += EPI_THREADS) {
           const int c = it & 7;                  // 8-channel chunk
           const int pp = it >> 3;
-          const int pyo = pp / POOL_HW;
-          const int px = pp - pyo * POOL_HW;
+          const int pyo = pp / wcols;
+          const int pxp = pp - pyo * wcols;
+          const int px = p.flat_out ? pxp - 1 : pxp;
           const int py = py_next + pyo;
-          // clamped 3x3 window: a clamped tap repeats an in-range pixel, which leaves the max unchanged
-          int rowoff[3], col[3];
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (px >= 0 && px < POOL_HW) {
+            // clamped 3x3 window: a clamped tap repeats an in-range pixel, which leaves the max unchanged
+            int rowoff[3], col[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            rowoff[i] = (min(max(2 * py - 1 + i, 0), CONV_HW - 1) - y_base) * CONV_HW + pix_off;
-            col[i] = min(max(2 * px - 1 + i, 0), CONV_HW - 1);
-          }
-          __nv_bfloat162 b0 = __floats2bfloat162_rn(0.0f, 0.0f);  // post-ReLU values are >= 0
-          __nv_bfloat162 b1 = b0, b2 = b0, b3 = b0;
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              int s2 = rowoff[i] + col[k];
-              s2 = (s2 >= RING_PIX) ? s2 - RING_PIX : s2;
-              uint4 w;
-              const uint32_t addr = ring_u32 + s2 * 128 + ((c ^ (s2 & 7)) << 4);
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                           : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(addr));
-              b0 = __hmax2(b0, *reinterpret_cast<const __nv_bfloat162*>(&w.x));
-              b1 = __hmax2(b1, *reinterpret_cast<const __nv_bfloat162*>(&w.y));
-              b2 = __hmax2(b2, *reinterpret_cast<const __nv_bfloat162*>(&w.z));
-              b3 = __hmax2(b3, *reinterpret_cast<const __nv_bfloat162*>(&w.w));
+            for (int i = 0; i < 3; ++i) {
+              rowoff[i] = (min(max(2 * py - 1 + i, 0), CONV_HW - 1) - y_base) * CONV_HW + pix_off;
+              col[i] = min(max(2 * px - 1 + i, 0), CONV_HW - 1);
             }
+            __nv_bfloat162 b0 = __floats2bfloat162_rn(0.0f, 0.0f);  // post-ReLU values are >= 0
+            __nv_bfloat162 b1 = b0, b2 = b0, b3 = b0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                int s2 = rowoff[i] + col[k];
+                s2 = (s2 >= RING_PIX) ? s2 - RING_PIX : s2;
+                uint4 w;
+                const uint32_t addr = ring_u32 + s2 * 128 + ((c ^ (s2 & 7)) << 4);
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(addr));
+                b0 = __hmax2(b0, *reinterpret_cast<const __nv_bfloat162*>(&w.x));
+                b1 = __hmax2(b1, *reinterpret_cast<const __nv_bfloat162*>(&w.y));
+                b2 = __hmax2(b2, *reinterpret_cast<const __nv_bfloat162*>(&w.z));
+                b3 = __hmax2(b3, *reinterpret_cast<const __nv_bfloat162*>(&w.w));
+              }
+            }
+            o.x = *reinterpret_cast<uint32_t*>(&b0);
+            o.y = *reinterpret_cast<uint32_t*>(&b1);
+            o.z = *reinterpret_cast<uint32_t*>(&b2);
+            o.w = *reinterpret_cast<uint32_t*>(&b3);
           }
-          uint4 o;
-          o.x = *reinterpret_cast<uint32_t*>(&b0);
-          o.y = *reinterpret_cast<uint32_t*>(&b1);
-          o.z = *reinterpret_cast<uint32_t*>(&b2);
-          o.w = *reinterpret_cast<uint32_t*>(&b3);
-          __nv_bfloat16* op = p.out + ((static_cast<size_t>(f) * POOL_HW + py) * POOL_HW + px) * COUT + c * 8;
-          *reinterpret_cast<uint4*>(op) = o;
+          const size_t opix = p.flat_out
+              ? (static_cast<size_t>(f) * (POOL_HW + 1) + 1 + py) * (POOL_HW + 2) + pxp
+              : (static_cast<size_t>(f) * POOL_HW + py) * POOL_HW + px;
+          *reinterpret_cast<uint4*>(p.out + opix * COUT + c * 8) = o;
         }
         py_next = py_stop;
         // the next group's ring writes may overwrite pixels this group's pooling just read
         asm volatile("bar.sync 2, 512;" ::: "memory");
+      }
+      if (p.flat_out) {
+        // zero row between frames (written by the frame's second half) and the leading zero row (frame 0)
+        const int zrow = half ? (f + 1) * (POOL_HW + 1) : (f == 0 ? 0 : -1);
+        if (zrow >= 0 && etid < (POOL_HW + 2) * 8)
+          *reinterpret_cast<uint4*>(p.out + (static_cast<size_t>(zrow) * (POOL_HW + 2)) * COUT + etid * 8) =
+              make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }

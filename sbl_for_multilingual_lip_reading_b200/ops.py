@@ -139,22 +139,85 @@ def prep_clip(x, out=None):
     return out, n, t
 
 
-def conv3d_bn_relu_pool(xp, wp, bias, out=None):
-    """prepped clip (out, N, T) of prep_clip -> bf16 NHWC [N*T,22,22,64]."""
+class FlatActs:
+    """Activations in the zero-haloed flat layout of csrc/sblk_flatconv.cuh: `data` is bf16 [rows, C] with pixel
+    (f, y, x) at row (f*(H+1) + 1 + y)*(W+2) + 1 + x and zeros everywhere else."""
+    __slots__ = ("data", "f", "h", "w")
+
+    def __init__(self, data, f, h, w):
+        self.data, self.f, self.h, self.w = data, f, h, w
+
+    @property
+    def c(self):
+        return self.data.shape[1]
+
+    def dense(self):
+        """-> bf16 NHWC [F,H,W,C] copy (tests / debugging; torch indexing only)."""
+        f, h, w, c = self.f, self.h, self.w, self.c
+        v = self.data[(w + 2):(w + 2) + f * (h + 1) * (w + 2)].view(f, h + 1, w + 2, c)
+        return v[:, :h, 1:w + 1, :].contiguous()
+
+
+def flat_rows(f, h, w):
+    return int(_lib.load().sblk_flat_rows(f, h, w))
+
+
+def conv3d_bn_relu_pool(xp, wp, bias, out=None, flat=False):
+    """prepped clip (out, N, T) of prep_clip -> bf16 NHWC [N*T,22,22,64], or FlatActs when flat=True."""
     xp, n, t = xp
     _req(xp, BF16, "xp"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
     if out is None:
-        out = torch.empty((n * t, 22, 22, 64), dtype=BF16, device=xp.device)
+        shape = (flat_rows(n * t, 22, 22), 64) if flat else (n * t, 22, 22, 64)
+        out = torch.empty(shape, dtype=BF16, device=xp.device)
     _req(out, BF16, "out")
     _call("sblk_conv3d_bn_relu_pool_fwd", f"conv3d N={n} T={t}", 2 * 64 * 44 * 44 * 245 * n * t,
-          2 * xp.numel() + 2 * out.numel(), _p(xp), _p(wp), _p(bias), _p(out), n, t, _stream())
-    return out
+          2 * xp.numel() + 2 * out.numel(), _p(xp), _p(wp), _p(bias), _p(out), n, t, 1 if flat else 0, _stream())
+    return FlatActs(out, n * t, 22, 22) if flat else out
+
+
+def pack_flat_weight(wp):
+    """pack_conv2d's bf16 [C,3,3,C] -> [C, 10*C]: the 9 taps followed by a CxC identity (residual via the tensor core)."""
+    _req(wp, BF16, "wp")
+    c = wp.shape[0]
+    if tuple(wp.shape) != (c, 3, 3, c):
+        raise RuntimeError(f"pack_flat_weight: weight shape {tuple(wp.shape)} != {(c, 3, 3, c)}")
+    return torch.cat([wp.view(c, 9 * c), torch.eye(c, dtype=BF16, device=wp.device)], dim=1).contiguous()
+
+
+def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None):
+    """Stride-1 3x3 conv over FlatActs (C -> C, C = 64) -> FlatActs.  wp bf16 [C, 10*C] (pack_flat_weight)."""
+    _req(x.data, BF16, "x"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
+    c = x.c
+    if tuple(wp.shape) != (c, 10 * c):
+        raise RuntimeError(f"conv3x3_flat: weight shape {tuple(wp.shape)} != {(c, 10 * c)} (use pack_flat_weight)")
+    if residual is not None:
+        _req(residual.data, BF16, "residual")
+        if residual.data.shape != x.data.shape:
+            raise RuntimeError("conv3x3_flat: residual shape mismatch")
+    if out is None:
+        out = torch.empty_like(x.data)
+    _req(out, BF16, "out")
+    _call("sblk_flatconv3x3_fwd", f"flatconv3x3 H={x.h} {c}->{c}", 2 * x.f * x.h * x.w * c * 9 * c,
+          2 * (x.data.numel() + wp.numel() + out.numel() + (0 if residual is None else residual.data.numel())),
+          _p(x.data), _p(wp), _p(bias), None if residual is None else _p(residual.data), _p(out), x.f, x.h, x.w, c,
+          1 if relu else 0, _stream())
+    return FlatActs(out, x.f, x.h, x.w)
 
 
 def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
-    """x bf16 NHWC [F,H,W,Cin], wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout]."""
-    _req(x, BF16, "x"); _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
-    f, h, w, cin = x.shape
+    """x bf16 NHWC [F,H,W,Cin] (or FlatActs), wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout]."""
+    _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
+    if isinstance(x, FlatActs):
+        _req(x.data, BF16, "x")
+        f, h, w, cin = x.f, x.h, x.w, x.c
+        xptr = x.data.data_ptr() + (w + 3) * cin * 2           # pixel (0,0,0)
+        row_pitch, frame_pitch = w + 2, (h + 1) * (w + 2)
+        x_elems = x.data.numel()
+    else:
+        _req(x, BF16, "x")
+        f, h, w, cin = x.shape
+        xptr, row_pitch, frame_pitch = x.data_ptr(), 0, 0
+        x_elems = x.numel()
     cout, r, s, cin2 = wp.shape
     if cin2 != cin:
         raise RuntimeError(f"conv2d: Cin mismatch {cin} vs {cin2}")
@@ -162,14 +225,14 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     p = (h + 2 * pad - r) // stride + 1
     q = (w + 2 * pad - s) // stride + 1
     if out is None:
-        out = torch.empty((f, p, q, cout), dtype=BF16, device=x.device)
+        out = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
     _req(out, BF16, "out")
     if residual is not None and residual.numel() != out.numel():
         raise RuntimeError("conv2d: residual shape mismatch")
     _call("sblk_conv2d_igemm_fwd", f"conv{r}x{s} H={h} {cin}->{cout} s{stride}", 2 * f * p * q * cout * r * s * cin,
-          2 * (x.numel() + wp.numel() + out.numel() + (0 if residual is None else residual.numel())),
-          _p(x), _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout, r, s, stride, pad, 1 if relu else 0,
-          _stream())
+          2 * (x_elems + wp.numel() + out.numel() + (0 if residual is None else residual.numel())),
+          xptr, _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout, r, s, stride, pad, 1 if relu else 0,
+          row_pitch, frame_pitch, _stream())
     return out
 
 

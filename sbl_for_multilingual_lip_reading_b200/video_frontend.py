@@ -164,6 +164,8 @@ class Lipreading(nn.Module):
                 w1, b1 = fold(blk.conv1, blk.bn1)
                 w2, b2 = fold(blk.conv2, blk.bn2)
                 ds = fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                if layer is self.resnet18.layer1:  # flat shifted-window kernel: taps + identity (residual) packing
+                    w1, w2 = ops.pack_flat_weight(w1), ops.pack_flat_weight(w2)
                 pk.blocks.append((blk.stride, w1, b1, w2, b2, ds))
         self._packed = pk
         return pk
@@ -186,8 +188,14 @@ class Lipreading(nn.Module):
         pk = self._get_packed()
         with torch.cuda.device(x.device):
             xp = ops.prep_clip(x)
-            a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b)
+            # layer1 (64 -> 64, stride 1) runs on the zero-haloed flat layout (flat shifted-window kernel);
+            # from layer2 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
+            a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
             for (stride, w1, b1, w2, b2, ds) in pk.blocks:
+                if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
+                    y = ops.conv3x3_flat(a, w1, b1, relu=True)
+                    a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
+                    continue
                 y = ops.conv2d(a, w1, b1, stride=stride, relu=True)
                 res = a if ds is None else ops.conv2d(a, ds[0], ds[1], stride=stride, relu=False)
                 a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)

@@ -145,17 +145,23 @@ def test_oracle_basic_block_chain(frontend, dev):
     with torch.no_grad():
         y = O.frontend3d(x, sd).transpose(1, 2).contiguous().view(-1, 64, 22, 22)
         pk = frontend._get_packed()
-        a = ops.conv3d_bn_relu_pool(ops.prep_clip(x.to(dev)), pk.c3w, pk.c3b)
-        assert rel_fro(a.permute(0, 3, 1, 2), y) < REL_TOL
+        a = ops.conv3d_bn_relu_pool(ops.prep_clip(x.to(dev)), pk.c3w, pk.c3b, flat=True)   # zero-haloed flat layout
+        assert rel_fro(a.dense().permute(0, 3, 1, 2), y) < REL_TOL
         bi = 0
         for li, stride in ((1, 1), (2, 2), (3, 2), (4, 2)):
             for b in range(2):
                 y = O.basic_block(y, sd, f"resnet18.layer{li}.{b}", stride if b == 0 else 1, b == 0 and li != 1)
                 (st, w1, b1, w2, b2, ds) = pk.blocks[bi]
-                h = ops.conv2d(a, w1, b1, stride=st, relu=True)
-                res = a if ds is None else ops.conv2d(a, ds[0], ds[1], stride=st, relu=False)
-                a = ops.conv2d(h, w2, b2, stride=1, relu=True, residual=res)
-                assert rel_fro(a.permute(0, 3, 1, 2), y) < REL_TOL, f"layer{li}.{b}"
+                if li == 1:   # flat shifted-window kernel, residual accumulated by the tensor core
+                    h = ops.conv3x3_flat(a, w1, b1, relu=True)
+                    a = ops.conv3x3_flat(h, w2, b2, relu=True, residual=a)
+                    got = a.dense()
+                else:         # TMA-im2col kernel (layer2.0 reads the flat layout through pitched strides)
+                    h = ops.conv2d(a, w1, b1, stride=st, relu=True)
+                    res = a if ds is None else ops.conv2d(a, ds[0], ds[1], stride=st, relu=False)
+                    a = ops.conv2d(h, w2, b2, stride=1, relu=True, residual=res)
+                    got = a
+                assert rel_fro(got.permute(0, 3, 1, 2), y) < REL_TOL, f"layer{li}.{b}"
                 bi += 1
 
 
@@ -249,3 +255,44 @@ def test_config2_linearity_of_conv_stage(frontend, dev):
     ref = torch.einsum("ptc,otc->po", patches.double(), w.float().cpu().reshape(64, 9, 64).double())
     got = a.reshape(-1, 64)[idx.to(dev)].float().cpu().double()
     assert ((got - ref).norm() / ref.norm()).item() < 5e-3
+
+
+def _to_flat(x):
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    f, h, w, c = x.shape
+    data = torch.zeros(ops.flat_rows(f, h, w), c, dtype=torch.bfloat16, device=x.device)
+    v = data[(w + 2):(w + 2) + f * (h + 1) * (w + 2)].view(f, h + 1, w + 2, c)
+    v[:, :h, 1:w + 1, :] = x
+    return ops.FlatActs(data, f, h, w)
+
+
+def test_config2_flat_conv_properties(dev):
+    """Flat shifted-window conv at the full layer-1 size (928 frames): linearity (exact for power-of-two scaling),
+    zero halos, residual exactness (R*I on the tensor core), agreement with the im2col kernel and an fp64 spot check."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(928, 22, 22, 64, generator=g).to(torch.bfloat16).to(dev)
+    w = (torch.randn(64, 3, 3, 64, generator=g) / 24).to(torch.bfloat16).to(dev)
+    wf = ops.pack_flat_weight(w)
+    zero = torch.zeros(64, device=dev)
+    xf, xf4 = _to_flat(x), _to_flat(x * 4)
+    a = ops.conv3x3_flat(xf, wf, zero, relu=False)
+    b = ops.conv3x3_flat(xf4, wf, zero, relu=False)
+    assert torch.equal(a.dense().float() * 4, b.dense().float())
+    # halo rows / columns are exactly zero
+    d = a.data.float().clone()
+    d[24:24 + 928 * 23 * 24].view(928, 23, 24, 64)[:, :22, 1:23, :] = 0
+    assert bool((d == 0).all())
+    # same numbers as the TMA-im2col kernel on the dense layout (both accumulate in fp32, different order)
+    ref = ops.conv2d(x, w, zero, relu=False)
+    assert rel_fro(a.dense(), ref) < 1e-3
+    # residual through the identity MMA == adding it afterwards in fp32 and rounding once
+    r = ops.conv3x3_flat(xf, wf, zero, relu=True, residual=xf)
+    idx = torch.randint(0, 928 * 484, (4096,), generator=g)
+    f, yy, xx = idx // 484, (idx % 484) // 22, idx % 22
+    xp = torch.nn.functional.pad(x.float().cpu(), (0, 0, 1, 1, 1, 1))
+    patches = torch.stack([xp[f, yy + rr, xx + ss] for rr in range(3) for ss in range(3)], dim=1)
+    conv = torch.einsum("ptc,otc->po", patches.double(), w.float().cpu().reshape(64, 9, 64).double())
+    want = torch.relu(conv + x.float().cpu().reshape(-1, 64)[idx].double())
+    got = r.dense().reshape(-1, 64)[idx.to(dev)].float().cpu().double()
+    assert ((got - want).norm() / want.norm()).item() < 5e-3

@@ -251,6 +251,63 @@ def conv3d_ref(x, w3, gam, bet, mu, var):
     return y.permute(0, 2, 3, 4, 1).reshape(n * t, h, w, c)
 
 
+def to_flat(x):
+    """dense bf16 NHWC [F,H,W,C] -> ops.FlatActs (torch indexing; test helper)."""
+    f, h, w, c = x.shape
+    data = torch.zeros(ops.flat_rows(f, h, w), c, dtype=torch.bfloat16, device=x.device)
+    v = data[(w + 2):(w + 2) + f * (h + 1) * (w + 2)].view(f, h + 1, w + 2, c)
+    v[:, :h, 1:w + 1, :] = x
+    return ops.FlatActs(data, f, h, w)
+
+
+def halo_is_zero(fa):
+    f, h, w, c = fa.f, fa.h, fa.w, fa.c
+    d = fa.data.float().clone()
+    v = d[(w + 2):(w + 2) + f * (h + 1) * (w + 2)].view(f, h + 1, w + 2, c)
+    v[:, :h, 1:w + 1, :] = 0
+    return bool((d == 0).all())
+
+
+def sec_flat():
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for (Fr, H) in [(1, 22), (3, 22), (29, 22), (64, 22), (7, 11), (928, 22)]:
+        x = bf(torch.randn(Fr, H, H, 64, generator=g)).to(DEV)
+        w = (torch.randn(64, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
+        gam = (torch.rand(64, generator=g) + 0.5).to(DEV)
+        bet = (torch.randn(64, generator=g) * 0.1).to(DEV)
+        mu = (torch.randn(64, generator=g) * 0.1).to(DEV)
+        var = (torch.rand(64, generator=g) + 0.5).to(DEV)
+        wp, bias = ops.pack_conv2d(w, gam, bet, mu, var)
+        xf = to_flat(x)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().permute(0, 3, 1, 2), bias, padding=1)
+        wpf = ops.pack_flat_weight(wp)
+        out = ops.conv3x3_flat(xf, wpf, bias, relu=True)
+        torch.cuda.synchronize()
+        report(f"flatconv F{Fr} H{H} relu", out.dense(), bf(torch.relu(ref).permute(0, 2, 3, 1)))
+        if not halo_is_zero(out):
+            print("[BAD] halo not zero"); FAILS.append("halo")
+        out2 = ops.conv3x3_flat(xf, wpf, bias, relu=True, residual=xf)
+        report(f"flatconv F{Fr} H{H} +res+relu", out2.dense(),
+               bf(torch.relu(ref + x.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)))
+        if not halo_is_zero(out2):
+            print("[BAD] halo not zero (res)"); FAILS.append("halo")
+        # strided im2col conv on the flat layout == on the dense layout
+        w2 = (torch.randn(128, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
+        wp2, b2 = ops.pack_conv2d(w2)
+        report(f"conv s2 on flat F{Fr} H{H}", ops.conv2d(xf, wp2, b2, stride=2), ops.conv2d(x, wp2, b2, stride=2))
+    # stem flat output == dense output
+    w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / (245 ** 0.5)).to(DEV)
+    one, zero = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
+    wp3, b3 = ops.pack_conv3d(w3, one, zero, zero, one)
+    xin = torch.randn(2, 1, 7, 88, 88, generator=g).to(DEV)
+    xp = ops.prep_clip(xin)
+    dense = ops.conv3d_bn_relu_pool(xp, wp3, b3)
+    flat = ops.conv3d_bn_relu_pool(xp, wp3, b3, flat=True)
+    report("stem flat vs dense", flat.dense(), dense, tol=1e-6)
+    if not halo_is_zero(flat):
+        print("[BAD] stem halo not zero"); FAILS.append("stemhalo")
+
+
 def sec_conv3d():
     g = torch.Generator(device="cpu").manual_seed(4)
     w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / (245 ** 0.5)).to(DEV)
@@ -310,6 +367,17 @@ def sec_perf():
         w = bf(torch.randn(N, K, generator=g)).to(DEV)
         ms = timeit(lambda: ops.gemm(a, w, out_bf16=True))
         print(f"perf gemm M{M} N{N} K{K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    xd = bf(torch.randn(928, 22, 22, 64, generator=g)).to(DEV)
+    xf = to_flat(xd)
+    wf = ops.pack_flat_weight(bf(torch.randn(64, 3, 3, 64, generator=g) / 24).to(DEV))
+    bfz = torch.zeros(64, device=DEV)
+    of = torch.empty_like(xf.data)
+    ms = timeit(lambda: ops.conv3x3_flat(xf, wf, bfz, relu=True, residual=xf, out=of))
+    print(f"perf flatconv H22 64->64 (+res): {ms * 1e3:.1f} us  {2.0 * 928 * 484 * 64 * 576 / ms / 1e9:.1f} TFLOP/s",
+          flush=True)
+    ms = timeit(lambda: ops.conv3x3_flat(xf, wf, bfz, relu=True, out=of))
+    print(f"perf flatconv H22 64->64 (no res): {ms * 1e3:.1f} us  {2.0 * 928 * 484 * 64 * 576 / ms / 1e9:.1f} TFLOP/s",
+          flush=True)
     w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / 16).to(DEV)
     one = torch.ones(64, device=DEV)
     zero = torch.zeros(64, device=DEV)
@@ -332,7 +400,7 @@ if __name__ == "__main__":
         ops.set_pdl(True)
         print("PDL enabled")
     try:
-        {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d,
+        {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d, "flat": sec_flat,
          "perf": sec_perf}[sec]()
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001

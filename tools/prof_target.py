@@ -30,6 +30,18 @@ elif what in ("l1conv", "l2conv", "l3conv", "l4conv"):
     out = torch.empty(928, H, H, C, dtype=bf, device=dev)
     for _ in range(iters):
         ops.conv2d(x, w, bias, relu=True, residual=x, out=out)
+if what == "flat":
+    F_, H = 928, 22
+    rows = ops.flat_rows(F_, H, H)
+    data = torch.zeros(rows, 64, dtype=bf, device=dev)
+    v = data[(H + 2):(H + 2) + F_ * (H + 1) * (H + 2)].view(F_, H + 1, H + 2, 64)
+    v[:, :H, 1:H + 1, :] = torch.randn(F_, H, H, 64, generator=g).to(bf).to(dev)
+    xf = ops.FlatActs(data, F_, H, H)
+    w = ops.pack_flat_weight((torch.randn(64, 3, 3, 64, generator=g) / 24).to(bf).to(dev))
+    bias = torch.zeros(64, device=dev)
+    out = torch.empty_like(data)
+    for _ in range(iters):
+        ops.conv3x3_flat(xf, w, bias, relu=True, residual=xf, out=out)
 if what == "forward":
     # whole hot path, eager (one launch per kernel), BASELINE configs[1] shape: 32 clips x 29 frames
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
