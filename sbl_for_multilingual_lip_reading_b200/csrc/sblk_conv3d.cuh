@@ -105,7 +105,7 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int num_units = p.frames * 2;
 
@@ -127,33 +127,36 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
 
   grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
   grid_dep_wait();
 
   if (warp == 0) {
     // ------------------------------------------------ loader: weights once, then (group, dt) stages
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&weights_bar, B_BYTES);
 #pragma unroll
       for (int j = 0; j < 5; ++j) tma_load_2d(smem + OFF_B + j * (COUT * 128), &tmW, &weights_bar, j * 64, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      const int TP = p.T + 2 * TPAD;
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        const int f = u >> 1;
-        const int half = u & 1;
-        const int n = f / p.T;
-        const int t = f - n * p.T;
-        const int m_start = half ? HALF1_ROW * CONV_HW - HALF1_OFF : 0;
-        for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
-          const int m0 = m_start + g * GROUP_PIX;
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    const int TP = p.T + 2 * TPAD;
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      const int f = u >> 1;
+      const int half = u & 1;
+      const int n = f / p.T;
+      const int t = f - n * p.T;
+      const int m_start = half ? HALF1_ROW * CONV_HW - HALF1_OFF : 0;
+      for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
+        const int m0 = m_start + g * GROUP_PIX;
 #pragma unroll 1
-          for (int dt = 0; dt < 5; ++dt) {
-            mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0201);
-            uint8_t* dst = smem + OFF_A + stage * A_STAGE_BYTES;
-            const uint4* src = p.x8 + static_cast<size_t>(n * TP + t + dt) * FRAME_ENTRIES + m0;
+        for (int dt = 0; dt < 5; ++dt) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0201);
+          uint8_t* dst = smem + OFF_A + stage * A_STAGE_BYTES;
+          const uint4* src = p.x8 + static_cast<size_t>(n * TP + t + dt) * FRAME_ENTRIES + m0;
+          if (elect_one()) {
             if (p.debug_mode == 2) {
               mbar_arrive(&full_bar[stage]);
             } else {
@@ -161,33 +164,34 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
               bulk_load(dst, src, STAGE_PLANE_BYTES, &full_bar[stage]);
               bulk_load(dst + STAGE_PLANE_BYTES, src + PLANE_ENTRIES, STAGE_PLANE_BYTES, &full_bar[stage]);
             }
-            if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
           }
+          __syncwarp();
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      mbar_wait(&weights_bar, 0, 0x0202);
-      int stage = 0;
-      uint32_t phase = 0;
-      int set = 0;
-      uint32_t set_phase = 0;
-      const uint64_t db0 = make_desc_sw128(smem_base + OFF_B);
-      for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
-        for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
-          mbar_wait(&tempty_bar[set], set_phase ^ 1u, 0x0203);
-          tc_fence_after_sync();
+    // ------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)
+    mbar_wait(&weights_bar, 0, 0x0202);
+    int stage = 0;
+    uint32_t phase = 0;
+    int set = 0;
+    uint32_t set_phase = 0;
+    const uint64_t db0 = make_desc_sw128(smem_base + OFF_B);
+    for (int u = blockIdx.x; u < num_units; u += gridDim.x) {
+      for (int g = 0; g < GROUPS_PER_UNIT; ++g) {
+        mbar_wait(&tempty_bar[set], set_phase ^ 1u, 0x0203);
+        tc_fence_after_sync();
 #pragma unroll 1
-          for (int dt = 0; dt < 5; ++dt) {
-            mbar_wait(&full_bar[stage], phase, 0x0204);
-            tc_fence_after_sync();
-            const uint32_t a_base = smem_base + OFF_A + stage * A_STAGE_BYTES;
-            // descriptors differ only in the low word (start address >> 4): one 32-bit add per operand per MMA
-            const uint64_t da0 = make_desc_kmajor_noswizzle(a_base, STAGE_PLANE_BYTES, 128);
-            const uint32_t da0_lo = static_cast<uint32_t>(da0);
-            const uint32_t db_lo = static_cast<uint32_t>(db0) + static_cast<uint32_t>((dt * COUT * 128) >> 4);
+        for (int dt = 0; dt < 5; ++dt) {
+          mbar_wait(&full_bar[stage], phase, 0x0204);
+          tc_fence_after_sync();
+          const uint32_t a_base = smem_base + OFF_A + stage * A_STAGE_BYTES;
+          // descriptors differ only in the low word (start address >> 4): one 32-bit add per operand per MMA
+          const uint64_t da0 = make_desc_kmajor_noswizzle(a_base, STAGE_PLANE_BYTES, 128);
+          const uint32_t da0_lo = static_cast<uint32_t>(da0);
+          const uint32_t db_lo = static_cast<uint32_t>(db0) + static_cast<uint32_t>((dt * COUT * 128) >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < TILES_PER_GROUP; ++j) {
               if (p.debug_mode == 1) break;
@@ -200,11 +204,12 @@ conv3d_bn_relu_pool_kernel(const __grid_constant__ CUtensorMap tmW, const Conv3d
               }
             }
             umma_commit(&empty_bar[stage]);
-            if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
+            if (dt == 4) umma_commit(&tfull_bar[set]);
           }
-          umma_commit(&tfull_bar[set]);
-          if (++set == 2) { set = 0; set_phase ^= 1u; }
+          __syncwarp();
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
         }
+        if (++set == 2) { set = 0; set_phase ^= 1u; }
       }
     }
   } else {

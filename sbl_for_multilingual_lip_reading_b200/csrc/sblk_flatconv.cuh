@@ -113,16 +113,19 @@ flatconv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 
   if (warp == 0) {
     // ------------------------------------------------ loader: filter once, then one stage per tile
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(&weights_bar, W_BYTES);
 #pragma unroll
       for (int t = 0; t < W_TAPS; ++t) tma_load_2d(smem + OFF_W + t * (C * 128), &tmW, &weights_bar, t * 64, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += TILES_PER_STAGE) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0301);
-        uint8_t* dst = smem + OFF_A + stage * STAGE_BYTES;
-        const int px0 = tile * TILE_M - (Wp + 1);   // may be negative / run past the end: TMA zero-fills
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0301);
+      uint8_t* dst = smem + OFF_A + stage * STAGE_BYTES;
+      const int px0 = tile * TILE_M - (Wp + 1);   // may be negative / run past the end: TMA zero-fills
+      if (elect_one()) {
         if (p.debug_mode & 1) {
           mbar_arrive(&full_bar[stage]);
         } else {
@@ -130,8 +133,9 @@ flatconv3x3_c64_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           tma_load_2d(dst, &tmX, &full_bar[stage], 0, px0);
           if (p.has_res) tma_load_2d(dst + A_BOX_BYTES, &tmR, &full_bar[stage], 0, tile * TILE_M);
         }
-        if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
       }
+      __syncwarp();
+      if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (warp-uniform control flow, one elected lane issues)

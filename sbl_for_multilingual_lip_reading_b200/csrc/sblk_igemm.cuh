@@ -67,7 +67,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
 
   const int n_tiles = p.N / BLOCK_N;
@@ -94,36 +94,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
 
   // Everything above overlaps the tail of the previous kernel under PDL; inputs are read below.
   grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
   grid_dep_wait();
 
   if (warp == 0) {
-    // ------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles;
-        const int n_blk = tile - m_blk * n_tiles;
-        const int m0 = m_blk * Cfg::BLOCK_M;
-        int img = 0, base_w = 0, base_h = 0;
-        if (IM2COL) {
-          const int pq = p.P * p.Q;
-          img = m0 / pq;
-          const int rem = m0 - img * pq;
-          const int ph = rem / p.Q;
-          const int qw = rem - ph * p.Q;
-          base_w = qw * p.stride - p.pad;
-          base_h = ph * p.stride - p.pad;
-        }
-        int tap = 0, cb = 0, r = 0, s = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0101);
-          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+    // ------------------------------------------------ TMA producer (warp-uniform control flow, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int m0 = m_blk * Cfg::BLOCK_M;
+      int img = 0, base_w = 0, base_h = 0;
+      if (IM2COL) {
+        const int pq = p.P * p.Q;
+        img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int ph = rem / p.Q;
+        const int qw = rem - ph * p.Q;
+        base_w = qw * p.stride - p.pad;
+        base_h = ph * p.stride - p.pad;
+      }
+      int cb = 0, r = 0, s = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0101);
+        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           if (IM2COL) {
             tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], cb * 64, base_w, base_h, img,
@@ -132,44 +132,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * 64, m0);
           }
           tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
-          if (++cb == p.cblocks) {
-            cb = 0;
-            ++tap;
-            if (++s == p.taps_s) { s = 0; ++r; }
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
+        __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++s == p.taps_s) { s = 0; ++r; }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x0102);
+    // ------------------------------------------------ MMA issuer (warp-uniform, one elected lane issues)
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x0102);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 0x0103);
         tc_fence_after_sync();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, 0x0103);
-          tc_fence_after_sync();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint64_t da = make_desc_sw128(a_addr);
-          const uint64_t db = make_desc_sw128(a_addr + Cfg::A_BYTES);
+        const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint64_t da = make_desc_sw128(a_addr);
+        const uint64_t db = make_desc_sw128(a_addr + Cfg::A_BYTES);
+        const uint32_t da_lo = static_cast<uint32_t>(da), db_lo = static_cast<uint32_t>(db);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
             // advance 16 bf16 = 32 B inside the 128-B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), IDESC,
+            umma_bf16(d_tmem, desc_with_lo(da, da_lo + 2 * k), desc_with_lo(db, db_lo + 2 * k), IDESC,
                       (kb > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees this smem slot once the MMAs above retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   } else {
     // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
