@@ -172,8 +172,12 @@ int pick_block_n(int m_tiles, int N, int num_sms) {
 }
 
 template <bool IM2COL>
-int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, const sblk::IgemmParams& p, int num_sms,
+int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::IgemmParams p, int num_sms,
                  cudaStream_t stream) {
+  {
+    const char* dm = getenv("SBLK_IGEMM_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    p.debug_mode = dm ? atoi(dm) : 0;
+  }
   const int m_tiles = (p.M + 127) / 128;
   const int tiles = m_tiles * (p.N / bn);
   const int grid = tiles < num_sms ? tiles : num_sms;

@@ -32,6 +32,7 @@ struct IgemmParams {
   const __nv_bfloat16* residual;   // [M, ldo] bf16 or nullptr
   __nv_bfloat16* out_bf16;         // [M, ldo] or nullptr
   float* out_f32;                  // [M, ldo] or nullptr
+  int debug_mode;                  // timing experiments only: bit0 = skip B loads, bit1 = skip A loads
 };
 
 template <int BLOCK_N>
@@ -124,14 +125,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (IM2COL) {
-            tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], cb * 64, base_w, base_h, img,
-                               static_cast<uint16_t>(s), static_cast<uint16_t>(r));
-          } else {
-            tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * 64, m0);
+          mbar_arrive_expect_tx(&full_bar[stage], ((p.debug_mode & 2) ? 0 : Cfg::A_BYTES) +
+                                                      ((p.debug_mode & 1) ? 0 : Cfg::B_BYTES));
+          if (!(p.debug_mode & 2)) {
+            if (IM2COL) {
+              tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], cb * 64, base_w, base_h, img,
+                                 static_cast<uint16_t>(s), static_cast<uint16_t>(r));
+            } else {
+              tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * 64, m0);
+            }
           }
-          tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
+          if (!(p.debug_mode & 1)) tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
         }
         __syncwarp();
         if (++cb == p.cblocks) {

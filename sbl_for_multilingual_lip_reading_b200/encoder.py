@@ -107,12 +107,21 @@ class Encoder(nn.Module):
             EncoderLayer(d_model, d_inner, n_head, d_k, d_v, dropout=dropout) for _ in range(n_layers)])
         self._packed = None
         self._len_cache = {}
+        self._streams = {}
+        self.parallel_chains = 4   # clip groups run as concurrent kernel chains (1 = single chain)
 
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"] = None
         st["_len_cache"] = {}
+        st["_streams"] = {}
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.__dict__.setdefault("_streams", {})
+        self.__dict__.setdefault("_len_cache", {})
+        self.__dict__.setdefault("parallel_chains", 4)
 
     # ------------------------------------------------------------------------------------------
     def _check_config(self):
@@ -150,6 +159,42 @@ class Encoder(nn.Module):
         self._packed = pk
         return pk
 
+    def _side_streams(self, device, k):
+        key = str(device)
+        pool = self._streams.setdefault(key, [])
+        while len(pool) < k:
+            pool.append(torch.cuda.Stream(device=device))
+        return pool[:k]
+
+    def _run_chain(self, x, out, pk, n0, n1, t, lengths, return_attns, attns):
+        """The whole encoder stack for clips [n0, n1) on the current stream; writes rows of `out` (fp32 [N*T, d])."""
+        nc = n1 - n0
+        xs = x[n0 * t:n1 * t]
+        lens_c = None if lengths is None else lengths[n0:n1]
+        pe = self.positional_encoding.pe[0]
+        last = len(self.layer_stack) - 1
+        x16 = ops.cast_bf16(xs)
+        _, h32 = ops.gemm(x16, pk.w_in, bias=self.linear_in.bias.detach(), out_f32=True)
+        # encoder.py:53-55 — LN(linear_in(x)) + PE ; no pad mask at this point
+        x32, x16 = ops.add_layernorm(h32, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
+                                     pe=pe, T=t, eps=self.layer_norm_in.eps,
+                                     out_f32=out[n0 * t:n1 * t] if last < 0 else None)
+        for li, (lyr, w) in enumerate(zip(self.layer_stack, pk.layers)):
+            a, f = lyr.slf_attn, lyr.pos_ffn
+            qkv16, _ = ops.gemm(x16, w["wqkv"], bias=w["bqkv"], out_bf16=True)
+            att16, probs = ops.attention(qkv16, nc, t, self.n_head, self.d_k, lengths=lens_c,
+                                         want_probs=return_attns, scale=1.0 / a.temperature)
+            _, o32 = ops.gemm(att16, w["wfc"], bias=a.fc.bias.detach(), out_f32=True)
+            x32, x16 = ops.add_layernorm(o32, a.layer_norm.weight.detach(), a.layer_norm.bias.detach(),
+                                         residual=x32, lengths=lens_c, T=t, eps=a.layer_norm.eps)
+            h16, _ = ops.gemm(x16, w["w1"], bias=f.w_1.bias.detach(), relu=True, out_bf16=True)
+            _, o32 = ops.gemm(h16, w["w2"], bias=f.w_2.bias.detach(), out_f32=True)
+            x32, x16 = ops.add_layernorm(o32, f.layer_norm.weight.detach(), f.layer_norm.bias.detach(),
+                                         residual=x32, lengths=lens_c, T=t, eps=f.layer_norm.eps,
+                                         want_bf16=li != last, out_f32=out[n0 * t:n1 * t] if li == last else None)
+            if return_attns:
+                attns.append(probs)
+
     def forward(self, padded_input, input_lengths, return_attns=False):
         """padded_input: N x T x d_input (fp32, CUDA); input_lengths: N ints -> (enc_output N x T x d_model,)"""
         self._check_config()
@@ -182,27 +227,32 @@ class Encoder(nn.Module):
                         self._len_cache.clear()
                     lengths = torch.tensor(lens, dtype=torch.int32, device=x.device)
                     self._len_cache[ck] = lengths
-            pe = self.positional_encoding.pe[0]
+            out = torch.empty((m, self.d_model), dtype=torch.float32, device=x.device)
             attns = []
-            x16 = ops.cast_bf16(x)
-            _, h32 = ops.gemm(x16, pk.w_in, bias=self.linear_in.bias.detach(), out_f32=True)
-            # encoder.py:53-55 — LN(linear_in(x)) + PE ; no pad mask at this point
-            x32, x16 = ops.add_layernorm(h32, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
-                                         pe=pe, T=t, eps=self.layer_norm_in.eps)
-            for lyr, w in zip(self.layer_stack, pk.layers):
-                a, f = lyr.slf_attn, lyr.pos_ffn
-                qkv16, _ = ops.gemm(x16, w["wqkv"], bias=w["bqkv"], out_bf16=True)
-                att16, probs = ops.attention(qkv16, n, t, self.n_head, self.d_k, lengths=lengths,
-                                             want_probs=return_attns, scale=1.0 / a.temperature)
-                _, o32 = ops.gemm(att16, w["wfc"], bias=a.fc.bias.detach(), out_f32=True)
-                x32, x16 = ops.add_layernorm(o32, a.layer_norm.weight.detach(), a.layer_norm.bias.detach(),
-                                             residual=x32, lengths=lengths, T=t, eps=a.layer_norm.eps)
-                h16, _ = ops.gemm(x16, w["w1"], bias=f.w_1.bias.detach(), relu=True, out_bf16=True)
-                _, o32 = ops.gemm(h16, w["w2"], bias=f.w_2.bias.detach(), out_f32=True)
-                x32, x16 = ops.add_layernorm(o32, f.layer_norm.weight.detach(), f.layer_norm.bias.detach(),
-                                             residual=x32, lengths=lengths, T=t, eps=f.layer_norm.eps)
-                if return_attns:
-                    attns.append(probs)
+            # Clips are independent through the whole stack (attention is per clip, LayerNorm per token), and at
+            # BASELINE batch sizes every kernel of the stack is latency-bound (~3 us fixed cost x 43 launches), so
+            # the batch is split into a few clip groups whose kernel chains run concurrently on side streams
+            # (fork / join with events: capturable into a CUDA graph as parallel branches).
+            groups = 1 if return_attns else max(1, min(self.parallel_chains, n // 4))
+            if groups == 1:
+                self._run_chain(x, out, pk, 0, n, t, lengths, return_attns, attns)
+            else:
+                main = torch.cuda.current_stream()
+                side = self._side_streams(x.device, groups - 1)
+                fork = torch.cuda.Event()
+                fork.record(main)
+                bounds = [(g * n) // groups for g in range(groups + 1)]
+                for g in range(groups):
+                    st = main if g == 0 else side[g - 1]
+                    if g > 0:
+                        st.wait_event(fork)
+                    with torch.cuda.stream(st):
+                        self._run_chain(x, out, pk, bounds[g], bounds[g + 1], t, lengths, False, attns)
+                for g in range(1, groups):
+                    ev = torch.cuda.Event()
+                    ev.record(side[g - 1])
+                    main.wait_event(ev)
+            x32 = out
         enc_output = x32.view(n, t, self.d_model)
         if return_attns:
             return enc_output, attns

@@ -264,11 +264,13 @@ def gemm(a, w, bias=None, residual=None, relu=False, out_bf16=False, out_f32=Fal
 
 
 def add_layernorm(x, gamma, beta, residual=None, pe=None, lengths=None, T=1, eps=1e-5, want_f32=True,
-                  want_bf16=True):
+                  want_bf16=True, out_f32=None):
     _req(x, F32, "x"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta"); _req(residual, F32, "residual")
-    _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths")
+    _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths"); _req(out_f32, F32, "out_f32")
     m, d = x.shape
-    o32 = torch.empty((m, d), dtype=F32, device=x.device) if want_f32 else None
+    if out_f32 is not None and tuple(out_f32.shape) != (m, d):
+        raise RuntimeError(f"add_layernorm: out_f32 shape {tuple(out_f32.shape)} != {(m, d)}")
+    o32 = out_f32 if out_f32 is not None else (torch.empty((m, d), dtype=F32, device=x.device) if want_f32 else None)
     o16 = torch.empty((m, d), dtype=BF16, device=x.device) if want_bf16 else None
     _call("sblk_add_layernorm_fwd", "add_layernorm", 0,
           m * d * (4 + (4 if residual is not None else 0) + (4 if want_f32 else 0) + (2 if want_bf16 else 0)),
