@@ -78,6 +78,14 @@ int sblk_conv2d_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const f
                           const void* residual_bf16, void* out_bf16, int F, int H, int W, int Cin, int Cout,
                           int R, int S, int stride, int pad, int relu, int in_row_pitch, int in_frame_pitch,
                           void* stream);
+/* BasicBlock head of layers 2-4 in one launch: out = relu(conv3x3_stride_s(x) + bias) and the downsample branch
+ * out_ds = conv1x1_stride_s(x) + bias_ds.  The 1x1 conv reads exactly the centre-tap A tiles of the 3x3 conv, so
+ * both share one pass over x (second TMEM accumulator).  w_ds_packed is [Cout][1][1][Cin]; Cout % 128 == 0.
+ * replaces: BasicBlock.conv1/bn1/relu + downsample(conv1x1, bn), transformer/video_frontend.py:30-32,35-36,68-72 */
+int sblk_conv2d_dual_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const float* bias,
+                               const void* w_ds_packed_bf16, const float* bias_ds, void* out_bf16, void* out_ds_bf16,
+                               int F, int H, int W, int Cin, int Cout, int stride, int relu, int in_row_pitch,
+                               int in_frame_pitch, void* stream);
 /* bf16 NHWC [F,HW,C] -> mean over HW: fp32 [F,C] and/or bf16 [F,C] (either may be NULL).
  * replaces: nn.AdaptiveAvgPool2d(1) + view, transformer/video_frontend.py:87-88 */
 int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);

@@ -108,6 +108,7 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<64, true>, sblk::IgemmCfg<64>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<128, true>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, true>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::igemm_kernel<128, true, true>, sblk::IgemmCfg<128, true>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<64, false>, sblk::IgemmCfg<64>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
@@ -184,13 +185,13 @@ int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::I
   switch (bn) {
     case 64:
       return launch(sblk::igemm_kernel<64, IM2COL>, dim3(grid), dim3(192), sblk::IgemmCfg<64>::SMEM_BYTES, stream,
-                    true, "igemm_kernel<64>", tmA, tmB, p);
+                    true, "igemm_kernel<64>", tmA, tmB, tmB, p);
     case 128:
       return launch(sblk::igemm_kernel<128, IM2COL>, dim3(grid), dim3(192), sblk::IgemmCfg<128>::SMEM_BYTES, stream,
-                    true, "igemm_kernel<128>", tmA, tmB, p);
+                    true, "igemm_kernel<128>", tmA, tmB, tmB, p);
     case 256:
       return launch(sblk::igemm_kernel<256, IM2COL>, dim3(grid), dim3(192), sblk::IgemmCfg<256>::SMEM_BYTES, stream,
-                    true, "igemm_kernel<256>", tmA, tmB, p);
+                    true, "igemm_kernel<256>", tmA, tmB, tmB, p);
     default:
       return fail(-11, "no BLOCK_N for N=%d", p.N);
   }
@@ -362,9 +363,33 @@ int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const
                 static_cast<cudaStream_t>(stream), true, "flatconv3x3_c64_kernel", tmX, tmW, tmR, p);
 }
 
+static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
+                             int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                             int in_row_pitch, int in_frame_pitch, const void* wp_ds, const float* bias_ds,
+                             void* out_ds, void* stream);
+
 int sblk_conv2d_igemm_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                           int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                           int in_row_pitch, int in_frame_pitch, void* stream) {
+  return conv2d_igemm_impl(x, wp, bias, residual, out, F, H, W, Cin, Cout, R, S, stride, pad, relu, in_row_pitch,
+                           in_frame_pitch, nullptr, nullptr, nullptr, stream);
+}
+
+int sblk_conv2d_dual_igemm_fwd(const void* x, const void* wp, const float* bias, const void* wp_ds,
+                               const float* bias_ds, void* out, void* out_ds, int F, int H, int W, int Cin, int Cout,
+                               int stride, int relu, int in_row_pitch, int in_frame_pitch, void* stream) {
+  if (!wp_ds || !bias_ds || !out_ds || !bias) return fail(-1, "sblk_conv2d_dual_igemm_fwd: null pointer");
+  if (!aligned16(wp_ds) || !aligned16(bias_ds) || !aligned16(out_ds))
+    return fail(-1, "sblk_conv2d_dual_igemm_fwd: pointers must be 16-byte aligned");
+  if (Cout % 128 != 0) return fail(-1, "sblk_conv2d_dual_igemm_fwd: Cout=%d must be a multiple of 128", Cout);
+  return conv2d_igemm_impl(x, wp, bias, nullptr, out, F, H, W, Cin, Cout, 3, 3, stride, 1, relu, in_row_pitch,
+                           in_frame_pitch, wp_ds, bias_ds, out_ds, stream);
+}
+
+static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
+                             int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
+                             int in_row_pitch, int in_frame_pitch, const void* wp_ds, const float* bias_ds,
+                             void* out_ds, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !wp || !out) return fail(-1, "sblk_conv2d_igemm_fwd: null pointer");
@@ -411,10 +436,28 @@ int sblk_conv2d_igemm_fwd(const void* x, const void* wp, const float* bias, cons
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
     const int m_tiles = (M + 127) / 128;
-    const int bn = pick_block_n(m_tiles, Cout, sms);
+    const int bn = wp_ds ? 128 : pick_block_n(m_tiles, Cout, sms);
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn)};
     if ((rc = encode_tiled(&tmB, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     sblk::IgemmParams p;
+    p.bias2 = bias_ds;
+    p.out2_bf16 = static_cast<__nv_bfloat16*>(out_ds);
+    p.debug_mode = 0;
+    if (wp_ds) {
+      // fused 1x1 downsample branch: its [Cout][Cin] filter rides along with the centre-tap k-blocks
+      CUtensorMap tmB2;
+      cuuint64_t dims2[2] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(Cout)};
+      cuuint64_t strides2[1] = {static_cast<cuuint64_t>(Cin) * 2};
+      if ((rc = encode_tiled(&tmB2, wp_ds, 2, dims2, strides2, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      p.M = M; p.N = Cout; p.taps_r = R; p.taps_s = S; p.cblocks = Cin / 64; p.P = P; p.Q = Q;
+      p.stride = stride; p.pad = pad; p.relu = relu; p.ldo = Cout;
+      p.bias = bias; p.residual = nullptr;
+      p.out_bf16 = static_cast<__nv_bfloat16*>(out); p.out_f32 = nullptr;
+      const int tiles = m_tiles * (Cout / 128);
+      const int grid = tiles < sms ? tiles : sms;
+      return launch(sblk::igemm_kernel<128, true, true>, dim3(grid), dim3(192), sblk::IgemmCfg<128, true>::SMEM_BYTES,
+                    static_cast<cudaStream_t>(stream), true, "igemm_kernel<128,dual>", tmA, tmB, tmB2, p);
+    }
     p.M = M; p.N = Cout; p.taps_r = R; p.taps_s = S; p.cblocks = Cin / 64; p.P = P; p.Q = Q;
     p.stride = stride; p.pad = pad; p.relu = relu; p.ldo = Cout;
     p.bias = bias;
@@ -451,6 +494,7 @@ int sblk_gemm_fwd(const void* a, const void* w, const float* bias, const void* r
     if ((rc = encode_tiled(&tmB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   sblk::IgemmParams p;
+  p.bias2 = nullptr; p.out2_bf16 = nullptr; p.debug_mode = 0;
   p.M = M; p.N = N; p.taps_r = 1; p.taps_s = 1; p.cblocks = K / 64; p.P = 1; p.Q = 1;
   p.stride = 1; p.pad = 0; p.relu = relu; p.ldo = N;
   p.bias = bias;

@@ -204,6 +204,35 @@ def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None):
     return FlatActs(out, x.f, x.h, x.w)
 
 
+def _conv_input(x):
+    if isinstance(x, FlatActs):
+        _req(x.data, BF16, "x")
+        f, h, w, cin = x.f, x.h, x.w, x.c
+        return (x.data.data_ptr() + (w + 3) * cin * 2, f, h, w, cin, w + 2, (h + 1) * (w + 2), x.data.numel())
+    _req(x, BF16, "x")
+    f, h, w, cin = x.shape
+    return (x.data_ptr(), f, h, w, cin, 0, 0, x.numel())
+
+
+def conv2d_dual(x, wp, bias, wp_ds, bias_ds, stride=2, relu=True):
+    """BasicBlock head with a downsample branch in one launch:
+    (relu(conv3x3_s(x) + bias), conv1x1_s(x) + bias_ds), both bf16 NHWC [F,P,Q,Cout]."""
+    _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(wp_ds, BF16, "wp_ds"); _req(bias_ds, F32, "bias_ds")
+    xptr, f, h, w, cin, row_pitch, frame_pitch, x_elems = _conv_input(x)
+    cout = wp.shape[0]
+    if tuple(wp.shape) != (cout, 3, 3, cin) or tuple(wp_ds.shape) != (cout, 1, 1, cin):
+        raise RuntimeError(f"conv2d_dual: weight shapes {tuple(wp.shape)} / {tuple(wp_ds.shape)} do not match Cin={cin}")
+    p = (h + 2 - 3) // stride + 1
+    q = (w + 2 - 3) // stride + 1
+    out = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
+    out_ds = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
+    _call("sblk_conv2d_dual_igemm_fwd", f"conv3x3+ds H={h} {cin}->{cout} s{stride}", 2 * f * p * q * cout * 10 * cin,
+          2 * (x_elems + wp.numel() + wp_ds.numel() + 2 * out.numel()),
+          xptr, _p(wp), _p(bias), _p(wp_ds), _p(bias_ds), _p(out), _p(out_ds), f, h, w, cin, cout, stride,
+          1 if relu else 0, row_pitch, frame_pitch, _stream())
+    return out, out_ds
+
+
 def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     """x bf16 NHWC [F,H,W,Cin] (or FlatActs), wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout]."""
     _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")

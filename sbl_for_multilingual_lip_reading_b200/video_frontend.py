@@ -196,8 +196,10 @@ class Lipreading(nn.Module):
                     y = ops.conv3x3_flat(a, w1, b1, relu=True)
                     a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
                     continue
-                y = ops.conv2d(a, w1, b1, stride=stride, relu=True)
-                res = a if ds is None else ops.conv2d(a, ds[0], ds[1], stride=stride, relu=False)
+                if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input
+                    y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
+                else:
+                    y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a
                 a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
             feat, _ = ops.avgpool(a, want_f32=True, want_bf16=False)
         return feat

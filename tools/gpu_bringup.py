@@ -295,6 +295,24 @@ def sec_flat():
         w2 = (torch.randn(128, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
         wp2, b2 = ops.pack_conv2d(w2)
         report(f"conv s2 on flat F{Fr} H{H}", ops.conv2d(xf, wp2, b2, stride=2), ops.conv2d(x, wp2, b2, stride=2))
+    # fused conv1 + downsample (DUAL) == two separate launches, on dense and flat inputs
+    for (Fr, H, Ci, Co) in [(5, 22, 64, 128), (29, 22, 64, 128), (7, 11, 128, 256), (9, 6, 256, 512), (928, 6, 256, 512)]:
+        x = bf(torch.randn(Fr, H, H, Ci, generator=g)).to(DEV)
+        w1 = (torch.randn(Co, Ci, 3, 3, generator=g) / (9 * Ci) ** 0.5).to(DEV)
+        wd = (torch.randn(Co, Ci, 1, 1, generator=g) / Ci ** 0.5).to(DEV)
+        gam = (torch.rand(Co, generator=g) + 0.5).to(DEV); bet = (torch.randn(Co, generator=g) * 0.1).to(DEV)
+        mu = (torch.randn(Co, generator=g) * 0.1).to(DEV); var = (torch.rand(Co, generator=g) + 0.5).to(DEV)
+        wp1, b1 = ops.pack_conv2d(w1, gam, bet, mu, var)
+        wpd, bd = ops.pack_conv2d(wd, bet.abs() + 0.5, gam - 1.0, mu, var)
+        y_ref = ops.conv2d(x, wp1, b1, stride=2, relu=True)
+        d_ref = ops.conv2d(x, wpd, bd, stride=2, relu=False)
+        y, d = ops.conv2d_dual(x, wp1, b1, wpd, bd, stride=2)
+        report(f"dual conv1 F{Fr} H{H} {Ci}->{Co}", y, y_ref, tol=1e-6)
+        report(f"dual ds    F{Fr} H{H} {Ci}->{Co}", d, d_ref, tol=1e-6)
+        if Ci == 64:
+            y2, d2 = ops.conv2d_dual(to_flat(x), wp1, b1, wpd, bd, stride=2)
+            report(f"dual conv1 (flat in) F{Fr}", y2, y_ref, tol=1e-6)
+            report(f"dual ds    (flat in) F{Fr}", d2, d_ref, tol=1e-6)
     # stem flat output == dense output
     w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / (245 ** 0.5)).to(DEV)
     one, zero = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
@@ -367,6 +385,13 @@ def sec_perf():
         w = bf(torch.randn(N, K, generator=g)).to(DEV)
         ms = timeit(lambda: ops.gemm(a, w, out_bf16=True))
         print(f"perf gemm M{M} N{N} K{K}: {ms * 1e3:.1f} us  {2.0 * M * N * K / ms / 1e9:.1f} TFLOP/s", flush=True)
+    for (H, Ci, Co) in [(22, 64, 128), (11, 128, 256), (6, 256, 512)]:
+        x = bf(torch.randn(928, H, H, Ci, generator=g)).to(DEV)
+        wa = bf(torch.randn(Co, 3, 3, Ci, generator=g) / (9 * Ci) ** 0.5).to(DEV)
+        wb = bf(torch.randn(Co, 1, 1, Ci, generator=g) / Ci ** 0.5).to(DEV)
+        bz = torch.zeros(Co, device=DEV)
+        ms = timeit(lambda: ops.conv2d_dual(x, wa, bz, wb, bz, stride=2))
+        print(f"perf dual conv3x3+ds H{H} {Ci}->{Co} s2: {ms * 1e3:.1f} us", flush=True)
     xd = bf(torch.randn(928, 22, 22, 64, generator=g)).to(DEV)
     xf = to_flat(xd)
     wf = ops.pack_flat_weight(bf(torch.randn(64, 3, 3, 64, generator=g) / 24).to(DEV))
