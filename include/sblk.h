@@ -96,6 +96,18 @@ int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, 
  * replaces: nn.Linear call sites, transformer/attention.py:41-43,57 ; module.py:49 ; encoder.py:53 */
 int sblk_gemm_fwd(const void* a_bf16, const void* w_bf16, const float* bias, const void* residual_bf16,
                   void* out_bf16, float* out_f32, int M, int N, int K, int relu, void* stream);
+/* Split-K plan for a Linear at small M: the number of K ranges (1, 2, 4 or 8) that fills the SMs with one tile each
+ * (negative on error).  The caller allocates [splits, M, N] fp32 for sblk_gemm_splitk_fwd. */
+int sblk_gemm_splitk_plan(int M, int N, int K);
+/* Split-K Linear: partial s = A[:, K_s] W[:, K_s]^T (+ bias for s == 0) -> out_partials[s] fp32 [M,N]; the partials
+ * are summed by sblk_sum_layernorm_fwd (deterministic: no atomics).  (K / 64) % splits == 0.
+ * replaces: nn.Linear call sites whose output feeds a LayerNorm, attention.py:57 ; module.py:49 ; encoder.py:53 */
+int sblk_gemm_splitk_fwd(const void* a_bf16, const void* w_bf16, const float* bias, float* out_partials, int M, int N,
+                         int K, int splits, void* stream);
+/* sblk_add_layernorm_fwd over the sum of nparts partial inputs x_parts[nparts][M,512] (+ bias[512]). */
+int sblk_sum_layernorm_fwd(const float* x_parts, int nparts, const float* bias, const float* residual,
+                           const float* gamma, const float* beta, const float* pe, const int* lengths,
+                           float* out_f32, void* out_bf16, int M, int T, int D, float eps, void* stream);
 /* y = LayerNorm(x + residual) * gamma + beta (+ pe[m % T]) (* (m % T < lengths[m / T])), D must be 512.
  * residual, pe, lengths, out_f32, out_bf16 may be NULL.
  * replaces: nn.LayerNorm call sites attention.py:58, module.py:51, encoder.py:53-55 (+PositionalEncoding,
@@ -110,6 +122,27 @@ int sblk_add_layernorm_fwd(const float* x, const float* residual, const float* g
  * get_attn_pad_mask, transformer/utils.py:140-147 */
 int sblk_attention_fwd(const void* qkv_bf16, void* out_bf16, float* probs, const int* lengths, int N, int T,
                        int H, int d_k, float scale, void* stream);
+
+/* One launch for Linear(K -> 512) + bias + fp32 residual + LayerNorm(512) (+ pe[m % T]) (* pad mask):
+ * y = LN(A[M,K] W[512,K]^T + bias + residual) * gamma + beta (+ pe) (* (m % T < lengths[m / T])).
+ * A, W bf16; accumulation, statistics (two-pass) and the residual stream fp32.  N must be 512, K % 64 == 0.
+ * A cluster of 4 CTAs owns each 128-row tile and combines the row statistics through distributed shared memory.
+ * replaces: fc + layer_norm(out + residual) attention.py:57-58 ; w_2 + layer_norm(out + x) module.py:49-51 ;
+ * layer_norm_in(linear_in(x)) + positional_encoding encoder.py:53-55 ; `*= non_pad_mask` encoder.py:86,89 */
+int sblk_gemm_ln_fwd(const void* a_bf16, const void* w_bf16, const float* bias, const float* residual_f32,
+                     const float* gamma, const float* beta, const float* pe, const int* lengths, float* out_f32,
+                     void* out_bf16, int M, int N, int K, int T, float eps, void* stream);
+/* Clips per 128-row tile used by sblk_qkv_attention_fwd for T frames per clip (-1 if T is unsupported). */
+int sblk_qkv_group_clips(int T);
+/* One launch for the q/k/v projections + scaled-dot-product self-attention of all heads:
+ * x bf16 [N*T, K]; w_heads bf16 [H*192, K] head-major (rows h*192 + [0,64) = w_qs rows of head h, [64,128) = w_ks,
+ * [128,192) = w_vs); bias_heads fp32 [H*192] in the same order -> out bf16 [N*T, H*64] (heads concatenated).
+ * d_k must be 64, T <= 128, K % 64 == 0.
+ * replaces: MultiHeadAttention.forward up to the head merge, attention.py:41-55, ScaledDotProductAttention.forward,
+ * attention.py:72-83, and get_attn_pad_mask, utils.py:140-147 (attention maps are not produced by this entry point:
+ * use sblk_gemm_fwd + sblk_attention_fwd when return_attns is requested) */
+int sblk_qkv_attention_fwd(const void* x_bf16, const void* w_heads_bf16, const float* bias_heads, const int* lengths,
+                           void* out_bf16, int N, int T, int H, int d_k, int K, float scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,10 +13,13 @@
 #include "../../include/sblk.h"
 #include "sblk_common.cuh"
 #include "sblk_igemm.cuh"
+#include "sblk_igemm2.cuh"
 #include "sblk_conv3d.cuh"
 #include "sblk_flatconv.cuh"
 #include "sblk_aux.cuh"
 #include "sblk_attention.cuh"
+#include "sblk_gemm_ln.cuh"
+#include "sblk_qkv_attn.cuh"
 
 namespace {
 
@@ -109,11 +112,18 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<128, true>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, true>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<128, true, true>, sblk::IgemmCfg<128, true>::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::igemm2_kernel<128, true>, sblk::Igemm2Cfg<128>::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::igemm2_kernel<256, true>, sblk::Igemm2Cfg<256>::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::igemm2_kernel<128, true, true>, sblk::Igemm2Cfg<128, true>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<64, false>, sblk::IgemmCfg<64>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::flatconv3x3_c64_kernel, sblk::fc::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::gemm_ln512_kernel, sblk::gln::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::qkv_attention_kernel<4>, sblk::qa::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::qkv_attention_kernel<8>, sblk::qa::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::qkv_attention_kernel<16>, sblk::qa::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<4>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<8>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<16>, 100 * 1024))) return rc;
@@ -180,7 +190,7 @@ int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::I
     p.debug_mode = dm ? atoi(dm) : 0;
   }
   const int m_tiles = (p.M + 127) / 128;
-  const int tiles = m_tiles * (p.N / bn);
+  const int tiles = m_tiles * (p.N / bn) * p.splits;
   const int grid = tiles < num_sms ? tiles : num_sms;
   switch (bn) {
     case 64:
@@ -195,6 +205,12 @@ int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::I
     default:
       return fail(-11, "no BLOCK_N for N=%d", p.N);
   }
+}
+
+// SBLK_CTA_PAIRS=0 routes every conv through the 1-CTA kernel (A/B timing experiments); default on.
+bool use_cta_pairs() {
+  const char* e = getenv("SBLK_CTA_PAIRS");
+  return e == nullptr || atoi(e) != 0;
 }
 
 int elementwise_grid(long long work_items, int block, int num_sms) {
@@ -436,10 +452,13 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
     const int m_tiles = (M + 127) / 128;
-    const int bn = wp_ds ? 128 : pick_block_n(m_tiles, Cout, sms);
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn)};
+    // CTA-pair kernel (sblk_igemm2.cuh) for every conv with Cout >= 128: half the B bytes per SM
+    const int bn2 = use_cta_pairs() && Cout % 128 == 0 ? ((wp_ds || Cout % 256 != 0) ? 128 : 256) : 0;
+    const int bn = bn2 ? bn2 : wp_ds ? 128 : pick_block_n(m_tiles, Cout, sms);
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn2 ? bn2 / 2 : bn)};
     if ((rc = encode_tiled(&tmB, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     sblk::IgemmParams p;
+    p.splits = 1; p.split_stride = 0;
     p.bias2 = bias_ds;
     p.out2_bf16 = static_cast<__nv_bfloat16*>(out_ds);
     p.debug_mode = 0;
@@ -453,6 +472,13 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
       p.stride = stride; p.pad = pad; p.relu = relu; p.ldo = Cout;
       p.bias = bias; p.residual = nullptr;
       p.out_bf16 = static_cast<__nv_bfloat16*>(out); p.out_f32 = nullptr;
+      if (bn2) {
+        const int tiles2 = ((M + 255) / 256) * (Cout / 128);
+        const int pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
+        return launch(sblk::igemm2_kernel<128, true, true>, dim3(2 * pairs), dim3(192),
+                      sblk::Igemm2Cfg<128, true>::SMEM_BYTES, static_cast<cudaStream_t>(stream), true,
+                      "igemm2_kernel<128,dual>", tmA, tmB, tmB2, p);
+      }
       const int tiles = m_tiles * (Cout / 128);
       const int grid = tiles < sms ? tiles : sms;
       return launch(sblk::igemm_kernel<128, true, true>, dim3(grid), dim3(192), sblk::IgemmCfg<128, true>::SMEM_BYTES,
@@ -464,20 +490,49 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     p.residual = static_cast<const __nv_bfloat16*>(residual);
     p.out_bf16 = static_cast<__nv_bfloat16*>(out);
     p.out_f32 = nullptr;
+    if (bn2) {
+      const int tiles2 = ((M + 255) / 256) * (Cout / bn2);
+      const int pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
+      if (bn2 == 256)
+        return launch(sblk::igemm2_kernel<256, true>, dim3(2 * pairs), dim3(192), sblk::Igemm2Cfg<256>::SMEM_BYTES,
+                      static_cast<cudaStream_t>(stream), true, "igemm2_kernel<256>", tmA, tmB, tmB, p);
+      return launch(sblk::igemm2_kernel<128, true>, dim3(2 * pairs), dim3(192), sblk::Igemm2Cfg<128>::SMEM_BYTES,
+                    static_cast<cudaStream_t>(stream), true, "igemm2_kernel<128>", tmA, tmB, tmB, p);
+    }
     return launch_igemm<true>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
   }
 }
 
-int sblk_gemm_fwd(const void* a, const void* w, const float* bias, const void* residual, void* out_bf16,
-                  float* out_f32, int M, int N, int K, int relu, void* stream) {
+// Linear layers: the BLOCK_N that minimises the operand bytes one CTA has to pull through its L2 port,
+// rounds * (128 + BLOCK_N) (the path is latency / port bound at the BASELINE token count, not tensor bound).
+static int pick_block_n_linear(int m_tiles, int N, int splits, int num_sms) {
+  const int cand[3] = {256, 128, 64};
+  int best = 0;
+  long long best_cost = 0;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cand[i];
+    if (N % bn != 0) continue;
+    const long long tiles = static_cast<long long>(m_tiles) * (N / bn) * splits;
+    const long long cost = ((tiles + num_sms - 1) / num_sms) * (128 + bn);
+    if (best == 0 || cost < best_cost) { best = bn; best_cost = cost; }
+  }
+  return best;
+}
+
+static int gemm_impl(const void* a, const void* w, const float* bias, const void* residual, void* out_bf16,
+                     float* out_f32, int M, int N, int K, int relu, int splits, void* stream, const char* who) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
-  if (!a || !w || (!out_bf16 && !out_f32)) return fail(-1, "sblk_gemm_fwd: null pointer");
+  if (!a || !w || (!out_bf16 && !out_f32)) return fail(-1, "%s: null pointer", who);
   if (M <= 0 || N <= 0 || K <= 0 || N % 64 != 0 || K % 64 != 0)
-    return fail(-1, "sblk_gemm_fwd: M=%d N=%d K=%d unsupported (N and K must be multiples of 64)", M, N, K);
+    return fail(-1, "%s: M=%d N=%d K=%d unsupported (N and K must be multiples of 64)", who, M, N, K);
+  if (splits < 1 || (K / 64) % splits != 0)
+    return fail(-1, "%s: splits=%d must divide the %d K-blocks of 64", who, splits, K / 64);
+  if (splits > 1 && (out_bf16 || residual || relu || !out_f32))
+    return fail(-1, "%s: split-K writes raw fp32 partials only (no bf16 output, residual or ReLU)", who);
   if (!aligned16(a) || !aligned16(w) || (out_bf16 && !aligned16(out_bf16)) || (out_f32 && !aligned16(out_f32)) ||
       (residual && !aligned16(residual)) || (bias && !aligned16(bias)))
-    return fail(-1, "sblk_gemm_fwd: pointers must be 16-byte aligned");
+    return fail(-1, "%s: pointers must be 16-byte aligned", who);
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(M)};
@@ -486,7 +541,11 @@ int sblk_gemm_fwd(const void* a, const void* w, const float* bias, const void* r
     if ((rc = encode_tiled(&tmA, a, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   const int m_tiles = (M + 127) / 128;
-  const int bn = pick_block_n(m_tiles, N, sms);
+  int bn = pick_block_n_linear(m_tiles, N, splits, sms);
+  {
+    const char* e = getenv("SBLK_GEMM_BN");   // tuning experiments only
+    if (e && atoi(e) > 0 && N % atoi(e) == 0) bn = atoi(e);
+  }
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
@@ -501,7 +560,31 @@ int sblk_gemm_fwd(const void* a, const void* w, const float* bias, const void* r
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
+  p.splits = splits;
+  p.split_stride = static_cast<long long>(M) * N;
   return launch_igemm<false>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
+}
+
+int sblk_gemm_fwd(const void* a, const void* w, const float* bias, const void* residual, void* out_bf16,
+                  float* out_f32, int M, int N, int K, int relu, void* stream) {
+  return gemm_impl(a, w, bias, residual, out_bf16, out_f32, M, N, K, relu, 1, stream, "sblk_gemm_fwd");
+}
+
+int sblk_gemm_splitk_plan(int M, int N, int K) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc < 0 ? rc : -rc;
+  if (M <= 0 || N <= 0 || K <= 0 || N % 64 != 0 || K % 64 != 0) return fail(-1, "sblk_gemm_splitk_plan: bad shape");
+  const int bn = N % 128 == 0 ? 128 : 64;
+  const long long base = static_cast<long long>((M + 127) / 128) * (N / bn);
+  int splits = 1;
+  while (splits < 8 && base * (splits * 2) <= sms && (K / 64) % (splits * 2) == 0 && K / 64 / (splits * 2) >= 2)
+    splits *= 2;
+  return splits;
+}
+
+int sblk_gemm_splitk_fwd(const void* a, const void* w, const float* bias, float* out_partials, int M, int N, int K,
+                         int splits, void* stream) {
+  return gemm_impl(a, w, bias, nullptr, nullptr, out_partials, M, N, K, 0, splits, stream, "sblk_gemm_splitk_fwd");
 }
 
 int sblk_avgpool_fwd(const void* x, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream) {
@@ -515,25 +598,36 @@ int sblk_avgpool_fwd(const void* x, float* out_f32, void* out_bf16, int F, int H
                 out_f32, static_cast<__nv_bfloat16*>(out_bf16), F, HW, C);
 }
 
+int sblk_sum_layernorm_fwd(const float* x_parts, int nparts, const float* bias, const float* residual,
+                           const float* gamma, const float* beta, const float* pe, const int* lengths,
+                           float* out_f32, void* out_bf16, int M, int T, int D, float eps, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x_parts || !gamma || !beta || (!out_f32 && !out_bf16)) return fail(-1, "sblk_sum_layernorm_fwd: null pointer");
+  if (D != 512) return fail(-1, "sblk_sum_layernorm_fwd: d_model=%d not implemented (only 512)", D);
+  if (M <= 0 || T <= 0 || M % T != 0 || nparts < 1)
+    return fail(-1, "sblk_sum_layernorm_fwd: bad shape M=%d T=%d nparts=%d", M, T, nparts);
+  if (!aligned16(x_parts) || !aligned16(gamma) || !aligned16(beta) || (residual && !aligned16(residual)) ||
+      (bias && !aligned16(bias)) || (pe && !aligned16(pe)) || (out_f32 && !aligned16(out_f32)) ||
+      (out_bf16 && !aligned16(out_bf16)))
+    return fail(-1, "sblk_sum_layernorm_fwd: pointers must be 16-byte aligned");
+  sblk::LnParams p;
+  p.x = x_parts; p.nparts = nparts; p.part_stride = static_cast<long long>(M) * D; p.bias = bias;
+  p.residual = residual; p.gamma = gamma; p.beta = beta; p.pe = pe; p.lengths = lengths;
+  p.out_f32 = out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.M = M; p.T = T; p.eps = eps;
+  // one warp per row; 4 rows per CTA so that the BASELINE 928 tokens spread over all SMs
+  const int rows_per_block = 4;
+  int grid = (M + rows_per_block - 1) / rows_per_block;
+  if (grid > sms * 16) grid = sms * 16;
+  return launch(sblk::add_layernorm512_kernel, dim3(grid), dim3(32 * rows_per_block), 0,
+                static_cast<cudaStream_t>(stream), true, "add_layernorm512_kernel", p);
+}
+
 int sblk_add_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta,
                            const float* pe, const int* lengths, float* out_f32, void* out_bf16, int M, int T, int D,
                            float eps, void* stream) {
-  int sms, rc;
-  if ((rc = ensure_init(&sms))) return rc;
-  if (!x || !gamma || !beta || (!out_f32 && !out_bf16)) return fail(-1, "sblk_add_layernorm_fwd: null pointer");
-  if (D != 512) return fail(-1, "sblk_add_layernorm_fwd: d_model=%d not implemented (only 512)", D);
-  if (M <= 0 || T <= 0 || M % T != 0) return fail(-1, "sblk_add_layernorm_fwd: bad shape M=%d T=%d", M, T);
-  if (!aligned16(x) || !aligned16(gamma) || !aligned16(beta) || (residual && !aligned16(residual)) ||
-      (pe && !aligned16(pe)) || (out_f32 && !aligned16(out_f32)) || (out_bf16 && !aligned16(out_bf16)))
-    return fail(-1, "sblk_add_layernorm_fwd: pointers must be 16-byte aligned");
-  sblk::LnParams p;
-  p.x = x; p.residual = residual; p.gamma = gamma; p.beta = beta; p.pe = pe; p.lengths = lengths;
-  p.out_f32 = out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.M = M; p.T = T; p.eps = eps;
-  const int rows_per_block = 8;
-  int grid = (M + rows_per_block - 1) / rows_per_block;
-  if (grid > sms * 8) grid = sms * 8;
-  return launch(sblk::add_layernorm512_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), true,
-                "add_layernorm512_kernel", p);
+  return sblk_sum_layernorm_fwd(x, 1, nullptr, residual, gamma, beta, pe, lengths, out_f32, out_bf16, M, T, D, eps,
+                                stream);
 }
 
 int sblk_attention_fwd(const void* qkv, void* out, float* probs, const int* lengths, int N, int T, int H, int d_k,
@@ -560,6 +654,86 @@ int sblk_attention_fwd(const void* qkv, void* out, float* probs, const int* leng
                   "attention_kernel<8>", p);
   return launch(sblk::attention_kernel<16>, grid, block, sblk::ATTN_WARPS * 3 * 128 * 128, s, true,
                 "attention_kernel<16>", p);
+}
+
+int sblk_gemm_ln_fwd(const void* a, const void* w, const float* bias, const float* residual, const float* gamma,
+                     const float* beta, const float* pe, const int* lengths, float* out_f32, void* out_bf16, int M,
+                     int N, int K, int T, float eps, void* stream) {
+  using namespace sblk::gln;
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!a || !w || !gamma || !beta || (!out_f32 && !out_bf16)) return fail(-1, "sblk_gemm_ln_fwd: null pointer");
+  if (N != D) return fail(-1, "sblk_gemm_ln_fwd: N=%d not implemented (LayerNorm width must be 512)", N);
+  if (M <= 0 || K <= 0 || K % 64 != 0 || T <= 0 || M % T != 0)
+    return fail(-1, "sblk_gemm_ln_fwd: bad shape M=%d K=%d T=%d (K %% 64 == 0, M %% T == 0)", M, K, T);
+  if (!aligned16(a) || !aligned16(w) || !aligned16(gamma) || !aligned16(beta) || (bias && !aligned16(bias)) ||
+      (residual && !aligned16(residual)) || (pe && !aligned16(pe)) || (out_f32 && !aligned16(out_f32)) ||
+      (out_bf16 && !aligned16(out_bf16)))
+    return fail(-1, "sblk_gemm_ln_fwd: pointers must be 16-byte aligned");
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, BLOCK_M};
+    if ((rc = encode_tiled(&tmA, a, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, BLOCK_N};
+    if ((rc = encode_tiled(&tmB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  sblk::GemmLnParams p;
+  p.M = M; p.K = K; p.T = T; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta; p.pe = pe;
+  p.lengths = lengths; p.out_f32 = out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.eps = eps;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  return launch(sblk::gemm_ln512_kernel, dim3(CLUSTER * m_tiles), dim3(THREADS), SMEM_BYTES,
+                static_cast<cudaStream_t>(stream), true, "gemm_ln512_kernel", tmA, tmB, p);
+}
+
+int sblk_qkv_group_clips(int T) {
+  if (T <= 0 || T > 128) return -1;
+  const int tp = T <= 32 ? 32 : T <= 64 ? 64 : 128;
+  int g = 128 / T;
+  const int cap = (sblk::qa::QKV_ROWS - tp) / T + 1;   // key padding of the group's last clip stays inside the tile
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : g;
+}
+
+int sblk_qkv_attention_fwd(const void* x, const void* w_heads, const float* bias_heads, const int* lengths, void* out,
+                           int N, int T, int H, int d_k, int K, float scale, void* stream) {
+  using namespace sblk::qa;
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !w_heads || !bias_heads || !out) return fail(-1, "sblk_qkv_attention_fwd: null pointer");
+  if (d_k != 64) return fail(-1, "sblk_qkv_attention_fwd: d_k=%d not implemented (only 64)", d_k);
+  if (N <= 0 || T <= 0 || H <= 0 || K <= 0 || K % 64 != 0)
+    return fail(-1, "sblk_qkv_attention_fwd: bad shape N=%d T=%d H=%d K=%d", N, T, H, K);
+  if (T > 128) return fail(-1, "sblk_qkv_attention_fwd: T=%d > 128 not implemented", T);
+  if (!aligned16(x) || !aligned16(w_heads) || !aligned16(bias_heads) || !aligned16(out))
+    return fail(-1, "sblk_qkv_attention_fwd: pointers must be 16-byte aligned");
+  const long long M = static_cast<long long>(N) * T;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, BLOCK_M};
+    if ((rc = encode_tiled(&tmA, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(H) * BLOCK_N};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
+    cuuint32_t box[2] = {64, BLOCK_N};
+    if ((rc = encode_tiled(&tmB, w_heads, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  sblk::QkvAttnParams p;
+  p.N = N; p.T = T; p.H = H; p.G = sblk_qkv_group_clips(T); p.K = K; p.bias = bias_heads; p.lengths = lengths;
+  p.out = static_cast<__nv_bfloat16*>(out); p.scale = scale;
+  const dim3 grid((N + p.G - 1) / p.G, H), block(THREADS);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T <= 32) return launch(sblk::qkv_attention_kernel<4>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<4>", tmA, tmB, p);
+  if (T <= 64) return launch(sblk::qkv_attention_kernel<8>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<8>", tmA, tmB, p);
+  return launch(sblk::qkv_attention_kernel<16>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<16>", tmA, tmB, p);
 }
 
 }  // extern "C"

@@ -148,7 +148,10 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out_f32,
 // Writes the fp32 residual stream and the bf16 copy the next GEMM consumes.
 // --------------------------------------------------------------------------------------------
 struct LnParams {
-  const float* x;         // [M, 512] GEMM output (bias already added)
+  const float* x;         // [nparts][M, 512] GEMM output (split-K partials are summed here; bias added if given)
+  int nparts;             // >= 1
+  long long part_stride;  // elements between partials
+  const float* bias;      // [512] or nullptr
   const float* residual;  // [M, 512] or nullptr
   const float* gamma;     // [512]
   const float* beta;      // [512]
@@ -174,6 +177,21 @@ add_layernorm512_kernel(const LnParams p) {
     for (int j = 0; j < 4; ++j) {
       const float4 a = __ldg(xr + j * 32 + lane);
       v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+    }
+    for (int s = 1; s < p.nparts; ++s) {
+      const float4* xs = reinterpret_cast<const float4*>(p.x + s * p.part_stride + static_cast<size_t>(m) * 512);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = __ldg(xs + j * 32 + lane);
+        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+      }
+    }
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias) + j * 32 + lane);
+        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+      }
     }
     if (p.residual != nullptr) {
       const float4* rr = reinterpret_cast<const float4*>(p.residual + static_cast<size_t>(m) * 512);

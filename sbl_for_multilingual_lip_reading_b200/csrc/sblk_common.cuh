@@ -14,8 +14,8 @@ namespace sblk {
 // Device-side watchdog: a barrier wait that spins longer than this many polls records a code in
 // a global word and traps, so a mis-programmed pipeline fails loudly instead of hanging the GPU.
 // ----------------------------------------------------------------------------------------------
-#ifndef SBLK_WATCHDOG_POLLS
-#define SBLK_WATCHDOG_POLLS (1u << 26)
+#ifndef SBLK_WATCHDOG_NS
+#define SBLK_WATCHDOG_NS 4000000000ull   // 4 s of wall time (the slowest kernel of the path runs ~100 us)
 #endif
 
 // Points at a host-mapped (zero-copy) word so the code survives the trap that follows it.
@@ -73,15 +73,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // `code` identifies the wait site in the watchdog word (kernel id << 8 | site).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t code) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t polls = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls > SBLK_WATCHDOG_POLLS) {
-      unsigned int* wd = g_sblk_watchdog_ptr;
-      if (wd != nullptr) {
-        atomicCAS_system(wd, 0u, code | 0x80000000u);
-        __threadfence_system();
+    if ((++polls & 1023u) == 0u) {   // wall-clock check every 1024 failed polls
+      uint64_t now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      if (now - t0 > SBLK_WATCHDOG_NS) {
+        unsigned int* wd = g_sblk_watchdog_ptr;
+        if (wd != nullptr) {
+          atomicCAS_system(wd, 0u, code | 0x80000000u);
+          __threadfence_system();
+        }
+        __trap();
       }
-      __trap();
     }
   }
 }

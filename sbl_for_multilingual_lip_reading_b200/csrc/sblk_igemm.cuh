@@ -36,6 +36,10 @@ struct IgemmParams {
   // DUAL only: the 1x1 / same-stride downsample conv of a BasicBlock shares the centre-tap A tiles of conv1
   const float* bias2;              // [N] folded BN shift of the downsample branch
   __nv_bfloat16* out2_bf16;        // [M, ldo] downsample output (no ReLU)
+  // split-K (linear layers at small M): K is cut into `splits` ranges, one tile per (split, m, n); split s writes its
+  // fp32 partial to out_f32 + s * split_stride (bias added by split 0 only); the consumer sums the partials
+  int splits;                      // >= 1
+  long long split_stride;          // elements between partial outputs
 };
 
 template <int BLOCK_N, bool DUAL = false>
@@ -77,8 +81,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   const int n_tiles = p.N / BLOCK_N;
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
-  const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = p.taps_r * p.taps_s * p.cblocks;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * p.splits;
+  const int num_kb = p.taps_r * p.taps_s * p.cblocks / p.splits;   // k-blocks per tile
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -111,9 +116,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile - m_blk * n_tiles;
+      const int split = tile / mn_tiles;
+      const int mn = tile - split * mn_tiles;
+      const int m_blk = mn / n_tiles;
+      const int n_blk = mn - m_blk * n_tiles;
       const int m0 = m_blk * Cfg::BLOCK_M;
+      const int kb0 = split * num_kb;   // first k-block of this split (linear layers only)
       int img = 0, base_w = 0, base_h = 0;
       if (IM2COL) {
         const int pq = p.P * p.Q;
@@ -140,10 +148,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               tma_load_im2col_4d(a_dst, &tmA, &full_bar[stage], cb * 64, base_w, base_h, img,
                                  static_cast<uint16_t>(s), static_cast<uint16_t>(r));
             } else {
-              tma_load_2d(a_dst, &tmA, &full_bar[stage], kb * 64, m0);
+              tma_load_2d(a_dst, &tmA, &full_bar[stage], (kb0 + kb) * 64, m0);
             }
           }
-          if (!(p.debug_mode & 1)) tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * 64, n_blk * BLOCK_N);
+          if (!(p.debug_mode & 1)) tma_load_2d(b_dst, &tmB, &full_bar[stage], (kb0 + kb) * 64, n_blk * BLOCK_N);
         }
         __syncwarp();
         if (++cb == p.cblocks) {
@@ -202,8 +210,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles;
-      const int n_blk = tile - m_blk * n_tiles;
+      const int split = tile / mn_tiles;
+      const int mn = tile - split * mn_tiles;
+      const int m_blk = mn / n_tiles;
+      const int n_blk = mn - m_blk * n_tiles;
       const int m = m_blk * Cfg::BLOCK_M + row;
       const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[acc], acc_phase, 0x0104);
@@ -221,7 +231,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+          if (p.bias != nullptr && split == 0) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -257,7 +267,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           if (p.out_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + row_off + n0);
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(split) * p.split_stride + row_off + n0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
           }

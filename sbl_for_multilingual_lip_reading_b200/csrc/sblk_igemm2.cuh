@@ -1,0 +1,364 @@
+// sblk_igemm2.cuh — CTA-pair (cta_group::2) variant of the persistent tcgen05 implicit GEMM of sblk_igemm.cuh.
+//
+// Why: ncu on the 1-CTA kernel at the BASELINE shape (profiles/r01f_*) shows the 3x3 convs of ResNet layers 2-4 stalled
+// on L2->SM operand delivery (479-631 MB per launch at ~12 TB/s, tensor pipe 41-58 % busy): a 128 x BLOCK_N tile
+// fetches 16 KB of A plus BLOCK_N*128 B of B per 64-wide K block.  Here two CTAs of a cluster (the two SMs of a TPC)
+// compute one 256 x BLOCK_N tile with tcgen05.mma.cta_group::2: each CTA stages its own 128 A rows and only HALF of the
+// B tile, the tensor cores read both halves, so operand bytes per FLOP drop by 1.5x (BLOCK_N = 256) to 2x.
+//
+// Same roles as the 1-CTA kernel (192 threads: warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2-5
+// epilogue), same fused epilogue.  Protocol differences (CTA rank 0 = leader):
+//   * full barriers live in the LEADER: its producer posts expect_tx for both CTAs' bytes, the peer's TMA loads
+//     (cp.async.bulk.tensor...cta_group::2) complete_tx on the leader's barrier through its shared::cluster address
+//   * only the leader issues MMAs; tcgen05.commit...multicast::cluster arrives on the empty / accumulator-full
+//     barriers of BOTH CTAs (same smem offsets)
+//   * accumulator-empty barrier lives in the leader and counts the epilogue warps of both CTAs (remote arrive)
+//   * TMEM is allocated / freed with cta_group::2 by warp 1 of each CTA; cluster barriers bracket the kernel and the
+//     producer drains its empty barriers before exit so no multicast arrive can land in a retired CTA's smem.
+// Reference call sites: BasicBlock convs + downsample, SBL/transformer/video_frontend.py:10-12,28-41,68-72.
+#pragma once
+#include "sblk_common.cuh"
+#include "sblk_igemm.cuh"
+
+namespace sblk {
+
+// ------------------------------------------------------------------ cluster / cta_group::2 PTX wrappers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// TMA loads whose completion is signalled on an mbarrier given by its shared::cluster address (may be the peer's)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* d, uint32_t bar_cluster_addr, int c0,
+                                             int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(void* smem_dst, const CUtensorMap* d, uint32_t bar_cluster_addr,
+                                                    int c, int w, int h, int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(d)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all previously issued MMAs retired) on the barrier at this smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
+template <int BLOCK_N, bool DUAL = false>
+struct Igemm2Cfg {
+  static constexpr int BLOCK_M = 128;                 // rows per CTA; the pair computes 256
+  static constexpr int PAIR_M = 256;
+  static constexpr int BLOCK_K = 64;
+  static constexpr int BH = BLOCK_N / 2;              // B rows staged by each CTA
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BH * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + (DUAL ? 2 : 1) * B_BYTES;
+  static constexpr int STAGES = (227 * 1024 - 2048) / STAGE_BYTES;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = (DUAL ? 2 : 1) * ACC_STAGES * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+  static constexpr int THREADS = 192;
+};
+
+template <int BLOCK_N, bool IM2COL, bool DUAL = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
+  using Cfg = Igemm2Cfg<BLOCK_N, DUAL>;
+  static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+  static_assert(!DUAL || (IM2COL && BLOCK_N == 128), "DUAL needs im2col and BLOCK_N = 128");
+  static_assert(Cfg::TMEM_COLS <= 512, "TMEM");
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr uint32_t IDESC = make_idesc_bf16(Cfg::PAIR_M, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[STAGES];
+  __shared__ uint64_t empty_bar[STAGES];
+  __shared__ uint64_t tfull_bar[Cfg::ACC_STAGES];
+  __shared__ uint64_t tempty_bar[Cfg::ACC_STAGES];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+  const int warp = uniform_warp_idx();
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  const int n_tiles = p.N / BLOCK_N;
+  const int m_pairs = (p.M + Cfg::PAIR_M - 1) / Cfg::PAIR_M;
+  const int num_tiles = m_pairs * n_tiles;
+  const int num_kb = p.taps_r * p.taps_s * p.cblocks;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (DUAL) tma_prefetch_desc(&tmB2);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);    // used in the leader only: one expect_tx arrive covering both CTAs' bytes
+      mbar_init(&empty_bar[i], 1);   // one multicast commit per use
+    }
+#pragma unroll
+    for (int i = 0; i < Cfg::ACC_STAGES; ++i) {
+      mbar_init(&tfull_bar[i], 1);   // one multicast commit per tile
+      mbar_init(&tempty_bar[i], 8);  // used in the leader only: 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2cta(&tmem_base_slot, Cfg::TMEM_COLS);
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // barrier inits of both CTAs are visible cluster-wide before any remote arrive / TMA signal
+  tc_fence_after_sync();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_slot, 0);
+
+  grid_dep_launch();  // PDL: let the next kernel start its prologue now; its own wait orders the data
+  grid_dep_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs): own A rows, own half of the B tile
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int m0 = m_blk * Cfg::PAIR_M + static_cast<int>(rank) * Cfg::BLOCK_M;
+      const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * Cfg::BH;
+      int img = 0, base_w = 0, base_h = 0;
+      if (IM2COL) {
+        const int pq = p.P * p.Q;
+        img = m0 / pq;
+        const int rem = m0 - img * pq;
+        const int ph = rem / p.Q;
+        const int qw = rem - ph * p.Q;
+        base_w = qw * p.stride - p.pad;
+        base_h = ph * p.stride - p.pad;
+      }
+      int cb = 0, r = 0, s = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0401);
+        uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+        uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+        const bool centre = DUAL && r == p.taps_r / 2 && s == p.taps_s / 2;
+        const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
+        if (elect_one()) {
+          if (leader)
+            mbar_arrive_expect_tx(&full_bar[stage], 2u * (Cfg::A_BYTES + Cfg::B_BYTES + (centre ? Cfg::B_BYTES : 0)));
+          if (centre) tma2_load_2d(b_dst + Cfg::B_BYTES, &tmB2, bar, cb * 64, n0);
+          if (IM2COL) {
+            tma2_load_im2col_4d(a_dst, &tmA, bar, cb * 64, base_w, base_h, img, static_cast<uint16_t>(s),
+                                static_cast<uint16_t>(r));
+          } else {
+            tma2_load_2d(a_dst, &tmA, bar, kb * 64, m0);
+          }
+          tma2_load_2d(b_dst, &tmB, bar, kb * 64, n0);
+        }
+        __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++s == p.taps_s) { s = 0; ++r; }
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    // drain: every slot this CTA filled has been released (no multicast arrive can land after this CTA retires)
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0405);
+      if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer: leader CTA only (one elected lane issues)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x0402);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        const uint32_t d_tmem2 = tmem_base + static_cast<uint32_t>((Cfg::ACC_STAGES + acc) * BLOCK_N);
+        const int centre_kb0 = ((p.taps_r / 2) * p.taps_s + p.taps_s / 2) * p.cblocks;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 0x0403);
+          tc_fence_after_sync();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint64_t da = make_desc_sw128(a_addr);
+          const uint64_t db = make_desc_sw128(a_addr + Cfg::A_BYTES);
+          const uint32_t da_lo = static_cast<uint32_t>(da), db_lo = static_cast<uint32_t>(db);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / 16; ++k) {
+              umma2_bf16(d_tmem, desc_with_lo(da, da_lo + 2 * k), desc_with_lo(db, db_lo + 2 * k), IDESC,
+                         (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            if (DUAL && kb >= centre_kb0 && kb < centre_kb0 + p.cblocks) {
+#pragma unroll
+              for (int k = 0; k < Cfg::BLOCK_K / 16; ++k)
+                umma2_bf16(d_tmem2, desc_with_lo(da, da_lo + 2 * k),
+                           desc_with_lo(db, db_lo + static_cast<uint32_t>(Cfg::B_BYTES / 16 + 2 * k)), IDESC,
+                           (kb > centre_kb0 || k > 0) ? 1u : 0u);
+            }
+            umma2_commit_mc(&empty_bar[stage]);                      // frees the slot in both CTAs
+            if (kb == num_kb - 1) umma2_commit_mc(&tfull_bar[acc]);  // accumulators complete in both CTAs
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4), both CTAs
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair_id; tile < num_tiles; tile += num_pairs) {
+      const int m_blk = tile / n_tiles;
+      const int n_blk = tile - m_blk * n_tiles;
+      const int m = m_blk * Cfg::PAIR_M + static_cast<int>(rank) * Cfg::BLOCK_M + row;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tfull_bar[acc], acc_phase, 0x0404);
+      tc_fence_after_sync();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(acc * BLOCK_N);
+      const size_t row_off = static_cast<size_t>(m) * static_cast<size_t>(p.ldo);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + static_cast<uint32_t>(c * 32), v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int n0 = n_blk * BLOCK_N + c * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(bp + j);
+              f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
+            }
+          }
+          if (p.residual != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 r4 = __ldg(rp + j);
+              f[8 * j + 0] += bf16_lo(r4.x); f[8 * j + 1] += bf16_hi(r4.x);
+              f[8 * j + 2] += bf16_lo(r4.y); f[8 * j + 3] += bf16_hi(r4.y);
+              f[8 * j + 4] += bf16_lo(r4.z); f[8 * j + 5] += bf16_hi(r4.z);
+              f[8 * j + 6] += bf16_lo(r4.w); f[8 * j + 7] += bf16_hi(r4.w);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+          if (p.out_bf16 != nullptr) {
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + row_off + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              op[j] = o;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + row_off + n0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        }
+      }
+      if (DUAL) {
+        // downsample branch: accumulator 2, + bias2, no ReLU, no residual
+        const uint32_t t_row2 = t_row + static_cast<uint32_t>(Cfg::ACC_STAGES * BLOCK_N);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row2 + static_cast<uint32_t>(c * 32), v);
+          tmem_ld_wait();
+          if (row_ok) {
+            const int n0 = n_blk * BLOCK_N + c * 32;
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + n0);
+            uint4* op = reinterpret_cast<uint4*>(p.out2_bf16 + row_off + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
+              o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
+              o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
+              o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
+              op[j] = o;
+            }
+          }
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // the leader's barrier
+      if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs are done with each other's smem / TMEM / barriers
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace sblk

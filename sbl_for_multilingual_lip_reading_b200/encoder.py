@@ -6,9 +6,11 @@ attention.py / module.py / utils.py it uses).
 `enc_out, *_ = self.encoder(...)`, transformer/transformer.py:38).  Submodules are parameter holders with the
 reference's names and initialisation; the forward pass runs libsblk kernels only:
 
-    cast -> linear_in (tcgen05 GEMM) -> LayerNorm + PE  -> n_layers x {
-        packed QKV GEMM (tcgen05) -> fused softmax attention -> fc GEMM -> residual + LayerNorm (+pad mask)
+    cast -> linear_in GEMM -> LayerNorm + PE  -> n_layers x {
+        [per-head QKV projection + softmax attention] (one launch) -> fc GEMM -> residual + LayerNorm (+pad mask)
         w_1 GEMM + ReLU -> w_2 GEMM -> residual + LayerNorm (+pad mask) }
+    (GEMM -> LayerNorm pairs: split-K partials summed by the LayerNorm kernel at small token counts, one
+    cluster-fused launch at large ones; see ops.linear_ln)
 
 The residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation.
 Masks are never materialised: `input_lengths` goes to the kernels as an int32 vector
@@ -151,8 +153,12 @@ class Encoder(nn.Module):
             ops.cast_bf16(a.w_ks.weight.detach().contiguous(), out=wqkv[hk:2 * hk])
             ops.cast_bf16(a.w_vs.weight.detach().contiguous(), out=wqkv[2 * hk:3 * hk])
             bqkv = torch.cat([a.w_qs.bias.detach(), a.w_ks.bias.detach(), a.w_vs.bias.detach()]).contiguous()
+            # head-major copy (q_h | k_h | v_h per head) for the fused projection + attention kernel
+            wheads, bheads = ops.pack_qkv_heads(wqkv[0:hk], wqkv[hk:2 * hk], wqkv[2 * hk:3 * hk],
+                                                a.w_qs.bias.detach(), a.w_ks.bias.detach(), a.w_vs.bias.detach(),
+                                                self.n_head, self.d_k)
             pk.layers.append(dict(
-                wqkv=wqkv, bqkv=bqkv,
+                wqkv=wqkv, bqkv=bqkv, wheads=wheads, bheads=bheads,
                 wfc=ops.cast_bf16(a.fc.weight.detach().contiguous()),
                 w1=ops.cast_bf16(f.w_1.weight.detach().contiguous()),
                 w2=ops.cast_bf16(f.w_2.weight.detach().contiguous())))
@@ -174,26 +180,28 @@ class Encoder(nn.Module):
         pe = self.positional_encoding.pe[0]
         last = len(self.layer_stack) - 1
         x16 = ops.cast_bf16(xs)
-        _, h32 = ops.gemm(x16, pk.w_in, bias=self.linear_in.bias.detach(), out_f32=True)
-        # encoder.py:53-55 — LN(linear_in(x)) + PE ; no pad mask at this point
-        x32, x16 = ops.add_layernorm(h32, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
-                                     pe=pe, T=t, eps=self.layer_norm_in.eps,
-                                     out_f32=out[n0 * t:n1 * t] if last < 0 else None)
+        # encoder.py:53-55 — LN(linear_in(x)) + PE in one launch ; no pad mask at this point
+        x32, x16 = ops.linear_ln(x16, pk.w_in, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
+                               bias=self.linear_in.bias.detach(), pe=pe, T=t, eps=self.layer_norm_in.eps,
+                               out_f32=out[n0 * t:n1 * t] if last < 0 else None)
         for li, (lyr, w) in enumerate(zip(self.layer_stack, pk.layers)):
             a, f = lyr.slf_attn, lyr.pos_ffn
-            qkv16, _ = ops.gemm(x16, w["wqkv"], bias=w["bqkv"], out_bf16=True)
-            att16, probs = ops.attention(qkv16, nc, t, self.n_head, self.d_k, lengths=lens_c,
-                                         want_probs=return_attns, scale=1.0 / a.temperature)
-            _, o32 = ops.gemm(att16, w["wfc"], bias=a.fc.bias.detach(), out_f32=True)
-            x32, x16 = ops.add_layernorm(o32, a.layer_norm.weight.detach(), a.layer_norm.bias.detach(),
-                                         residual=x32, lengths=lens_c, T=t, eps=a.layer_norm.eps)
-            h16, _ = ops.gemm(x16, w["w1"], bias=f.w_1.bias.detach(), relu=True, out_bf16=True)
-            _, o32 = ops.gemm(h16, w["w2"], bias=f.w_2.bias.detach(), out_f32=True)
-            x32, x16 = ops.add_layernorm(o32, f.layer_norm.weight.detach(), f.layer_norm.bias.detach(),
-                                         residual=x32, lengths=lens_c, T=t, eps=f.layer_norm.eps,
-                                         want_bf16=li != last, out_f32=out[n0 * t:n1 * t] if li == last else None)
-            if return_attns:
+            if return_attns:  # attention maps requested: unfused projection + attention kernel that writes them
+                qkv16, _ = ops.gemm(x16, w["wqkv"], bias=w["bqkv"], out_bf16=True)
+                att16, probs = ops.attention(qkv16, nc, t, self.n_head, self.d_k, lengths=lens_c,
+                                             want_probs=True, scale=1.0 / a.temperature)
                 attns.append(probs)
+            else:
+                att16 = ops.qkv_attention(x16, w["wheads"], w["bheads"], nc, t, self.n_head, self.d_k,
+                                          lengths=lens_c, scale=1.0 / a.temperature)
+            # attention.py:57-58 — fc + LayerNorm(out + residual), then `*= non_pad_mask` (encoder.py:86)
+            x32, x16 = ops.linear_ln(att16, w["wfc"], a.layer_norm.weight.detach(), a.layer_norm.bias.detach(),
+                                   bias=a.fc.bias.detach(), residual=x32, lengths=lens_c, T=t, eps=a.layer_norm.eps)
+            # module.py:49-51 — w_2(relu(w_1(x))) + LayerNorm(out + x), then `*= non_pad_mask` (encoder.py:89)
+            h16, _ = ops.gemm(x16, w["w1"], bias=f.w_1.bias.detach(), relu=True, out_bf16=True)
+            x32, x16 = ops.linear_ln(h16, w["w2"], f.layer_norm.weight.detach(), f.layer_norm.bias.detach(),
+                                   bias=f.w_2.bias.detach(), residual=x32, lengths=lens_c, T=t, eps=f.layer_norm.eps,
+                                   want_bf16=li != last, out_f32=out[n0 * t:n1 * t] if li == last else None)
 
     def forward(self, padded_input, input_lengths, return_attns=False):
         """padded_input: N x T x d_input (fp32, CUDA); input_lengths: N ints -> (enc_output N x T x d_model,)"""

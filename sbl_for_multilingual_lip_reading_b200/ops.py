@@ -307,6 +307,93 @@ def add_layernorm(x, gamma, beta, residual=None, pe=None, lengths=None, T=1, eps
     return o32, o16
 
 
+def gemm_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, T=1, eps=1e-5, want_f32=True,
+            want_bf16=True, out_f32=None):
+    """LayerNorm(a @ w.T + bias + residual) * gamma + beta (+ pe[m % T]) (* pad mask) in one launch.
+    a bf16 [M,K], w bf16 [512,K], residual fp32 [M,512] -> (fp32 [M,512] | None, bf16 [M,512] | None)."""
+    _req(a, BF16, "a"); _req(w, BF16, "w"); _req(bias, F32, "bias"); _req(residual, F32, "residual")
+    _req(gamma, F32, "gamma"); _req(beta, F32, "beta"); _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths")
+    _req(out_f32, F32, "out_f32")
+    m, k = a.shape
+    n, k2 = w.shape
+    if k2 != k:
+        raise RuntimeError(f"gemm_ln: K mismatch {k} vs {k2}")
+    if residual is not None and tuple(residual.shape) != (m, n):
+        raise RuntimeError(f"gemm_ln: residual shape {tuple(residual.shape)} != {(m, n)}")
+    if out_f32 is not None and tuple(out_f32.shape) != (m, n):
+        raise RuntimeError(f"gemm_ln: out_f32 shape {tuple(out_f32.shape)} != {(m, n)}")
+    o32 = out_f32 if out_f32 is not None else (torch.empty((m, n), dtype=F32, device=a.device) if want_f32 else None)
+    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if want_bf16 else None
+    _call("sblk_gemm_ln_fwd", f"gemm+ln K={k}", 2 * m * n * k,
+          2 * (m * k + n * k) + m * n * ((4 if residual is not None else 0) + (4 if o32 is not None else 0) +
+                                         (2 if want_bf16 else 0)),
+          _p(a), _p(w), _p(bias), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths), _p(o32), _p(o16), m, n, k, T,
+          eps, _stream())
+    return o32, o16
+
+
+def linear_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, T=1, eps=1e-5, want_bf16=True,
+              out_f32=None):
+    """LayerNorm(a @ w.T + bias + residual) * gamma + beta (+ pe) (* pad mask) -> (fp32 [M,512], bf16 [M,512] | None).
+
+    Strategy by token count: when a 128-row tiling already fills the machine the cluster-fused kernel (gemm_ln) does
+    it in one launch; at small M (the BASELINE 928 tokens) the GEMM is operand-delivery bound per SM, so it runs
+    split-K over all SMs into fp32 partials that the LayerNorm kernel sums (deterministic, no atomics)."""
+    _req(a, BF16, "a"); _req(w, BF16, "w")
+    m, k = a.shape
+    n = w.shape[0]
+    splits = int(_lib.load().sblk_gemm_splitk_plan(m, n, k))
+    if splits < 1:
+        raise RuntimeError(f"linear_ln: {_lib.last_error()}")
+    if splits == 1 and (m + 127) // 128 * 4 >= 64:
+        return gemm_ln(a, w, gamma, beta, bias=bias, residual=residual, pe=pe, lengths=lengths, T=T, eps=eps,
+                       want_bf16=want_bf16, out_f32=out_f32)
+    _req(bias, F32, "bias"); _req(residual, F32, "residual"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta")
+    _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths"); _req(out_f32, F32, "out_f32")
+    if w.shape[1] != k or n != 512:
+        raise RuntimeError(f"linear_ln: weight shape {tuple(w.shape)} does not match K={k}, d_model=512")
+    parts = torch.empty((splits, m, n), dtype=F32, device=a.device)
+    _call("sblk_gemm_splitk_fwd", f"gemm splitK={splits} N={n} K={k}", 2 * m * n * k,
+          2 * (m * k + n * k) + 4 * splits * m * n, _p(a), _p(w), None, _p(parts), m, n, k, splits, _stream())
+    o32 = out_f32 if out_f32 is not None else torch.empty((m, n), dtype=F32, device=a.device)
+    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if want_bf16 else None
+    _call("sblk_sum_layernorm_fwd", f"sum{splits}+layernorm", 0,
+          m * n * (4 * splits + (4 if residual is not None else 0) + 4 + (2 if want_bf16 else 0)),
+          _p(parts), splits, _p(bias), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths), _p(o32), _p(o16), m, T, n,
+          eps, _stream())
+    return o32, o16
+
+
+def pack_qkv_heads(wq, wk, wv, bq, bk, bv, h, d_k=64):
+    """bf16 [h*d_k, K] x3 + fp32 [h*d_k] x3 -> head-major (bf16 [h*3*d_k, K], fp32 [h*3*d_k]) for qkv_attention
+    (pure re-indexing of already packed weights; no arithmetic)."""
+    for t_, n_ in ((wq, "wq"), (wk, "wk"), (wv, "wv")):
+        _req(t_, BF16, n_)
+    for t_, n_ in ((bq, "bq"), (bk, "bk"), (bv, "bv")):
+        _req(t_, F32, n_)
+    k = wq.shape[1]
+    w = torch.stack([wq.view(h, d_k, k), wk.view(h, d_k, k), wv.view(h, d_k, k)], dim=1).reshape(h * 3 * d_k, k)
+    b = torch.stack([bq.view(h, d_k), bk.view(h, d_k), bv.view(h, d_k)], dim=1).reshape(h * 3 * d_k)
+    return w.contiguous(), b.contiguous()
+
+
+def qkv_attention(x, w_heads, b_heads, n, t, h, d_k=64, lengths=None, scale=None):
+    """x bf16 [n*t, K] -> heads-concatenated self-attention output bf16 [n*t, h*d_k] (projection + attention fused)."""
+    _req(x, BF16, "x"); _req(w_heads, BF16, "w_heads"); _req(b_heads, F32, "b_heads")
+    _req(lengths, torch.int32, "lengths")
+    k = x.shape[1]
+    if tuple(x.shape) != (n * t, k) or tuple(w_heads.shape) != (h * 3 * d_k, k) or b_heads.numel() != h * 3 * d_k:
+        raise RuntimeError(f"qkv_attention: shapes x{tuple(x.shape)} w{tuple(w_heads.shape)} do not match "
+                           f"n={n} t={t} h={h} d_k={d_k}")
+    out = torch.empty((n * t, h * d_k), dtype=BF16, device=x.device)
+    if scale is None:
+        scale = 1.0 / (d_k ** 0.5)
+    _call("sblk_qkv_attention_fwd", f"qkv+attention T={t}", 2 * n * t * 3 * h * d_k * k + 4 * n * h * t * t * d_k,
+          2 * (x.numel() + w_heads.numel() + out.numel()),
+          _p(x), _p(w_heads), _p(b_heads), _p(lengths), _p(out), n, t, h, d_k, k, scale, _stream())
+    return out
+
+
 def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
     _req(qkv, BF16, "qkv"); _req(lengths, torch.int32, "lengths")
     if tuple(qkv.shape) != (n * t, 3 * h * d_k):

@@ -351,6 +351,63 @@ def sec_conv3d():
             print("   bad by channel[:16]:", (d > thr).float().mean(dim=(0, 1, 2)).tolist()[:16])
 
 
+def sec_enc():
+    """Fused encoder kernels: gemm+LayerNorm (cluster of 4) and per-head QKV projection + attention."""
+    g = torch.Generator(device="cpu").manual_seed(6)
+    for (N, T, K, lens) in [(4, 29, 512, None), (32, 29, 2048, None), (3, 40, 512, [40, 17, 1]), (1, 1, 512, None),
+                            (5, 7, 2048, [7, 3, 0, 7, 1]), (2, 100, 512, None)]:
+        M = N * T
+        a = bf(torch.randn(M, K, generator=g)).to(DEV)
+        w = bf(torch.randn(512, K, generator=g) / K ** 0.5).to(DEV)
+        bias = torch.randn(512, generator=g).to(DEV)
+        res = torch.randn(M, 512, generator=g).to(DEV)
+        gm = torch.randn(512, generator=g).to(DEV)
+        bt = torch.randn(512, generator=g).to(DEV)
+        pe = torch.randn(128, 512, generator=g).to(DEV)
+        lt = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=DEV)
+        o32, o16 = ops.gemm_ln(a, w, gm, bt, bias=bias, residual=res, pe=pe, lengths=lt, T=T)
+        torch.cuda.synchronize()
+        ref = F.layer_norm(a.float() @ w.float().t() + bias + res, (512,), gm, bt, 1e-5) + pe[:T].repeat(N, 1)
+        if lens is not None:
+            ref = ref * (torch.arange(T, device=DEV)[None, :] < lt[:, None]).reshape(-1, 1).float()
+        ok = report(f"gemm_ln N{N} T{T} K{K} lens={lens} f32", o32, ref, tol=2e-4)
+        report(f"gemm_ln N{N} T{T} K{K} bf16", o16, bf(ref))
+        if not ok:
+            pattern("gemm_ln", o32, ref)
+        l32, l16 = ops.linear_ln(a, w, gm, bt, bias=bias, residual=res, pe=pe, lengths=lt, T=T)
+        report(f"linear_ln N{N} T{T} K{K} f32", l32, ref, tol=2e-4)
+        report(f"linear_ln N{N} T{T} K{K} bf16", l16, bf(ref))
+        o32, _ = ops.gemm_ln(a, w, gm, bt, T=T, want_bf16=False)
+        report(f"gemm_ln plain N{N} T{T} K{K}", o32, F.layer_norm(a.float() @ w.float().t(), (512,), gm, bt, 1e-5),
+               tol=2e-4)
+
+
+def sec_enc2():
+    g = torch.Generator(device="cpu").manual_seed(7)
+    H = 8
+    for (N, T, lens) in [(4, 29, None), (32, 29, None), (3, 40, [40, 17, 1]), (2, 100, [100, 64]), (1, 1, None),
+                         (9, 7, None), (5, 31, [31, 1, 5, 31, 30]), (3, 64, None), (2, 65, None), (130, 1, None)]:
+        K = 512
+        x = bf(torch.randn(N * T, K, generator=g)).to(DEV)
+        wq, wk, wv = [bf(torch.randn(H * 64, K, generator=g) / K ** 0.5).to(DEV) for _ in range(3)]
+        bq, bk, bv = [torch.randn(H * 64, generator=g).to(DEV) for _ in range(3)]
+        wh, bh = ops.pack_qkv_heads(wq, wk, wv, bq, bk, bv, H)
+        lt = None if lens is None else torch.tensor(lens, dtype=torch.int32, device=DEV)
+        out = ops.qkv_attention(x, wh, bh, N, T, H, lengths=lt)
+        torch.cuda.synchronize()
+        # reference = the unfused kernels' semantics: bf16-rounded projections, fp32 attention
+        q, k, v = [bf(x.float() @ w_.float().t() + b_).float().reshape(N, T, H, 64).permute(2, 0, 1, 3)
+                   .reshape(H * N, T, 64) for w_, b_ in ((wq, bq), (wk, bk), (wv, bv))]
+        att = torch.bmm(q, k.transpose(1, 2)) / 8.0
+        if lens is not None:
+            km = (torch.arange(T, device=DEV)[None, :] >= lt[:, None])
+            att = att.masked_fill(km[:, None, :].expand(N, T, T).repeat(H, 1, 1), float("-inf"))
+        o = torch.bmm(torch.softmax(att, dim=2), v).reshape(H, N, T, 64).permute(1, 2, 0, 3).reshape(N * T, H * 64)
+        ok = report(f"qkv_attention N{N} T{T} lens={lens}", out, bf(o))
+        if not ok:
+            pattern("qkv_attention", out, o, rows_mod=T)
+
+
 def sec_perf():
     """Quick per-layer timing at the C2 shape (F = 928) to see where the time goes."""
     g = torch.Generator(device="cpu").manual_seed(5)
@@ -425,7 +482,7 @@ if __name__ == "__main__":
         ops.set_pdl(True)
         print("PDL enabled")
     try:
-        {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d, "flat": sec_flat,
+        {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d, "flat": sec_flat, "enc": sec_enc, "enc2": sec_enc2,
          "perf": sec_perf}[sec]()
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
