@@ -61,11 +61,12 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* x_prepped_bf16, const void* w_packe
 /* Rows of the zero-haloed flat activation layout for F frames of H x W pixels:
  * pixel (f,y,x) -> row (f*(H+1) + 1 + y)*(W+2) + 1 + x of a [rows, C] bf16 matrix; all other rows are zero. */
 long long sblk_flat_rows(int F, int H, int W);
-/* Stride-1 3x3 / pad 1 Conv2d (C -> C, C == 64) + folded BN (+ residual) (+ ReLU) over the flat layout
- * (flat_out of sblk_conv3d_bn_relu_pool_fwd or a previous call); output is again flat with zero halos.
- * w_packed_bf16 is [C][10*C]: the 9 taps of sblk_pack_conv2d's [C][3][3][C] followed by a CxC identity
- * (the residual is accumulated by the tensor core as R*I).
- * replaces: the four 64->64 convs of ResNet layer1, transformer/video_frontend.py:10-12,28-41 */
+/* Stride-1 3x3 / pad 1 Conv2d (C -> C, C == 64 or 128) + folded BN (+ residual) (+ ReLU) over the flat layout
+ * (flat_out of sblk_conv3d_bn_relu_pool_fwd / sblk_conv2d_dual_igemm_fwd or a previous call); output is again flat
+ * with zero halos.  w_packed_bf16 is [C][10*C]: the 9 taps of sblk_pack_conv2d's [C][3][3][C] followed by a CxC
+ * identity (used only by the single-CTA C == 64 kernel, which accumulates the residual on the tensor core as R*I).
+ * W + 2 <= 31 for C == 64, <= 15 for C == 128.  CTA-pair (cta_group::2) shifted-window implicit GEMM.
+ * replaces: the stride-1 convs of ResNet layer1 and layer2, transformer/video_frontend.py:10-12,28-41 */
 int sblk_flatconv3x3_fwd(const void* x_flat, const void* w_packed_bf16, const float* bias, const void* residual_flat,
                          void* out_flat, int F, int H, int W, int C, int relu, void* stream);
 /* Implicit-GEMM Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) over bf16 NHWC [F,H,W,Cin] with folded BN:
@@ -81,11 +82,13 @@ int sblk_conv2d_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const f
 /* BasicBlock head of layers 2-4 in one launch: out = relu(conv3x3_stride_s(x) + bias) and the downsample branch
  * out_ds = conv1x1_stride_s(x) + bias_ds.  The 1x1 conv reads exactly the centre-tap A tiles of the 3x3 conv, so
  * both share one pass over x (second TMEM accumulator).  w_ds_packed is [Cout][1][1][Cin]; Cout % 128 == 0.
- * replaces: BasicBlock.conv1/bn1/relu + downsample(conv1x1, bn), transformer/video_frontend.py:30-32,35-36,68-72 */
+ * replaces: BasicBlock.conv1/bn1/relu + downsample(conv1x1, bn), transformer/video_frontend.py:30-32,35-36,68-72
+ * flat_out = 1 writes both outputs into the zero-haloed flat layout (pixel rows only: the caller provides buffers
+ * whose halo rows are already zero), so a stride-1 sblk_flatconv3x3_fwd can consume them directly. */
 int sblk_conv2d_dual_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const float* bias,
                                const void* w_ds_packed_bf16, const float* bias_ds, void* out_bf16, void* out_ds_bf16,
                                int F, int H, int W, int Cin, int Cout, int stride, int relu, int in_row_pitch,
-                               int in_frame_pitch, void* stream);
+                               int in_frame_pitch, int flat_out, void* stream);
 /* bf16 NHWC [F,HW,C] -> mean over HW: fp32 [F,C] and/or bf16 [F,C] (either may be NULL).
  * replaces: nn.AdaptiveAvgPool2d(1) + view, transformer/video_frontend.py:87-88 */
 int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);

@@ -16,6 +16,7 @@
 #include "sblk_igemm2.cuh"
 #include "sblk_conv3d.cuh"
 #include "sblk_flatconv.cuh"
+#include "sblk_flatconv2.cuh"
 #include "sblk_aux.cuh"
 #include "sblk_attention.cuh"
 #include "sblk_gemm_ln.cuh"
@@ -120,6 +121,8 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::flatconv3x3_c64_kernel, sblk::fc::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::flatconv2_kernel<1>, sblk::Fc2Cfg<1>::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::flatconv2_kernel<2>, sblk::Fc2Cfg<2>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::gemm_ln512_kernel, sblk::gln::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::qkv_attention_kernel<4>, sblk::qa::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::qkv_attention_kernel<8>, sblk::qa::SMEM_BYTES))) return rc;
@@ -290,8 +293,10 @@ int sblk_prep_clip(const float* x, void* out, int N, int T, void* stream) {
   if (!x || !out) return fail(-1, "sblk_prep_clip: null pointer");
   if (N <= 0 || T <= 0) return fail(-1, "sblk_prep_clip: bad shape N=%d T=%d", N, T);
   if (!aligned16(out)) return fail(-1, "sblk_prep_clip: output must be 16-byte aligned");
-  const long long items = static_cast<long long>(N) * (T + 2 * sblk::c3d::TPAD) * sblk::c3d::FRAME_ENTRIES;
-  return launch(sblk::prep_clip_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
+  const long long rows = static_cast<long long>(N) * (T + 2 * sblk::c3d::TPAD) * 2 * sblk::c3d::PLANE_ROWS;
+  long long grid = (rows + 7) / 8;   // one warp per plane row, 8 warps per CTA
+  if (grid > static_cast<long long>(sms) * 8) grid = static_cast<long long>(sms) * 8;
+  return launch(sblk::prep_clip_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
                 static_cast<cudaStream_t>(stream), false, "prep_clip_kernel", x, static_cast<uint4*>(out), N, T);
 }
 
@@ -333,19 +338,63 @@ long long sblk_flat_rows(int F, int H, int W) {
   return (static_cast<long long>(F) * (H + 1) + 1) * (W + 2);
 }
 
+extern "C++" {
+template <int CB>
+static int launch_flatconv2(const void* x, const void* wp, const float* bias, const void* residual, void* out,
+                            long long rows, int H, int W, int relu, int sms, cudaStream_t stream) {
+  using Cfg = sblk::Fc2Cfg<CB>;
+  constexpr int C = Cfg::C;
+  int rc;
+  if (2 * (W + 3) + Cfg::TILE_M > Cfg::BOX_PIX)
+    return fail(-1, "sblk_flatconv3x3_fwd: W=%d too wide for the %d-row staged run of the C=%d kernel", W,
+                Cfg::BOX_PIX, C);
+  CUtensorMap tmX, tmW, tmR, tmO;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+    cuuint32_t box[2] = {64, Cfg::BOX_PIX};
+    if ((rc = encode_tiled(&tmX, x, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    cuuint32_t rbox[2] = {64, Cfg::TILE_M};
+    if ((rc = encode_tiled(&tmR, residual ? residual : x, 2, dims, strides, rbox, CU_TENSOR_MAP_SWIZZLE_128B)))
+      return rc;
+    if ((rc = encode_tiled(&tmO, out, 2, dims, strides, rbox, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  {
+    // packed filter [C][10*C]: tap (r,s) at K columns (3r+s)*C .. ; the trailing CxC identity is not used here
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(10 * C), static_cast<cuuint64_t>(C)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(10 * C) * 2};
+    cuuint32_t box[2] = {64, Cfg::BH};
+    if ((rc = encode_tiled(&tmW, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
+  sblk::FlatConv2Params p;
+  p.m_total = static_cast<int>(rows);
+  p.num_tiles = (p.m_total + 255) / 256;
+  p.H = H; p.W = W; p.relu = relu; p.has_res = residual ? 1 : 0;
+  p.bias = bias;
+  const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+  return launch(sblk::flatconv2_kernel<CB>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, true,
+                "flatconv2_kernel", tmX, tmW, tmR, tmO, p);
+}
+}  // extern "C++"
+
 int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                          int H, int W, int C, int relu, void* stream) {
   using namespace sblk::fc;
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !wp || !bias || !out) return fail(-1, "sblk_flatconv3x3_fwd: null pointer");
-  if (C != 64) return fail(-1, "sblk_flatconv3x3_fwd: only 64 -> 64 channels are implemented (got %d)", C);
+  if (C != 64 && C != 128)
+    return fail(-1, "sblk_flatconv3x3_fwd: only 64 -> 64 and 128 -> 128 channels are implemented (got %d)", C);
   if (F <= 0 || H <= 0 || W <= 0 || W + 2 > 31)
     return fail(-1, "sblk_flatconv3x3_fwd: bad shape F=%d H=%d W=%d (W <= 29)", F, H, W);
   if (!aligned16(x) || !aligned16(wp) || !aligned16(out) || (residual && !aligned16(residual)) || !aligned16(bias))
     return fail(-1, "sblk_flatconv3x3_fwd: pointers must be 16-byte aligned");
   const long long rows = sblk_flat_rows(F, H, W);
   if (rows > 0x7fffffffLL - 1024) return fail(-1, "sblk_flatconv3x3_fwd: problem too large");
+  const char* v2 = getenv("SBLK_FLATCONV2");   // 0 = single-CTA kernel for C == 64 (A/B timing experiments)
+  if (C == 128) return launch_flatconv2<2>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+  if (v2 == nullptr || atoi(v2) != 0)
+    return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
   CUtensorMap tmX, tmW, tmR;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows)};
@@ -382,30 +431,30 @@ int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const
 static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                              int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                              int in_row_pitch, int in_frame_pitch, const void* wp_ds, const float* bias_ds,
-                             void* out_ds, void* stream);
+                             void* out_ds, int flat_out, void* stream);
 
 int sblk_conv2d_igemm_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                           int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                           int in_row_pitch, int in_frame_pitch, void* stream) {
   return conv2d_igemm_impl(x, wp, bias, residual, out, F, H, W, Cin, Cout, R, S, stride, pad, relu, in_row_pitch,
-                           in_frame_pitch, nullptr, nullptr, nullptr, stream);
+                           in_frame_pitch, nullptr, nullptr, nullptr, 0, stream);
 }
 
 int sblk_conv2d_dual_igemm_fwd(const void* x, const void* wp, const float* bias, const void* wp_ds,
                                const float* bias_ds, void* out, void* out_ds, int F, int H, int W, int Cin, int Cout,
-                               int stride, int relu, int in_row_pitch, int in_frame_pitch, void* stream) {
+                               int stride, int relu, int in_row_pitch, int in_frame_pitch, int flat_out, void* stream) {
   if (!wp_ds || !bias_ds || !out_ds || !bias) return fail(-1, "sblk_conv2d_dual_igemm_fwd: null pointer");
   if (!aligned16(wp_ds) || !aligned16(bias_ds) || !aligned16(out_ds))
     return fail(-1, "sblk_conv2d_dual_igemm_fwd: pointers must be 16-byte aligned");
   if (Cout % 128 != 0) return fail(-1, "sblk_conv2d_dual_igemm_fwd: Cout=%d must be a multiple of 128", Cout);
   return conv2d_igemm_impl(x, wp, bias, nullptr, out, F, H, W, Cin, Cout, 3, 3, stride, 1, relu, in_row_pitch,
-                           in_frame_pitch, wp_ds, bias_ds, out_ds, stream);
+                           in_frame_pitch, wp_ds, bias_ds, out_ds, flat_out, stream);
 }
 
 static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                              int H, int W, int Cin, int Cout, int R, int S, int stride, int pad, int relu,
                              int in_row_pitch, int in_frame_pitch, const void* wp_ds, const float* bias_ds,
-                             void* out_ds, void* stream) {
+                             void* out_ds, int flat_out, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !wp || !out) return fail(-1, "sblk_conv2d_igemm_fwd: null pointer");
@@ -455,10 +504,11 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     // CTA-pair kernel (sblk_igemm2.cuh) for every conv with Cout >= 128: half the B bytes per SM
     const int bn2 = use_cta_pairs() && Cout % 128 == 0 ? ((wp_ds || Cout % 256 != 0) ? 128 : 256) : 0;
     const int bn = bn2 ? bn2 : wp_ds ? 128 : pick_block_n(m_tiles, Cout, sms);
+    if (flat_out && !bn2) return fail(-1, "sblk_conv2d_dual_igemm_fwd: flat_out needs the CTA-pair kernel (Cout %% 128 == 0)");
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn2 ? bn2 / 2 : bn)};
     if ((rc = encode_tiled(&tmB, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     sblk::IgemmParams p;
-    p.splits = 1; p.split_stride = 0;
+    p.splits = 1; p.split_stride = 0; p.flat_out = flat_out;
     p.bias2 = bias_ds;
     p.out2_bf16 = static_cast<__nv_bfloat16*>(out_ds);
     p.debug_mode = 0;
@@ -560,7 +610,7 @@ static int gemm_impl(const void* a, const void* w, const float* bias, const void
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
-  p.splits = splits;
+  p.splits = splits; p.flat_out = 0;
   p.split_stride = static_cast<long long>(M) * N;
   return launch_igemm<false>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
 }

@@ -13,42 +13,63 @@ namespace sblk {
 // i.e. the Conv3d zero padding (2 frames, 3 px) is materialised and every 16-byte entry already holds the 8
 // consecutive input pixels one (dt, r) filter row multiplies for conv pixel x, so the stem kernel streams its A
 // operand with plain bulk copies.  Reference: input layout of Lipreading.forward, SBL/transformer/video_frontend.py:
-// 119-121 (+ Conv3d padding=(2,3,3), stride (1,2,2), :100).  One thread per entry (16-B store).
+// 119-121 (+ Conv3d padding=(2,3,3), stride (1,2,2), :100).
 // --------------------------------------------------------------------------------------------
+// One WARP per plane row (n, tp, pl, yy): the 88-pixel input row is read once with coalesced 16-byte loads into a
+// zero-bordered shared-memory line, every lane then assembles its entries (8 consecutive pixels at even offsets)
+// from that line and the warp stores 512 contiguous bytes.
 __global__ void __launch_bounds__(256)
 prep_clip_kernel(const float* __restrict__ x, uint4* __restrict__ out, int N, int T) {
   using namespace c3d;
+  __shared__ __align__(16) float line[8][104];   // [warp][3 zero | 88 pixels | zeros up to 2*43 + 8 = 94 (+ slack)]
   const int TP = T + 2 * TPAD;
-  const long long total = static_cast<long long>(N) * TP * FRAME_ENTRIES;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int e_in_plane = static_cast<int>(i % PLANE_ENTRIES);  // entries >= 47*44 are zero padding
-    long long r = i / PLANE_ENTRIES;
-    const int yy = e_in_plane / CONV_HW;
-    const int cx = e_in_plane - yy * CONV_HW;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long rows = static_cast<long long>(N) * TP * 2 * PLANE_ROWS;
+  float* ln = line[warp];
+  for (int i = lane; i < 104; i += 32) ln[i] = 0.0f;   // borders stay zero for the whole kernel
+  __syncwarp();
+  for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows;
+       row += static_cast<long long>(gridDim.x) * 8) {
+    const int yy = static_cast<int>(row % PLANE_ROWS);
+    long long r = row / PLANE_ROWS;
     const int pl = static_cast<int>(r & 1);
     r >>= 1;
     const int tp = static_cast<int>(r % TP);
     const int n = static_cast<int>(r / TP);
     const int t = tp - TPAD;
     const int y = 2 * yy + pl - 3;
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = 0.0f;
-    if (t >= 0 && t < T && y >= 0 && y < IN_HW && yy < PLANE_ROWS) {
-      const float* src = x + ((static_cast<long long>(n) * T + t) * IN_HW + y) * IN_HW;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int xx = cx * 2 + e - 3;
-        if (xx >= 0 && xx < IN_HW) v[e] = __ldg(src + xx);
+    const bool inside = t >= 0 && t < T && y >= 0 && y < IN_HW;   // warp-uniform
+    uint4* dst = out + ((static_cast<long long>(n) * TP + tp) * 2 + pl) * PLANE_ENTRIES + yy * CONV_HW;
+    if (inside) {
+      if (lane < IN_HW / 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+                                   x + ((static_cast<long long>(n) * T + t) * IN_HW + y) * IN_HW) + lane);
+        ln[3 + 4 * lane + 0] = v.x; ln[3 + 4 * lane + 1] = v.y; ln[3 + 4 * lane + 2] = v.z; ln[3 + 4 * lane + 3] = v.w;
       }
+      __syncwarp();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cx = lane + 32 * h;
+        if (cx < CONV_HW) {
+          const float2* src = reinterpret_cast<const float2*>(ln + 2 * cx);
+          const float2 a = src[0], b = src[1], c = src[2], d = src[3];
+          uint4 o;
+          o.x = pack_bf16x2(a.x, a.y);
+          o.y = pack_bf16x2(b.x, b.y);
+          o.z = pack_bf16x2(c.x, c.y);
+          o.w = pack_bf16x2(d.x, d.y);
+          dst[cx] = o;
+        }
+      }
+      __syncwarp();   // the line is rewritten by the next row
+    } else {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      dst[lane] = z;
+      if (lane + 32 < CONV_HW) dst[lane + 32] = z;
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]);
-    o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]);
-    o.w = pack_bf16x2(v[6], v[7]);
-    out[i] = o;
+    if (yy == PLANE_ROWS - 1 && lane < PLANE_ENTRIES - PLANE_ROWS * CONV_HW)
+      dst[CONV_HW + lane] = make_uint4(0u, 0u, 0u, 0u);   // the 4 zero entries that pad the plane to 128 bytes
   }
 }
 

@@ -40,6 +40,9 @@ struct IgemmParams {
   // fp32 partial to out_f32 + s * split_stride (bias added by split 0 only); the consumer sums the partials
   int splits;                      // >= 1
   long long split_stride;          // elements between partial outputs
+  // CTA-pair kernel only: write out / out2 into the zero-haloed flat layout of sblk_flatconv.cuh (halo rows are not
+  // touched: the caller keeps them zero), output pixel (f, y, x) -> row (f*(P+1) + 1 + y)*(Q+2) + 1 + x
+  int flat_out;
 };
 
 template <int BLOCK_N, bool DUAL = false>

@@ -267,7 +267,15 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_after_sync();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N);
-      const size_t row_off = static_cast<size_t>(m) * static_cast<size_t>(p.ldo);
+      size_t out_row = static_cast<size_t>(m);
+      if (IM2COL && p.flat_out) {
+        const int pq = p.P * p.Q;
+        const int fr = m / pq;
+        const int rem = m - fr * pq;
+        const int y = rem / p.Q;
+        out_row = (static_cast<size_t>(fr) * (p.P + 1) + 1 + y) * (p.Q + 2) + 1 + (rem - y * p.Q);
+      }
+      const size_t row_off = out_row * static_cast<size_t>(p.ldo);
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t v[32];
@@ -287,7 +295,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
           }
           if (p.residual != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.ldo + n0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 r4 = __ldg(rp + j);

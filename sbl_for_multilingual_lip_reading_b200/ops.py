@@ -185,7 +185,7 @@ def pack_flat_weight(wp):
 
 
 def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None):
-    """Stride-1 3x3 conv over FlatActs (C -> C, C = 64) -> FlatActs.  wp bf16 [C, 10*C] (pack_flat_weight)."""
+    """Stride-1 3x3 conv over FlatActs (C -> C, C = 64 or 128) -> FlatActs.  wp bf16 [C, 10*C] (pack_flat_weight)."""
     _req(x.data, BF16, "x"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
     c = x.c
     if tuple(wp.shape) != (c, 10 * c):
@@ -214,9 +214,11 @@ def _conv_input(x):
     return (x.data_ptr(), f, h, w, cin, 0, 0, x.numel())
 
 
-def conv2d_dual(x, wp, bias, wp_ds, bias_ds, stride=2, relu=True):
+def conv2d_dual(x, wp, bias, wp_ds, bias_ds, stride=2, relu=True, flat_ws=None):
     """BasicBlock head with a downsample branch in one launch:
-    (relu(conv3x3_s(x) + bias), conv1x1_s(x) + bias_ds), both bf16 NHWC [F,P,Q,Cout]."""
+    (relu(conv3x3_s(x) + bias), conv1x1_s(x) + bias_ds), both bf16 NHWC [F,P,Q,Cout].
+    flat_ws = (buf, buf_ds): two bf16 [flat_rows(F,P,Q), Cout] workspaces whose halo rows are zero -> both outputs are
+    written into them in the flat layout and returned as FlatActs (input of conv3x3_flat)."""
     _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(wp_ds, BF16, "wp_ds"); _req(bias_ds, F32, "bias_ds")
     xptr, f, h, w, cin, row_pitch, frame_pitch, x_elems = _conv_input(x)
     cout = wp.shape[0]
@@ -224,12 +226,20 @@ def conv2d_dual(x, wp, bias, wp_ds, bias_ds, stride=2, relu=True):
         raise RuntimeError(f"conv2d_dual: weight shapes {tuple(wp.shape)} / {tuple(wp_ds.shape)} do not match Cin={cin}")
     p = (h + 2 - 3) // stride + 1
     q = (w + 2 - 3) // stride + 1
-    out = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
-    out_ds = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
+    if flat_ws is not None:
+        out, out_ds = flat_ws
+        _req(out, BF16, "flat_ws[0]"); _req(out_ds, BF16, "flat_ws[1]")
+        if tuple(out.shape) != (flat_rows(f, p, q), cout) or tuple(out_ds.shape) != tuple(out.shape):
+            raise RuntimeError(f"conv2d_dual: flat workspaces must be [{flat_rows(f, p, q)}, {cout}]")
+    else:
+        out = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
+        out_ds = torch.empty((f, p, q, cout), dtype=BF16, device=wp.device)
     _call("sblk_conv2d_dual_igemm_fwd", f"conv3x3+ds H={h} {cin}->{cout} s{stride}", 2 * f * p * q * cout * 10 * cin,
-          2 * (x_elems + wp.numel() + wp_ds.numel() + 2 * out.numel()),
+          2 * (x_elems + wp.numel() + wp_ds.numel() + 2 * f * p * q * cout),
           xptr, _p(wp), _p(bias), _p(wp_ds), _p(bias_ds), _p(out), _p(out_ds), f, h, w, cin, cout, stride,
-          1 if relu else 0, row_pitch, frame_pitch, _stream())
+          1 if relu else 0, row_pitch, frame_pitch, 0 if flat_ws is None else 1, _stream())
+    if flat_ws is not None:
+        return FlatActs(out, f, p, q), FlatActs(out_ds, f, p, q)
     return out, out_ds
 
 

@@ -111,12 +111,18 @@ class Lipreading(nn.Module):
         self._initialize_weights()
         self.always_on_dropout = True
         self._packed = None
+        self._flat_ws = {}
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"] = None
+        st["_flat_ws"] = {}
         return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self.__dict__.setdefault("_flat_ws", {})
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -164,11 +170,30 @@ class Lipreading(nn.Module):
                 w1, b1 = fold(blk.conv1, blk.bn1)
                 w2, b2 = fold(blk.conv2, blk.bn2)
                 ds = fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
-                if layer is self.resnet18.layer1:  # flat shifted-window kernel: taps + identity (residual) packing
-                    w1, w2 = ops.pack_flat_weight(w1), ops.pack_flat_weight(w2)
+                # layer1 / layer2 run on the zero-haloed flat layout (shifted-window kernels): [C, 10*C] packing
+                flat = layer is self.resnet18.layer1 or layer is self.resnet18.layer2
+                if flat and blk.stride == 1:
+                    w1 = ops.pack_flat_weight(w1)
+                if flat:
+                    w2 = ops.pack_flat_weight(w2)
                 pk.blocks.append((blk.stride, w1, b1, w2, b2, ds))
         self._packed = pk
         return pk
+
+    def _flat_workspace(self, a, cout, stride):
+        """Two zero-initialised flat buffers for the outputs of a strided block head.  Only pixel rows are ever written
+        (sblk_conv2d_dual_igemm_fwd, flat_out), so the halo rows stay zero across calls; cached per (device, shape)."""
+        f, h, w_ = (a.f, a.h, a.w) if isinstance(a, ops.FlatActs) else a.shape[:3]
+        p, q = (h - 1) // stride + 1, (w_ - 1) // stride + 1
+        key = (str(a.data.device if isinstance(a, ops.FlatActs) else a.device), f, p, q, cout)
+        ws = self._flat_ws.get(key)
+        if ws is None:
+            if len(self._flat_ws) > 8:
+                self._flat_ws.clear()
+            dev = a.data.device if isinstance(a, ops.FlatActs) else a.device
+            ws = tuple(torch.zeros((ops.flat_rows(f, p, q), cout), dtype=torch.bfloat16, device=dev) for _ in range(2))
+            self._flat_ws[key] = ws
+        return ws
 
     def _check_input(self, x):
         if self.training and torch.is_grad_enabled():
@@ -197,6 +222,11 @@ class Lipreading(nn.Module):
                     a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
                     continue
                 if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input
+                    if w2.dim() == 2:  # layer2: the block stays in the flat layout (conv2 is a flat stride-1 conv)
+                        y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True,
+                                                 flat_ws=self._flat_workspace(a, w1.shape[0], stride))
+                        a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res)
+                        continue
                     y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
                 else:
                     y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a

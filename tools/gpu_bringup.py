@@ -270,31 +270,36 @@ def halo_is_zero(fa):
 
 def sec_flat():
     g = torch.Generator(device="cpu").manual_seed(5)
-    for (Fr, H) in [(1, 22), (3, 22), (29, 22), (64, 22), (7, 11), (928, 22)]:
-        x = bf(torch.randn(Fr, H, H, 64, generator=g)).to(DEV)
-        w = (torch.randn(64, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
-        gam = (torch.rand(64, generator=g) + 0.5).to(DEV)
-        bet = (torch.randn(64, generator=g) * 0.1).to(DEV)
-        mu = (torch.randn(64, generator=g) * 0.1).to(DEV)
-        var = (torch.rand(64, generator=g) + 0.5).to(DEV)
+    for (Fr, H, C) in [(1, 22, 64), (3, 22, 64), (29, 22, 64), (64, 22, 64), (7, 11, 64), (928, 22, 64),
+                       (1, 11, 128), (3, 11, 128), (29, 11, 128), (64, 11, 128), (5, 6, 128), (928, 11, 128)]:
+        x = bf(torch.randn(Fr, H, H, C, generator=g)).to(DEV)
+        w = (torch.randn(C, C, 3, 3, generator=g) / (9 * C) ** 0.5).to(DEV)
+        gam = (torch.rand(C, generator=g) + 0.5).to(DEV)
+        bet = (torch.randn(C, generator=g) * 0.1).to(DEV)
+        mu = (torch.randn(C, generator=g) * 0.1).to(DEV)
+        var = (torch.rand(C, generator=g) + 0.5).to(DEV)
         wp, bias = ops.pack_conv2d(w, gam, bet, mu, var)
         xf = to_flat(x)
         ref = F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().permute(0, 3, 1, 2), bias, padding=1)
         wpf = ops.pack_flat_weight(wp)
         out = ops.conv3x3_flat(xf, wpf, bias, relu=True)
         torch.cuda.synchronize()
-        report(f"flatconv F{Fr} H{H} relu", out.dense(), bf(torch.relu(ref).permute(0, 2, 3, 1)))
+        ok = report(f"flatconv C{C} F{Fr} H{H} relu", out.dense(), bf(torch.relu(ref).permute(0, 2, 3, 1)))
+        if not ok:
+            pattern("flatconv", out.dense(), torch.relu(ref).permute(0, 2, 3, 1))
         if not halo_is_zero(out):
             print("[BAD] halo not zero"); FAILS.append("halo")
-        out2 = ops.conv3x3_flat(xf, wpf, bias, relu=True, residual=xf)
-        report(f"flatconv F{Fr} H{H} +res+relu", out2.dense(),
-               bf(torch.relu(ref + x.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)))
+        res = bf(torch.randn(Fr, H, H, C, generator=g)).to(DEV)
+        out2 = ops.conv3x3_flat(xf, wpf, bias, relu=True, residual=to_flat(res))
+        report(f"flatconv C{C} F{Fr} H{H} +res+relu", out2.dense(),
+               bf(torch.relu(ref + res.float().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)))
         if not halo_is_zero(out2):
             print("[BAD] halo not zero (res)"); FAILS.append("halo")
-        # strided im2col conv on the flat layout == on the dense layout
-        w2 = (torch.randn(128, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
-        wp2, b2 = ops.pack_conv2d(w2)
-        report(f"conv s2 on flat F{Fr} H{H}", ops.conv2d(xf, wp2, b2, stride=2), ops.conv2d(x, wp2, b2, stride=2))
+        if C == 64:
+            # strided im2col conv on the flat layout == on the dense layout
+            w2 = (torch.randn(128, 64, 3, 3, generator=g) / (9 * 64) ** 0.5).to(DEV)
+            wp2, b2 = ops.pack_conv2d(w2)
+            report(f"conv s2 on flat F{Fr} H{H}", ops.conv2d(xf, wp2, b2, stride=2), ops.conv2d(x, wp2, b2, stride=2))
     # fused conv1 + downsample (DUAL) == two separate launches, on dense and flat inputs
     for (Fr, H, Ci, Co) in [(5, 22, 64, 128), (29, 22, 64, 128), (7, 11, 128, 256), (9, 6, 256, 512), (928, 6, 256, 512)]:
         x = bf(torch.randn(Fr, H, H, Ci, generator=g)).to(DEV)
@@ -313,6 +318,13 @@ def sec_flat():
             y2, d2 = ops.conv2d_dual(to_flat(x), wp1, b1, wpd, bd, stride=2)
             report(f"dual conv1 (flat in) F{Fr}", y2, y_ref, tol=1e-6)
             report(f"dual ds    (flat in) F{Fr}", d2, d_ref, tol=1e-6)
+            P = y_ref.shape[1]
+            ws = tuple(torch.zeros(ops.flat_rows(Fr, P, P), Co, dtype=torch.bfloat16, device=DEV) for _ in range(2))
+            y3, d3 = ops.conv2d_dual(to_flat(x), wp1, b1, wpd, bd, stride=2, flat_ws=ws)
+            report(f"dual conv1 (flat in, flat out) F{Fr}", y3.dense(), y_ref, tol=1e-6)
+            report(f"dual ds    (flat in, flat out) F{Fr}", d3.dense(), d_ref, tol=1e-6)
+            if not (halo_is_zero(y3) and halo_is_zero(d3)):
+                print("[BAD] dual flat halo not zero"); FAILS.append("dualhalo")
     # stem flat output == dense output
     w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / (245 ** 0.5)).to(DEV)
     one, zero = torch.ones(64, device=DEV), torch.zeros(64, device=DEV)
@@ -459,6 +471,17 @@ def sec_perf():
           flush=True)
     ms = timeit(lambda: ops.conv3x3_flat(xf, wf, bfz, relu=True, out=of))
     print(f"perf flatconv H22 64->64 (no res): {ms * 1e3:.1f} us  {2.0 * 928 * 484 * 64 * 576 / ms / 1e9:.1f} TFLOP/s",
+          flush=True)
+    xd2 = bf(torch.randn(928, 11, 11, 128, generator=g)).to(DEV)
+    xf2 = to_flat(xd2)
+    wf2 = ops.pack_flat_weight(bf(torch.randn(128, 3, 3, 128, generator=g) / 34).to(DEV))
+    bfz2 = torch.zeros(128, device=DEV)
+    of2 = torch.empty_like(xf2.data)
+    ms = timeit(lambda: ops.conv3x3_flat(xf2, wf2, bfz2, relu=True, residual=xf2, out=of2))
+    print(f"perf flatconv H11 128->128 (+res): {ms * 1e3:.1f} us  {2.0 * 928 * 121 * 128 * 1152 / ms / 1e9:.1f} TFLOP/s",
+          flush=True)
+    ms = timeit(lambda: ops.conv3x3_flat(xf2, wf2, bfz2, relu=True, out=of2))
+    print(f"perf flatconv H11 128->128 (no res): {ms * 1e3:.1f} us  {2.0 * 928 * 121 * 128 * 1152 / ms / 1e9:.1f} TFLOP/s",
           flush=True)
     w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / 16).to(DEV)
     one = torch.ones(64, device=DEV)
