@@ -147,6 +147,52 @@ int sblk_qkv_group_clips(int T);
 int sblk_qkv_attention_fwd(const void* x_bf16, const void* w_heads_bf16, const float* bias_heads, const int* lengths,
                            void* out_bf16, int N, int T, int H, int d_k, int K, float scale, void* stream);
 
+/* The whole transformer encoder stack in ONE launch (eval mode):
+ *   x = LayerNorm(x_in W_in^T + b_in) + pe[t];  n_layers x { x = LN(fc(attn(x)) + x) * keep ; x = LN(w_2 relu(w_1 x) + x) * keep }
+ * A thread-block cluster owns a group of floor(128 / T) whole clips and runs it through every layer without any
+ * inter-group synchronisation; each CTA of the cluster computes 1 / cluster_size of every step's output features.
+ * All per-layer tensors are STACKED along their first dimension:
+ *   w_heads bf16 [L*1536, 512] (per layer the head-major q_h|k_h|v_h rows of sblk_qkv_attention_fwd), b_heads fp32 [L*1536],
+ *   w_fc bf16 [L*512, 512], b_fc / ln1_gamma / ln1_beta fp32 [L*512], w_1 bf16 [L*d_inner, 512], b_1 fp32 [L*d_inner],
+ *   w_2 bf16 [L*512, d_inner], b_2 / ln2_gamma / ln2_beta fp32 [L*512].
+ * x_in bf16 [N*T, d_in]; w_in bf16 [512, d_in]; pe fp32 [>= T, 512]; lengths int32 [N] or NULL; out fp32 [N*T, 512];
+ * workspace: sblk_encoder_stack_workspace_bytes(N, T, d_inner) bytes of device memory (contents irrelevant).
+ * Implemented for n_head = 8, d_k = d_v = 64, d_model = 512, T <= 128, d_in % 128 == 0, d_inner % 512 == 0 and <= 3072;
+ * anything else returns < 0 (callers then use the per-step entry points above).
+ * replaces: Encoder.forward transformer/encoder.py:36-67 ; EncoderLayer.forward encoder.py:83-91 ;
+ * MultiHeadAttention.forward attention.py:32-60 ; ScaledDotProductAttention.forward attention.py:72-83 ;
+ * PositionwiseFeedForward.forward module.py:47-52 ; get_non_pad_mask / get_attn_pad_mask utils.py:98-113,140-147 */
+typedef struct sblk_encoder_stack_args {
+  const void* x_in;
+  const void* w_in;
+  const float* b_in;
+  const float* ln_in_gamma;
+  const float* ln_in_beta;
+  const float* pe;
+  const void* w_heads;
+  const float* b_heads;
+  const void* w_fc;
+  const float* b_fc;
+  const float* ln1_gamma;
+  const float* ln1_beta;
+  const void* w_1;
+  const float* b_1;
+  const void* w_2;
+  const float* b_2;
+  const float* ln2_gamma;
+  const float* ln2_beta;
+  const int* lengths;
+  float* out;
+  void* workspace;
+  int N, T, n_layers, n_head, d_k, d_model, d_in, d_inner;
+  float scale; /* 1 / temperature */
+  float eps;   /* LayerNorm eps (shared by all LayerNorms of the stack) */
+  void* debug_stamps; /* NULL, or device uint64 [(1 + 4*n_layers)*8 + 2*groups]: per-stage clock64 stamps of CTA 0, then
+                       * (start, end) globaltimer ns of every cluster (profiling aid) */
+} sblk_encoder_stack_args;
+long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
+int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,17 @@ _i = ctypes.c_int
 _f = ctypes.c_float
 _ll = ctypes.c_longlong
 
+
+
+class EncoderStackArgs(ctypes.Structure):
+    """Mirror of `sblk_encoder_stack_args` (include/sblk.h)."""
+    _fields_ = ([(n, _vp) for n in (
+        "x_in", "w_in", "b_in", "ln_in_gamma", "ln_in_beta", "pe", "w_heads", "b_heads", "w_fc", "b_fc", "ln1_gamma",
+        "ln1_beta", "w_1", "b_1", "w_2", "b_2", "ln2_gamma", "ln2_beta", "lengths", "out", "workspace")] +
+        [(n, _i) for n in ("N", "T", "n_layers", "n_head", "d_k", "d_model", "d_in", "d_inner")] +
+        [("scale", _f), ("eps", _f), ("debug_stamps", _vp)])
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).
 SIGNATURES = {
     "sblk_version": (_i, []),
@@ -49,6 +60,8 @@ SIGNATURES = {
     "sblk_gemm_ln_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "sblk_qkv_group_clips": (_i, [_i]),
     "sblk_qkv_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "sblk_encoder_stack_workspace_bytes": (_ll, [_i, _i, _i]),
+    "sblk_encoder_stack_fwd": (_i, [ctypes.POINTER(EncoderStackArgs), _vp]),
 }
 
 

@@ -21,6 +21,7 @@
 #include "sblk_attention.cuh"
 #include "sblk_gemm_ln.cuh"
 #include "sblk_qkv_attn.cuh"
+#include "sblk_encoder_stack.cuh"
 
 namespace {
 
@@ -784,6 +785,140 @@ int sblk_qkv_attention_fwd(const void* x, const void* w_heads, const float* bias
   if (T <= 32) return launch(sblk::qkv_attention_kernel<4>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<4>", tmA, tmB, p);
   if (T <= 64) return launch(sblk::qkv_attention_kernel<8>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<8>", tmA, tmB, p);
   return launch(sblk::qkv_attention_kernel<16>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<16>", tmA, tmB, p);
+}
+
+// ---- whole-encoder-stack kernel -------------------------------------------------------------------------------
+extern "C++" {
+template <int CL, int NT, bool MC>
+static int launch_encoder_stack(const CUtensorMap* tm, const sblk::EncStackParams& p, int groups, cudaStream_t stream) {
+  using Cfg = sblk::EncCfg<CL>;
+  auto kernel = sblk::encoder_stack_kernel<CL, NT, MC>;
+  static std::atomic<int> prepared[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (prepared[dev & 63].load(std::memory_order_acquire) == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_stack smem)");
+    if (CL > 8) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(NonPortableClusterSizeAllowed)");
+    }
+    prepared[dev & 63].store(1, std::memory_order_release);
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(groups * CL);
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  int nattr = 1;
+  if (g_pdl.load(std::memory_order_relaxed) != 0) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    nattr = 2;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = nattr;
+  if (getenv("SBLK_ENC_STACK_VERBOSE")) {
+    int ncl = -1;
+    cudaError_t oe = cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg);
+    fprintf(stderr, "[libsblk] encoder_stack CL=%d: max active clusters %d (%s), grid %d CTAs\n", CL, ncl,
+            cudaGetErrorName(oe), groups * CL);
+  }
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], tm[8], p);
+  if (e != cudaSuccess) return cuda_fail(e, "encoder_stack_kernel");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+template <int CL, bool MC>
+static int launch_encoder_stack_nt(int T, const CUtensorMap* tm, const sblk::EncStackParams& p, int groups,
+                                   cudaStream_t stream) {
+  if (T <= 32) return launch_encoder_stack<CL, 4, MC>(tm, p, groups, stream);
+  if (T <= 64) return launch_encoder_stack<CL, 8, MC>(tm, p, groups, stream);
+  return launch_encoder_stack<CL, 16, MC>(tm, p, groups, stream);
+}
+}  // extern "C++"
+
+long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner) {
+  if (N <= 0 || T <= 0 || d_inner <= 0) return -1;
+  const long long M = static_cast<long long>(N) * T;
+  return M * (512 + 512 + d_inner) * 2;   // x16 | att16 | h16, bf16
+}
+
+int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (a == nullptr) return fail(-1, "sblk_encoder_stack_fwd: null argument block");
+  const int N = a->N, T = a->T, L = a->n_layers, d_in = a->d_in, d_inner = a->d_inner;
+  if (a->n_head != 8 || a->d_k != 64 || a->d_model != 512)
+    return fail(-1, "sblk_encoder_stack_fwd: only n_head=8, d_k=d_v=64, d_model=512 are implemented (got %d, %d, %d)",
+                a->n_head, a->d_k, a->d_model);
+  if (N <= 0 || T <= 0 || T > 128 || L <= 0 || d_in <= 0 || d_in % 128 != 0 || d_inner <= 0 || d_inner % 256 != 0)
+    return fail(-1, "sblk_encoder_stack_fwd: bad shape N=%d T=%d layers=%d d_in=%d d_inner=%d (T <= 128, d_in %% 128 "
+                "== 0, d_inner %% 256 == 0)", N, T, L, d_in, d_inner);
+  const void* ptrs[] = {a->x_in, a->w_in, a->b_in, a->ln_in_gamma, a->ln_in_beta, a->pe, a->w_heads, a->b_heads,
+                        a->w_fc, a->b_fc, a->ln1_gamma, a->ln1_beta, a->w_1, a->b_1, a->w_2, a->b_2, a->ln2_gamma,
+                        a->ln2_beta, a->out, a->workspace};
+  for (const void* q : ptrs) {
+    if (q == nullptr) return fail(-1, "sblk_encoder_stack_fwd: null pointer");
+    if (!aligned16(q)) return fail(-1, "sblk_encoder_stack_fwd: pointers must be 16-byte aligned");
+  }
+  // Cluster size: 16 CTAs per clip group stream the least weight bytes per SM, but only 7 clusters of 16 are ever
+  // co-resident on a B200 (measured: GPC granularity), so batches with more groups use clusters of 8 (all 8 groups
+  // of the BASELINE batch in one wave).  SBLK_ENC_STACK_CL / SBLK_ENC_STACK_MC override for A/B timing.
+  const int G = sblk_qkv_group_clips(T);
+  const int groups = (N + G - 1) / G;
+  int cl = groups <= 7 ? 16 : 8;
+  bool mc = true;
+  if (const char* e = getenv("SBLK_ENC_STACK_CL")) cl = atoi(e);
+  if (const char* e = getenv("SBLK_ENC_STACK_MC")) mc = atoi(e) != 0;
+  if (cl != 8 && cl != 16) return fail(-1, "sblk_encoder_stack_fwd: SBLK_ENC_STACK_CL must be 8 or 16");
+  if (d_inner % (32 * cl) != 0 || d_inner / cl > (cl == 16 ? 192 : 256))
+    return fail(-1, "sblk_encoder_stack_fwd: d_inner=%d not supported by the fused stack (d_inner %% %d == 0, "
+                "d_inner / %d <= %d)", d_inner, 32 * cl, cl, cl == 16 ? 192 : 256);
+  const long long M = static_cast<long long>(N) * T;
+  __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(a->workspace);
+  sblk::EncStackParams p;
+  p.N = N; p.T = T; p.G = G; p.L = L; p.M = static_cast<int>(M); p.d_in = d_in; p.d_inner = d_inner;
+  p.b_in = a->b_in; p.g_in = a->ln_in_gamma; p.be_in = a->ln_in_beta; p.pe = a->pe;
+  p.b_heads = a->b_heads; p.b_fc = a->b_fc; p.g1 = a->ln1_gamma; p.be1 = a->ln1_beta;
+  p.b_w1 = a->b_1; p.b_w2 = a->b_2; p.g2 = a->ln2_gamma; p.be2 = a->ln2_beta;
+  p.lengths = a->lengths; p.out = a->out;
+  p.x16 = ws; p.att16 = ws + M * 512; p.h16 = ws + M * 1024;
+  p.scale = a->scale; p.eps = a->eps;
+  p.dbg = static_cast<unsigned long long*>(a->debug_stamps);
+
+  CUtensorMap tm[9];
+  const cuuint32_t a_rows = mc ? static_cast<cuuint32_t>(128 / cl) : 128u;
+  auto enc = [&](CUtensorMap* t, const void* ptr, long long rows, int cols, cuuint32_t box_rows) -> int {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    return encode_tiled(t, ptr, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  };
+  const cuuint32_t ns = static_cast<cuuint32_t>(512 / cl), nw = static_cast<cuuint32_t>(d_inner / cl);
+  if ((rc = enc(&tm[0], a->x_in, M, d_in, a_rows))) return rc;
+  if ((rc = enc(&tm[1], p.x16, M, 512, a_rows))) return rc;
+  if ((rc = enc(&tm[2], p.att16, M, 512, a_rows))) return rc;
+  if ((rc = enc(&tm[3], p.h16, M, d_inner, a_rows))) return rc;
+  if ((rc = enc(&tm[4], a->w_in, 512, d_in, ns))) return rc;
+  if ((rc = enc(&tm[5], a->w_heads, static_cast<long long>(L) * 1536, 512, 192))) return rc;
+  if ((rc = enc(&tm[6], a->w_fc, static_cast<long long>(L) * 512, 512, ns))) return rc;
+  if ((rc = enc(&tm[7], a->w_1, static_cast<long long>(L) * d_inner, 512, nw))) return rc;
+  if ((rc = enc(&tm[8], a->w_2, static_cast<long long>(L) * 512, d_inner, ns))) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (cl == 16) {
+    return mc ? launch_encoder_stack_nt<16, true>(T, tm, p, groups, s)
+              : launch_encoder_stack_nt<16, false>(T, tm, p, groups, s);
+  }
+  return mc ? launch_encoder_stack_nt<8, true>(T, tm, p, groups, s)
+            : launch_encoder_stack_nt<8, false>(T, tm, p, groups, s);
 }
 
 }  // extern "C"

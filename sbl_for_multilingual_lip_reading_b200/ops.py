@@ -5,6 +5,8 @@ torch's job, arithmetic is not) and enqueues the kernel on torch's current CUDA 
 """
 from __future__ import annotations
 
+import ctypes
+
 import torch
 
 from . import _lib
@@ -415,3 +417,54 @@ def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
     _call("sblk_attention_fwd", f"attention T={t}", 4 * n * h * t * t * d_k, 2 * qkv.numel() + 2 * out.numel(),
           _p(qkv), _p(out), _p(probs), _p(lengths), n, t, h, d_k, scale, _stream())
     return out, probs
+
+
+def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layers):
+    """Shapes the one-launch encoder stack (csrc/sblk_encoder_stack.cuh) implements."""
+    return (n_head == 8 and d_k == 64 and d_v == 64 and d_model == 512 and 0 < t <= 128 and n_layers >= 1 and
+            d_in % 128 == 0 and d_inner % 512 == 0 and d_inner <= 3072)
+
+
+def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None):
+    """The whole encoder stack in one launch.  x16 bf16 [n*t, d_in]; `stk` = dict of STACKED packed tensors
+    (w_in, b_in, g_in, be_in, pe, w_heads, b_heads, w_fc, b_fc, g1, be1, w_1, b_1, w_2, b_2, g2, be2, n_layers, d_inner)
+    -> fp32 [n*t, 512]."""
+    _req(x16, BF16, "x16"); _req(lengths, torch.int32, "lengths"); _req(out, F32, "out")
+    for k_ in ("w_in", "w_heads", "w_fc", "w_1", "w_2"):
+        _req(stk[k_], BF16, k_)
+    for k_ in ("b_in", "g_in", "be_in", "pe", "b_heads", "b_fc", "g1", "be1", "b_1", "b_2", "g2", "be2"):
+        _req(stk[k_], F32, k_)
+    m, d_in = x16.shape
+    nl, d_inner = stk["n_layers"], stk["d_inner"]
+    if m != n * t:
+        raise RuntimeError(f"encoder_stack: {m} rows != n*t = {n * t}")
+    if (tuple(stk["w_in"].shape) != (512, d_in) or tuple(stk["w_heads"].shape) != (nl * 1536, 512) or
+            tuple(stk["w_fc"].shape) != (nl * 512, 512) or tuple(stk["w_1"].shape) != (nl * d_inner, 512) or
+            tuple(stk["w_2"].shape) != (nl * 512, d_inner) or stk["pe"].shape[-1] != 512 or stk["pe"].shape[0] < t):
+        raise RuntimeError("encoder_stack: stacked weight shapes do not match the layer configuration")
+    if out is None:
+        out = torch.empty((m, 512), dtype=F32, device=x16.device)
+    elif tuple(out.shape) != (m, 512):
+        raise RuntimeError(f"encoder_stack: out shape {tuple(out.shape)} != {(m, 512)}")
+    lib = _lib.load()
+    need = int(lib.sblk_encoder_stack_workspace_bytes(n, t, d_inner))
+    if workspace is None:
+        workspace = torch.empty((need,), dtype=torch.uint8, device=x16.device)
+    elif workspace.numel() * workspace.element_size() < need or not workspace.is_cuda:
+        raise RuntimeError(f"encoder_stack: workspace needs {need} bytes of device memory")
+    a = _lib.EncoderStackArgs()
+    a.x_in, a.w_in, a.b_in = _p(x16), _p(stk["w_in"]), _p(stk["b_in"])
+    a.ln_in_gamma, a.ln_in_beta, a.pe = _p(stk["g_in"]), _p(stk["be_in"]), _p(stk["pe"])
+    a.w_heads, a.b_heads, a.w_fc, a.b_fc = _p(stk["w_heads"]), _p(stk["b_heads"]), _p(stk["w_fc"]), _p(stk["b_fc"])
+    a.ln1_gamma, a.ln1_beta = _p(stk["g1"]), _p(stk["be1"])
+    a.w_1, a.b_1, a.w_2, a.b_2 = _p(stk["w_1"]), _p(stk["b_1"]), _p(stk["w_2"]), _p(stk["b_2"])
+    a.ln2_gamma, a.ln2_beta = _p(stk["g2"]), _p(stk["be2"])
+    a.lengths, a.out, a.workspace = _p(lengths), _p(out), _p(workspace)
+    a.N, a.T, a.n_layers, a.n_head, a.d_k, a.d_model, a.d_in, a.d_inner = n, t, nl, 8, 64, 512, d_in, d_inner
+    a.scale, a.eps = scale, eps
+    a.debug_stamps = _p(debug_stamps)   # optional int64 [1 + 4*n_layers, 8] device tensor (profiling aid)
+    flops = 2 * m * 512 * d_in + nl * (2 * m * 512 * (4 * 512 + 2 * d_inner) + 4 * n * 8 * t * t * 64)
+    wbytes = 2 * (512 * d_in + nl * (4 * 512 * 512 + 2 * 512 * d_inner))
+    _call("sblk_encoder_stack_fwd", f"encoder stack L={nl} T={t}", flops, wbytes + m * (2 * d_in + 4 * 512),
+          ctypes.byref(a), _stream())
+    return out

@@ -222,6 +222,67 @@ def test_c_abi_rejects_bad_arguments(dev):
                    torch.zeros(64, device=dev))
 
 
+# ------------------------------------------------------------------ one-launch encoder stack (cluster kernel)
+@pytest.mark.parametrize("n,t,lens", [(1, 1, None), (4, 29, None), (5, 29, [29, 3, 17, 29, 1]), (3, 40, [40, 17, 1]),
+                                      (9, 31, None), (2, 100, [100, 64]), (32, 29, None), (40, 30, None)])
+def test_encoder_stack_matches_oracle_and_per_step_kernels(encoder6, dev, n, t, lens):
+    """sblk_encoder_stack_fwd (one launch, a thread-block cluster per clip group) against the CPU oracle and against
+    the per-step kernels, for single / multiple / partial groups, ragged lengths and both cluster sizes
+    (<= 7 groups run clusters of 16 CTAs, more run clusters of 8)."""
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    g = torch.Generator().manual_seed(1000 + 31 * n + t)
+    x = torch.randn(n, t, 512, generator=g)
+    ln = lens if lens is not None else [t] * n
+    assert encoder6._use_fused_stack(n, t, False)
+    with torch.no_grad():
+        fused, = encoder6(x.to(dev), ln)
+        encoder6.fused_stack = False
+        try:
+            steps, = encoder6(x.to(dev), ln)
+        finally:
+            encoder6.fused_stack = True
+        ref = O.encoder_forward(x, ln, synth.encoder_state_dict(2, 6), n_layers=6)[0]
+    assert rel_fro(fused, ref) < REL_TOL
+    assert rel_fro(fused, steps) < REL_TOL
+    if lens is not None:   # `*= non_pad_mask` (encoder.py:86,89): padded positions are exactly zero
+        for b, l_ in enumerate(lens):
+            assert float(fused[b, l_:].abs().max() if l_ < t else 0.0) == 0.0
+
+
+def test_encoder_stack_cluster_sizes_agree(encoder6, dev, monkeypatch):
+    """Clusters of 8 and of 16 CTAs, with and without TMA multicast of the activation tiles, compute the same
+    function (different feature slicing per CTA: results equal up to fp32 summation order in the LayerNorm stats)."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(6, 29, 512, generator=g).to(dev)
+    outs = []
+    with torch.no_grad():
+        for cl, mc in (("16", "1"), ("16", "0"), ("8", "1"), ("8", "0")):
+            monkeypatch.setenv("SBLK_ENC_STACK_CL", cl)
+            monkeypatch.setenv("SBLK_ENC_STACK_MC", mc)
+            outs.append(encoder6(x, [29, 29, 5, 29, 12, 29])[0].clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[2], outs[3])
+    assert rel_fro(outs[0], outs[2]) < 5e-3   # bf16 rounding flips of the activations, amplified over 6 layers
+
+
+def test_encoder_stack_rejects_unsupported_shapes(dev):
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    enc = Encoder(512, 1, 8, 64, 64, 512, 2048)
+    enc.load_state_dict(synth.encoder_state_dict(4, 1))
+    enc = enc.to(dev).eval()
+    stk = enc._get_packed().stacked
+    x16 = torch.zeros(4 * 130, 512, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(RuntimeError, match="T <= 128"):
+        ops.encoder_stack(x16, stk, 4, 130)
+    with pytest.raises(RuntimeError, match="workspace"):
+        ops.encoder_stack(x16[:40], stk, 4, 10, workspace=torch.empty(16, dtype=torch.uint8, device=dev))
+    # configurations outside the fused kernel's envelope take the per-step kernels (still libsblk, never torch)
+    wide = Encoder(512, 1, 8, 64, 64, 512, 1024 + 64).to(dev).eval()
+    assert not wide._use_fused_stack(2, 10, False)
+    assert not enc._use_fused_stack(2, 10, True) and enc._use_fused_stack(2, 10, False)
+
+
 # ------------------------------------------------------------------ BASELINE-size properties
 def test_config2_batch_independence_and_determinism(frontend, encoder6, dev):
     """Config 2 (32 x 29 x 88 x 88): clips are independent in eval mode, so clip i of the

@@ -61,6 +61,19 @@ def pattern(name, got, ref, rows_mod=128):
         print(f"   row {r0} got[:8]={got[r0, :8].tolist()}\n   row {r0} ref[:8]={ref[r0, :8].tolist()}")
 
 
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
 def bf(x):
     return x.to(torch.bfloat16)
 
@@ -420,22 +433,54 @@ def sec_enc2():
             pattern("qkv_attention", out, o, rows_mod=T)
 
 
+def sec_stack():
+    """One-launch encoder stack (cluster kernel) vs the per-step kernels and the CPU oracle.
+    usage: gpu_bringup.py stack <cluster 8|16> <multicast 0|1>"""
+    import os
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    cl, mc = sys.argv[2], sys.argv[3]
+    os.environ["SBLK_ENC_STACK_CL"] = cl
+    os.environ["SBLK_ENC_STACK_MC"] = mc
+    print(f"--- encoder stack cluster={cl} multicast={mc}", flush=True)
+    for nl in (1, 6):
+        enc = Encoder(512, nl, 8, 64, 64, 512, 2048).eval()
+        sd = synth.encoder_state_dict(2, nl)
+        enc.load_state_dict(sd)
+        enc = enc.to(DEV)
+        g = torch.Generator(device="cpu").manual_seed(11)
+        for (N, T, lens) in [(4, 29, None), (1, 1, None), (32, 29, None), (5, 29, None), (3, 40, [40, 17, 1]),
+                             (7, 40, None), (2, 100, [100, 64]), (64, 31, None)]:
+            x = torch.randn(N, T, 512, generator=g)
+            ln = lens if lens is not None else [T] * N
+            with torch.no_grad():
+                enc.fused_stack = True
+                got, = enc(x.to(DEV), ln)
+                torch.cuda.synchronize()
+                enc.fused_stack = False
+                ref, = enc(x.to(DEV), ln)
+                torch.cuda.synchronize()
+                report(f"stack L{nl} N{N} T{T} lens={lens} vs per-step kernels", got, ref, tol=1e-2)
+                if N * T <= 400:
+                    orc = O.encoder_forward(x, ln, {k: v for k, v in sd.items()}, n_layers=nl)[0]
+                    report(f"stack L{nl} N{N} T{T} lens={lens} vs oracle", got.cpu(), orc, tol=2e-2)
+    x = torch.randn(32, 29, 512, generator=g).to(DEV)
+    ln = [29] * 32
+    with torch.no_grad():
+        for fused in (True, False):
+            enc.fused_stack = fused
+            for pdl in (False, True):
+                ops.set_pdl(pdl)
+                ms = timeit(lambda: enc(x, ln))
+                print(f"perf encoder N32 T29 L6 fused={fused} pdl={pdl}: {ms * 1e3:.1f} us", flush=True)
+    ops.set_pdl(False)
+
+
 def sec_perf():
     """Quick per-layer timing at the C2 shape (F = 928) to see where the time goes."""
     g = torch.Generator(device="cpu").manual_seed(5)
     Fr = 928
-
-    def timeit(fn, n=20):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
 
     layers = [(22, 64, 64, 3, 1), (22, 64, 128, 3, 2), (11, 128, 128, 3, 1), (22, 64, 128, 1, 2),
               (11, 128, 256, 3, 2), (6, 256, 256, 3, 1), (6, 256, 512, 3, 2), (3, 512, 512, 3, 1)]
@@ -506,7 +551,7 @@ if __name__ == "__main__":
         print("PDL enabled")
     try:
         {"aux": sec_aux, "gemm": sec_gemm, "conv": sec_conv, "probe": sec_probe, "conv3d": sec_conv3d, "flat": sec_flat, "enc": sec_enc, "enc2": sec_enc2,
-         "perf": sec_perf}[sec]()
+         "perf": sec_perf, "stack": sec_stack}[sec]()
         torch.cuda.synchronize()
     except Exception as e:  # noqa: BLE001
         import traceback

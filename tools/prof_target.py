@@ -57,5 +57,15 @@ if what == "forward":
             out, = enc(fe(x), [29] * 32)
     torch.cuda.synchronize()
     print("done forward", float(out.abs().mean()))
+if what == "stack":
+    # the one-launch encoder stack alone, BASELINE configs[1] shape
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    enc = Encoder(512, 6, 8, 64, 64, 512, 2048)
+    enc.load_state_dict(synth.encoder_state_dict(2, 6))
+    enc = enc.to(dev).eval()
+    feat = torch.randn(32, 29, 512, generator=g).to(dev)
+    with torch.no_grad():
+        for _ in range(iters):
+            out, = enc(feat, [29] * 32)
 torch.cuda.synchronize()
 print("done", what)

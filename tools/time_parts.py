@@ -43,6 +43,13 @@ def graph_time(fn, reps=30):
 with torch.no_grad():
     feat = fe(x)
 print(f"frontend (prep+stem+trunk+pool+dropout): {graph_time(lambda: fe(x)):.1f} us")
+for cl, mc in (("16", "1"), ("8", "1")):
+    os.environ["SBLK_ENC_STACK_CL"], os.environ["SBLK_ENC_STACK_MC"] = cl, mc
+    enc.fused_stack = True
+    print(f"encoder  (6 layers), one launch, cluster {cl} multicast {mc}: {graph_time(lambda: enc(feat, [T] * N)):.1f} us")
+os.environ.pop("SBLK_ENC_STACK_CL"); os.environ.pop("SBLK_ENC_STACK_MC")
+print(f"whole path (one-launch encoder):         {graph_time(lambda: enc(fe(x), [T] * N)):.1f} us")
+enc.fused_stack = False
 for pc in [int(v) for v in os.environ.get("CHAINS", "4").split(",")]:
     enc.parallel_chains = pc
     print(f"encoder  (6 layers), {pc} chains:           {graph_time(lambda: enc(feat, [T] * N)):.1f} us")
