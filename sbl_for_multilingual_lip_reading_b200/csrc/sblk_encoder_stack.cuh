@@ -82,10 +82,13 @@ struct EncCfg {
   static constexpr int TMEM_COLS = 256;
   static constexpr int MC_ROWS = 128 / CL;             // A rows each CTA fetches and multicasts (8-row swizzle atoms)
   static_assert(2 * (A_BYTES + NS * 128) <= SLOT_BYTES, "two LayerNorm-stage k-blocks must fit one ring slot");
-  static_assert(CL * 128 * 8 <= QKV_BYTES, "statistics exchange area aliases the Q tile");
+  static_assert(16 * 128 * 8 <= QKV_BYTES, "statistics exchange area aliases the Q tile");
 };
 
 __device__ __forceinline__ void cl_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+// arrive without release semantics (threads that published nothing: producer, MMA issuer, idle epilogue warps); the
+// releasing form compiles to MEMBAR.ALL.GPU + ERRBAR in front of the arrive
+__device__ __forceinline__ void cl_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cl_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 // generic-proxy global writes -> visible to async-proxy (TMA) reads issued after the next acquire
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -144,7 +147,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sQKV = smem + Cfg::OFF_QKV;
-  float2* part = reinterpret_cast<float2*>(sQKV);   // [CL][128] (mean, M2) per source CTA; aliases the Q tile
+  float2* part = reinterpret_cast<float2*>(sQKV);   // [16][128] (mean, M2) per 32-column slice; aliases the Q tile
 
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
@@ -292,7 +295,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       EncStage nxt;
       pre = 0;
       for (int b = 0; b < nb; ++b) {
-        cl_arrive();
+        cl_arrive_relaxed();
         if (b == 0 && s < num_stages) {
           nxt = stage_desc(s);
           pre = prefetch_b(nxt);
@@ -343,7 +346,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         if (++slot == STAGES) { slot = 0; phase ^= 1u; }
       }
       stamp(s, 1);
-      for (int b = 0; b < d.end_barriers; ++b) { cl_arrive(); cl_wait(); }
+      for (int b = 0; b < d.end_barriers; ++b) { cl_arrive_relaxed(); cl_wait(); }
     }
   } else {
     // ================================================================= epilogue warps
@@ -362,7 +365,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     uint32_t tph = 0;
     float keep = 1.0f;
     if (row_ok && p.lengths != nullptr && t >= __ldg(p.lengths + clip)) keep = 0.0f;
-    const uint32_t my_part = smem_u32(&part[rank * 128 + row]);
+    const uint32_t my_part = smem_u32(&part[rank * (NS / 32) * 128 + row]);   // 32-column partial rank*NS/32 (+ sub)
     const int col0 = rank * NS;
 
     // per-column vectors of one layer for this CTA's column slices, staged in shared memory one layer ahead
@@ -424,18 +427,24 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             for (int j = 0; j < 32; ++j) v[c * 32 + j] += __uint_as_float(u[j]) + bias[c * 32 + j];
           }
           tc_fence_before_sync();
-          float sum = 0.0f;
+          // row statistics in 32-column partials (one per sub-slice), whatever the cluster size: the merged mean / M2
+          // are then bit-identical for clusters of 8 and 16, so a clip's output does not depend on the batch it is in
 #pragma unroll
-          for (int j = 0; j < NS; ++j) sum += v[j];
-          const float mean_c = sum * (1.0f / NS);
-          float m2_c = 0.0f;
+          for (int sub = 0; sub < NS / 32; ++sub) {
+            float sum = 0.0f;
 #pragma unroll
-          for (int j = 0; j < NS; ++j) {
-            const float dv = v[j] - mean_c;
-            m2_c += dv * dv;
+            for (int j = 0; j < 32; ++j) sum += v[sub * 32 + j];
+            const float mean_c = sum * (1.0f / 32.0f);
+            float m2_c = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float dv = v[sub * 32 + j] - mean_c;
+              m2_c += dv * dv;
+            }
+#pragma unroll
+            for (uint32_t r = 0; r < static_cast<uint32_t>(CL); ++r)
+              st_cluster_v2f32(mapa_u32(my_part + static_cast<uint32_t>(sub * 128 * 8), r), mean_c, m2_c);
           }
-#pragma unroll
-          for (uint32_t r = 0; r < static_cast<uint32_t>(CL); ++r) st_cluster_v2f32(mapa_u32(my_part, r), mean_c, m2_c);
           if (ew == 0) stamp(s, 4);
           cl_arrive();
           float pev[NS];   // positional encoding row (IN stage only): in flight while the barrier completes
@@ -454,14 +463,14 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           if (ew == 0) stamp(s, 6);
           float mean = 0.0f;
 #pragma unroll
-          for (int r = 0; r < CL; ++r) mean += part[r * 128 + row].x;
-          mean *= (1.0f / CL);
+          for (int r = 0; r < 16; ++r) mean += part[r * 128 + row].x;
+          mean *= (1.0f / 16.0f);
           float m2 = 0.0f;
 #pragma unroll
-          for (int r = 0; r < CL; ++r) {
+          for (int r = 0; r < 16; ++r) {
             const float2 pr = part[r * 128 + row];
             const float dm = pr.x - mean;
-            m2 += pr.y + static_cast<float>(NS) * dm * dm;
+            m2 += pr.y + 32.0f * dm * dm;
           }
           const float rstd = rsqrtf(m2 * (1.0f / D) + p.eps);
           const float mul = d.kind == 0 ? 1.0f : keep;   // encoder.py:53-55 applies no pad mask after layer_norm_in
@@ -489,8 +498,8 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           cl_arrive();
           cl_wait();
         } else {
-          cl_arrive(); cl_wait();
-          cl_arrive(); cl_wait();
+          cl_arrive_relaxed(); cl_wait();
+          cl_arrive_relaxed(); cl_wait();
         }
       } else if (d.kind == 1) {
         // ------------------------------------------------ + bias -> bf16 Q / K / V tiles -> attention of this head

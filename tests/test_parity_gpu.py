@@ -251,8 +251,9 @@ def test_encoder_stack_matches_oracle_and_per_step_kernels(encoder6, dev, n, t, 
 
 
 def test_encoder_stack_cluster_sizes_agree(encoder6, dev, monkeypatch):
-    """Clusters of 8 and of 16 CTAs, with and without TMA multicast of the activation tiles, compute the same
-    function (different feature slicing per CTA: results equal up to fp32 summation order in the LayerNorm stats)."""
+    """Clusters of 8 and of 16 CTAs, with and without TMA multicast of the activation tiles, are bit-identical
+    (LayerNorm statistics are merged from the same sixteen 32-column partials in the same order), so a clip's
+    output does not depend on how many clips share its batch."""
     g = torch.Generator().manual_seed(77)
     x = torch.randn(6, 29, 512, generator=g).to(dev)
     outs = []
@@ -261,8 +262,7 @@ def test_encoder_stack_cluster_sizes_agree(encoder6, dev, monkeypatch):
             monkeypatch.setenv("SBLK_ENC_STACK_CL", cl)
             monkeypatch.setenv("SBLK_ENC_STACK_MC", mc)
             outs.append(encoder6(x, [29, 29, 5, 29, 12, 29])[0].clone())
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[2], outs[3])
-    assert rel_fro(outs[0], outs[2]) < 5e-3   # bf16 rounding flips of the activations, amplified over 6 layers
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
 def test_encoder_stack_rejects_unsupported_shapes(dev):
