@@ -35,7 +35,9 @@ struct Fc2Cfg {
   static constexpr int A_STAGES = CB == 1 ? 5 : 2;    // a stage lasts a whole tile (>= one L2 round trip)
   static constexpr int R_BOX_BYTES = TILE_M * 128;                // one 64-channel block of the residual / output tile
   static constexpr int R_BYTES = CB * R_BOX_BYTES;                // 16 KB / 32 KB
-  static constexpr int R_BUFS = 2;
+  // residual / store-staging tiles: C = 64 has room for two per epilogue group, so the residual of the group's NEXT
+  // tile is already in flight while the current one is still being stored (else: load latency on the critical path)
+  static constexpr int R_BUFS = CB == 1 ? 4 : 2;
   static constexpr int BH = C / 2;                                // filter rows staged per CTA
   static constexpr int B_TILE_BYTES = BH * 128;                   // one (tap, channel block) k-block: 4 KB / 8 KB
   static constexpr int B_TILES = 9 * CB;                          // k-blocks per tile
@@ -175,8 +177,8 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       __syncwarp();
       if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
       if (p.has_res) {
-        const int rb = j & 1;                                        // staging buffer of epilogue group j & 1
-        mbar_wait(&r_empty[rb], (static_cast<uint32_t>(j >> 1) & 1u) ^ 1u, 0x0702);
+        const int rb = j % Cfg::R_BUFS;                              // staging buffer (group j & 1 owns the rb & 1 == j & 1 ones)
+        mbar_wait(&r_empty[rb], (static_cast<uint32_t>(j / Cfg::R_BUFS) & 1u) ^ 1u, 0x0702);
         uint8_t* r_dst = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
         if (elect_one()) {
           mbar_arrive_expect_tx(&r_full[rb], Cfg::R_BYTES);
@@ -295,19 +297,20 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int arow = quarter * 32 + lane;      // output row of this thread inside the CTA's 128-row tile
     const bool store_thread = (ew & 3) == 0 && lane == 0;
     const int Hp = p.H + 1;
-    uint8_t* stg = smem + Cfg::OFF_R + grp * Cfg::R_BYTES;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     for (int j = grp; j < my_cnt; j += 2) {
       const int tile = tile_begin + j;
       const int row0 = tile * 256 + static_cast<int>(rank) * Cfg::TILE_M;
       const int acc = j & (ACC_STAGES - 1);
       const uint32_t acc_phase = static_cast<uint32_t>(j >> 2) & 1u;
-      const uint32_t rphase = static_cast<uint32_t>(j >> 1) & 1u;
+      const int rb = j % Cfg::R_BUFS;
+      const uint32_t rphase = static_cast<uint32_t>(j / Cfg::R_BUFS) & 1u;
+      uint8_t* stg = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
       // the store thread gets here only after the previous TMA store of this buffer finished reading it
       named_bar_sync(1 + grp, 128);
       mbar_wait(&tfull_bar[acc], acc_phase, 0x070a);
       tc_fence_after_sync();
-      if (p.has_res) mbar_wait(&r_full[grp], rphase, 0x070b);
+      if (p.has_res) mbar_wait(&r_full[rb], rphase, 0x070b);
       const int m = row0 + arow;
       const int R = m / Wp;
       const int cpos = m - R * Wp;
@@ -361,7 +364,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tma_store_2d(&tmO, stg + cb * Cfg::R_BOX_BYTES, cb * 64, row0);
         bulk_commit_group();
         bulk_wait_group_read0();               // staging tile read out: the buffer may be refilled
-        if (p.has_res) mbar_arrive(&r_empty[grp]);
+        if (p.has_res) mbar_arrive(&r_empty[rb]);
       }
     }
     if (store_thread) bulk_wait_group0();      // all output bytes are in global memory before the CTA retires
