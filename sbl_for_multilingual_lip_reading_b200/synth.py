@@ -98,3 +98,58 @@ def synthetic_clips(n, t, seed=7, pad_frames=0):
     if pad_frames:
         x[:, :, t - pad_frames:] = 0.0
     return x
+
+
+def classifier_heads(seed=9, d_model=512, n_classes=1500, n_lang=2):
+    """Synthetic weights of the stage-1 pre-training heads `fc_1500` / `fc_2`
+    (VSR_visual_frontend_pretraining_on_LRW_LRW1000_classify/transformer/transformer.py:13-14), nn.Linear default
+    init; used by the 1,000-clip top-1 parity check (BASELINE.json north_star)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    bound = 1.0 / math.sqrt(d_model)
+
+    def u(*shape):
+        return (torch.rand(shape, generator=gen) * 2.0 - 1.0) * bound
+
+    return {"fc_1500.weight": u(n_classes, d_model), "fc_1500.bias": u(n_classes),
+            "fc_2.weight": u(n_lang, d_model), "fc_2.bias": u(n_lang)}
+
+
+def classify(enc_out, heads):
+    """Word / language logits from encoder outputs [N,T,512], the evident intent of the stage-1 model's forward
+    (…classify/transformer/transformer.py:31-36: pooled encoder output -> fc_1500, one frame -> fc_2): the word head
+    reads the time average, the language head the last frame.  fp32 on whatever device `enc_out` lives on."""
+    w1, b1 = heads["fc_1500.weight"].to(enc_out.device), heads["fc_1500.bias"].to(enc_out.device)
+    w2, b2 = heads["fc_2.weight"].to(enc_out.device), heads["fc_2.bias"].to(enc_out.device)
+    pooled = enc_out.float().mean(dim=1)
+    return pooled @ w1.t() + b1, enc_out[:, -1].float() @ w2.t() + b2
+
+
+def structured_clips(n, t, seed=11):
+    """Synthetic clips with per-clip structure (iid-noise clips all map to nearly the same encoder output, which makes
+    top-1 comparisons meaningless): each clip is a mixture of three drifting sinusoidal gratings with random
+    orientation / frequency / speed / contrast, a brightness offset and a soft elliptical "mouth" blob whose opening
+    oscillates over time, quantised to uint8 and normalised like the reference loader (cvtransforms.py:44-48).
+    -> fp32 [n,1,t,88,88]."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 88), torch.linspace(-1, 1, 88), indexing="ij")
+    tt = torch.arange(t, dtype=torch.float32).view(t, 1, 1)
+    clips = []
+    for _ in range(n):
+        img = torch.zeros(t, 88, 88)
+        for _g in range(3):
+            th = torch.rand(1, generator=gen) * math.pi
+            fr = 1.0 + 7.0 * torch.rand(1, generator=gen)
+            sp = (torch.rand(1, generator=gen) - 0.5) * 1.2
+            am = 0.15 + 0.35 * torch.rand(1, generator=gen)
+            ph = torch.rand(1, generator=gen) * 2 * math.pi
+            img = img + am * torch.sin(fr * math.pi * (xx * torch.cos(th) + yy * torch.sin(th)) + sp * tt + ph)
+        cx, cy = (torch.rand(2, generator=gen) - 0.5) * 0.6
+        ax = 0.25 + 0.35 * torch.rand(1, generator=gen)
+        rate = 0.2 + 0.8 * torch.rand(1, generator=gen)
+        ay = 0.08 + 0.25 * (0.5 + 0.5 * torch.sin(rate * tt + torch.rand(1, generator=gen) * 6.28))
+        blob = torch.exp(-(((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2))
+        img = img * (0.3 + 0.7 * torch.rand(1, generator=gen)) - (0.4 + 0.8 * torch.rand(1, generator=gen)) * blob
+        img = img + (torch.rand(1, generator=gen) - 0.5) * 0.8 + 0.05 * torch.randn(t, 88, 88, generator=gen)
+        u8 = ((img * 0.25 + 0.45).clamp(0, 1) * 255).round()
+        clips.append(((u8 / 255.0 - 0.413621) / 0.1700239).unsqueeze(0))
+    return torch.stack(clips).contiguous()

@@ -98,3 +98,24 @@ def test_flops_formula():
     assert O.flops_per_clip(31, 6) == 20800129024
     assert O.flops_per_clip(40, 6) == 26843299840
     assert O.flops_per_clip(31, 3) == 20209119232
+
+
+def test_top1_labels_first_chunk():
+    """The oracle reproduces the reference's top-1 labels (plain and centred heads) on the first 8 of the 1,000
+    clips of tests/golden/top1_1000.npz (the GPU suite checks all 1,000 against the CUDA path)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "top1_1000.npz"))
+    sd = {}
+    sd.update(synth.frontend_state_dict(1, prefix="visual_frontend."))
+    sd.update(synth.encoder_state_dict(2, 6, prefix="encoder."))
+    heads = synth.classifier_heads(9)
+    x = synth.structured_clips(int(g["chunk"]), int(g["frames"]), seed=5000)[:8]
+    with torch.no_grad():
+        out = O.visual_encoder_forward(x, sd)
+        logits, ll = synth.classify(out, heads)
+        lc = (out.mean(dim=1) - torch.from_numpy(g["mu"])) @ heads["fc_1500.weight"].t()
+    assert (logits.argmax(dim=1).numpy() == g["top1"][:8]).all()
+    assert (ll.argmax(dim=1).numpy() == g["lang"][:8]).all()
+    v, i = lc.topk(2, dim=1)
+    close(v[:, 0] - v[:, 1], g["margin_centred"][:8], tol=1e-3)
+    assert (i[:, 0].numpy() == g["top1_centred"][:8]).all()

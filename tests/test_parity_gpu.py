@@ -283,6 +283,44 @@ def test_encoder_stack_rejects_unsupported_shapes(dev):
     assert not enc._use_fused_stack(2, 10, True) and enc._use_fused_stack(2, 10, False)
 
 
+# ------------------------------------------------------------------ 1,000 synthetic clips: identical top-1 class
+def test_top1_class_identical_on_1000_synthetic_clips(frontend, encoder6, dev):
+    """BASELINE.json north_star: identical top-1 class on 1,000 synthetic clips.  The labels in
+    tests/golden/top1_1000.npz come from the unmodified reference modules (tests/golden/make_golden_top1.py);
+    the stage-1 heads (fc_1500 / fc_2, ...classify/transformer/transformer.py:13-14) run in fp32 on both sides.
+    (1) plain heads: every one of the 1,000 clips must get the reference's word and language class;
+    (2) centred word head (pooled output minus the reference mean `mu`, which removes the clip-independent part that
+        dominates with random weights and spreads the clips over hundreds of classes): every clip whose reference
+        top-1 / top-2 margin is clear of the bf16 error must agree, near-ties are counted and bounded."""
+    import os
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "top1_1000.npz")
+    g = np.load(path)
+    chunk, chunks, t = int(g["chunk"]), int(g["chunks"]), int(g["frames"])
+    heads = synth.classifier_heads(9)
+    mu = torch.from_numpy(g["mu"]).to(dev)
+    w1 = heads["fc_1500.weight"].to(dev)
+    top1, lang, top1c, err = [], [], [], []
+    with torch.no_grad():
+        for c in range(chunks):
+            x = synth.structured_clips(chunk, t, seed=5000 + c).to(dev)
+            out, = encoder6(frontend(x), [t] * chunk)
+            logits, ll = synth.classify(out, heads)
+            top1.append(logits.argmax(dim=1).cpu())
+            lang.append(ll.argmax(dim=1).cpu())
+            top1c.append(((out.mean(dim=1) - mu) @ w1.t()).argmax(dim=1).cpu())
+    top1, lang, top1c = torch.cat(top1).numpy(), torch.cat(lang).numpy(), torch.cat(top1c).numpy()
+    assert top1.shape == (chunk * chunks,) and chunk * chunks >= 1000
+    assert (top1 == g["top1"]).all(), f"{(top1 != g['top1']).sum()} of 1000 word classes differ"
+    assert (lang == g["lang"]).all()
+    same = top1c == g["top1_centred"]
+    clear = g["margin_centred"] > 0.015
+    print(f"centred head: {len(set(g['top1_centred'].tolist()))} reference classes, agreement {same.mean():.4f}, "
+          f"{int(clear.sum())} clips with a clear margin")
+    assert same[clear].all(), f"{(~same[clear]).sum()} clips with a clear reference margin disagree"
+    assert same.mean() >= 0.6
+
+
 # ------------------------------------------------------------------ BASELINE-size properties
 def test_config2_batch_independence_and_determinism(frontend, encoder6, dev):
     """Config 2 (32 x 29 x 88 x 88): clips are independent in eval mode, so clip i of the
