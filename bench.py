@@ -192,6 +192,8 @@ def run_b200_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL prints its version banner on stdout; stdout carries exactly ONE JSON line, so NCCL's log goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sblk_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     from sbl_for_multilingual_lip_reading_b200 import ops, synth

@@ -157,7 +157,7 @@ int sblk_qkv_attention_fwd(const void* x_bf16, const void* w_heads_bf16, const f
  *   w_2 bf16 [L*512, d_inner], b_2 / ln2_gamma / ln2_beta fp32 [L*512].
  * x_in bf16 [N*T, d_in]; w_in bf16 [512, d_in]; pe fp32 [>= T, 512]; lengths int32 [N] or NULL; out fp32 [N*T, 512];
  * workspace: sblk_encoder_stack_workspace_bytes(N, T, d_inner) bytes of device memory (contents irrelevant).
- * Implemented for n_head = 8, d_k = d_v = 64, d_model = 512, T <= 128, d_in % 128 == 0, d_inner % 512 == 0 and <= 3072;
+ * Implemented for n_head = 8, d_k = d_v = 64, d_model = 512, T <= 128, d_in % 128 == 0, d_inner % 1024 == 0 and <= 2048;
  * anything else returns < 0 (callers then use the per-step entry points above).
  * replaces: Encoder.forward transformer/encoder.py:36-67 ; EncoderLayer.forward encoder.py:83-91 ;
  * MultiHeadAttention.forward attention.py:32-60 ; ScaledDotProductAttention.forward attention.py:72-83 ;

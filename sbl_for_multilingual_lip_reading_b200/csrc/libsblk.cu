@@ -859,9 +859,9 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   if (a->n_head != 8 || a->d_k != 64 || a->d_model != 512)
     return fail(-1, "sblk_encoder_stack_fwd: only n_head=8, d_k=d_v=64, d_model=512 are implemented (got %d, %d, %d)",
                 a->n_head, a->d_k, a->d_model);
-  if (N <= 0 || T <= 0 || T > 128 || L <= 0 || d_in <= 0 || d_in % 128 != 0 || d_inner <= 0 || d_inner % 256 != 0)
+  if (N <= 0 || T <= 0 || T > 128 || L <= 0 || d_in <= 0 || d_in % 128 != 0 || d_inner <= 0 || d_inner % 1024 != 0)
     return fail(-1, "sblk_encoder_stack_fwd: bad shape N=%d T=%d layers=%d d_in=%d d_inner=%d (T <= 128, d_in %% 128 "
-                "== 0, d_inner %% 256 == 0)", N, T, L, d_in, d_inner);
+                "== 0, d_inner %% 1024 == 0)", N, T, L, d_in, d_inner);
   const void* ptrs[] = {a->x_in, a->w_in, a->b_in, a->ln_in_gamma, a->ln_in_beta, a->pe, a->w_heads, a->b_heads,
                         a->w_fc, a->b_fc, a->ln1_gamma, a->ln1_beta, a->w_1, a->b_1, a->w_2, a->b_2, a->ln2_gamma,
                         a->ln2_beta, a->out, a->workspace};
@@ -879,9 +879,9 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   if (const char* e = getenv("SBLK_ENC_STACK_CL")) cl = atoi(e);
   if (const char* e = getenv("SBLK_ENC_STACK_MC")) mc = atoi(e) != 0;
   if (cl != 8 && cl != 16) return fail(-1, "sblk_encoder_stack_fwd: SBLK_ENC_STACK_CL must be 8 or 16");
-  if (d_inner % (32 * cl) != 0 || d_inner / cl > (cl == 16 ? 192 : 256))
+  if (d_inner % (64 * cl) != 0 || d_inner / cl > (cl == 16 ? 192 : 256))
     return fail(-1, "sblk_encoder_stack_fwd: d_inner=%d not supported by the fused stack (d_inner %% %d == 0, "
-                "d_inner / %d <= %d)", d_inner, 32 * cl, cl, cl == 16 ? 192 : 256);
+                "d_inner / %d <= %d)", d_inner, 64 * cl, cl, cl == 16 ? 192 : 256);
   const long long M = static_cast<long long>(N) * T;
   __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(a->workspace);
   sblk::EncStackParams p;

@@ -422,7 +422,7 @@ def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
 def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layers):
     """Shapes the one-launch encoder stack (csrc/sblk_encoder_stack.cuh) implements."""
     return (n_head == 8 and d_k == 64 and d_v == 64 and d_model == 512 and 0 < t <= 128 and n_layers >= 1 and
-            d_in % 128 == 0 and d_inner % 512 == 0 and d_inner <= 3072)
+            d_in % 128 == 0 and d_inner % 1024 == 0 and d_inner <= 2048)
 
 
 def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None):
