@@ -28,6 +28,10 @@ int sblk_init(void);
 unsigned int sblk_watchdog_code(void);
 /* Enable (1) / disable (0) programmatic dependent launch between consecutive kernels. Returns previous value. */
 int sblk_set_pdl(int enable);
+/* Size the persistent grids of the calling thread's subsequent launches for at most max_sms SMs (rounded down to an
+ * even count; 0 = all SMs).  Used to run independent kernel chains (halves of a clip batch) concurrently on disjoint
+ * SM sets.  Returns the previous limit. */
+int sblk_set_sm_limit(int max_sms);
 /* Number of kernels launched by this library since load (all threads). */
 long long sblk_launch_count(void);
 

@@ -28,6 +28,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 std::atomic<int> g_pdl{0};
+thread_local int g_sm_limit = 0;   // > 0: size persistent grids for at most this many SMs (concurrent kernel chains)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -133,7 +134,8 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::attention_kernel<16>, 100 * 1024))) return rc;
     st.ready = true;
   }
-  if (num_sms_out != nullptr) *num_sms_out = st.num_sms;
+  if (num_sms_out != nullptr)
+    *num_sms_out = (g_sm_limit > 0 && g_sm_limit < st.num_sms) ? g_sm_limit : st.num_sms;
   return 0;
 }
 
@@ -247,6 +249,11 @@ unsigned int sblk_watchdog_code(void) {
 }
 
 int sblk_set_pdl(int enable) { return g_pdl.exchange(enable ? 1 : 0); }
+int sblk_set_sm_limit(int max_sms) {
+  const int prev = g_sm_limit;
+  g_sm_limit = max_sms > 0 ? (max_sms & ~1) : 0;   // even: CTA-pair kernels take whole TPCs
+  return prev;
+}
 long long sblk_launch_count(void) { return g_launches.load(); }
 
 int sblk_pack_conv3d(const float* w, const float* gamma, const float* beta, const float* mean, const float* var,

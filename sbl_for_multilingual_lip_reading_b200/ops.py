@@ -81,6 +81,11 @@ def set_pdl(enable: bool) -> bool:
     return bool(_lib.load().sblk_set_pdl(1 if enable else 0))
 
 
+def set_sm_limit(max_sms: int) -> int:
+    """Size persistent grids of this thread's next launches for at most `max_sms` SMs (0 = all); returns the old limit."""
+    return int(_lib.load().sblk_set_sm_limit(int(max_sms)))
+
+
 def launch_count() -> int:
     return int(_lib.load().sblk_launch_count())
 
@@ -277,11 +282,13 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     return out
 
 
-def avgpool(x, want_f32=True, want_bf16=False):
-    _req(x, BF16, "x")
+def avgpool(x, want_f32=True, want_bf16=False, out_f32=None):
+    _req(x, BF16, "x"); _req(out_f32, F32, "out_f32")
     f, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (f * c)
-    o32 = torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None
+    if out_f32 is not None and tuple(out_f32.shape) != (f, c):
+        raise RuntimeError(f"avgpool: out_f32 shape {tuple(out_f32.shape)} != {(f, c)}")
+    o32 = out_f32 if out_f32 is not None else (torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None)
     o16 = torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None
     _call("sblk_avgpool_fwd", f"avgpool HW={hw} C={c}", 0, 2 * x.numel() + (4 if want_f32 else 0) * f * c +
           (2 if want_bf16 else 0) * f * c, _p(x), _p(o32), _p(o16), f, hw, c, _stream())

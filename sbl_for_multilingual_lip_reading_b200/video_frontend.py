@@ -112,17 +112,24 @@ class Lipreading(nn.Module):
         self.always_on_dropout = True
         self._packed = None
         self._flat_ws = {}
+        self._streams = {}
+        self.parallel_chains = 1     # > 1: clip groups as concurrent kernel chains (measured SLOWER on B200, see _frontend_forward)
+        self.chain_sm_limit = 0      # > 0: each chain sizes its persistent grids for this many SMs
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"] = None
         st["_flat_ws"] = {}
+        st["_streams"] = {}
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         self.__dict__.setdefault("_flat_ws", {})
+        self.__dict__.setdefault("_streams", {})
+        self.__dict__.setdefault("parallel_chains", 1)
+        self.__dict__.setdefault("chain_sm_limit", 0)
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -180,15 +187,15 @@ class Lipreading(nn.Module):
         self._packed = pk
         return pk
 
-    def _flat_workspace(self, a, cout, stride):
+    def _flat_workspace(self, a, cout, stride, chain=0):
         """Two zero-initialised flat buffers for the outputs of a strided block head.  Only pixel rows are ever written
         (sblk_conv2d_dual_igemm_fwd, flat_out), so the halo rows stay zero across calls; cached per (device, shape)."""
         f, h, w_ = (a.f, a.h, a.w) if isinstance(a, ops.FlatActs) else a.shape[:3]
         p, q = (h - 1) // stride + 1, (w_ - 1) // stride + 1
-        key = (str(a.data.device if isinstance(a, ops.FlatActs) else a.device), f, p, q, cout)
+        key = (str(a.data.device if isinstance(a, ops.FlatActs) else a.device), f, p, q, cout, chain)
         ws = self._flat_ws.get(key)
         if ws is None:
-            if len(self._flat_ws) > 8:
+            if len(self._flat_ws) > 16:
                 self._flat_ws.clear()
             dev = a.data.device if isinstance(a, ops.FlatActs) else a.device
             ws = tuple(torch.zeros((ops.flat_rows(f, p, q), cout), dtype=torch.bfloat16, device=dev) for _ in range(2))
@@ -207,31 +214,73 @@ class Lipreading(nn.Module):
             x = x.float()
         return x.contiguous()
 
+    def _frontend_chain(self, x, pk, feat_out, chain):
+        """prep -> Conv3d stem -> ResNet-18 trunk -> average pool for the clips of `x`, on the current stream; writes
+        feat_out [n*T, 512] fp32."""
+        xp = ops.prep_clip(x)
+        # layer1 / layer2 run on the zero-haloed flat layout (flat shifted-window kernels);
+        # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
+        a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
+        for (stride, w1, b1, w2, b2, ds) in pk.blocks:
+            if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
+                y = ops.conv3x3_flat(a, w1, b1, relu=True)
+                a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
+                continue
+            if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input
+                if w2.dim() == 2:  # layer2: the block stays in the flat layout (conv2 is a flat stride-1 conv)
+                    y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True,
+                                             flat_ws=self._flat_workspace(a, w1.shape[0], stride, chain))
+                    a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res)
+                    continue
+                y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
+            else:
+                y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a
+            a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
+        ops.avgpool(a, out_f32=feat_out)
+
+    def _side_streams(self, device, k):
+        pool = self._streams.setdefault(str(device), [])
+        while len(pool) < k:
+            pool.append(torch.cuda.Stream(device=device))
+        return pool[:k]
+
     def _frontend_forward(self, x):
-        """reference :111-117 — returns pooled features [N*T,512] fp32 (before the always-on dropout)."""
+        """reference :111-117 — returns pooled features [N*T,512] fp32 (before the always-on dropout).
+
+        `parallel_chains` > 1 splits the batch into contiguous clip groups whose kernel chains run on separate streams
+        (fork / join with events, capturable as parallel graph branches), optionally with each chain's persistent grids
+        sized for `chain_sm_limit` SMs.  Measured on B200 at the BASELINE batch (32 x 29 frames, graph replay): 1 chain
+        638 us, 2 chains 694 us, 2 chains x 74 SMs 704 us, 4 chains 792 us — the trunk kernels already fill the machine,
+        so concurrency only adds per-kernel fixed cost; the default stays 1 (the option is kept for small-SM parts)."""
         x = self._check_input(x)
         pk = self._get_packed()
+        n, t = x.shape[0], x.shape[2]
         with torch.cuda.device(x.device):
-            xp = ops.prep_clip(x)
-            # layer1 (64 -> 64, stride 1) runs on the zero-haloed flat layout (flat shifted-window kernel);
-            # from layer2 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
-            a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
-            for (stride, w1, b1, w2, b2, ds) in pk.blocks:
-                if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
-                    y = ops.conv3x3_flat(a, w1, b1, relu=True)
-                    a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
-                    continue
-                if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input
-                    if w2.dim() == 2:  # layer2: the block stays in the flat layout (conv2 is a flat stride-1 conv)
-                        y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True,
-                                                 flat_ws=self._flat_workspace(a, w1.shape[0], stride))
-                        a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res)
-                        continue
-                    y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
-                else:
-                    y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a
-                a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
-            feat, _ = ops.avgpool(a, want_f32=True, want_bf16=False)
+            feat = torch.empty((n * t, self.inputDim), dtype=torch.float32, device=x.device)
+            chains = max(1, min(int(self.parallel_chains), n // 8))
+            if chains == 1:
+                self._frontend_chain(x, pk, feat, 0)
+                return feat
+            main = torch.cuda.current_stream()
+            side = self._side_streams(x.device, chains - 1)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            bounds = [(g * n) // chains for g in range(chains + 1)]
+            prev_limit = ops.set_sm_limit(self.chain_sm_limit) if self.chain_sm_limit > 0 else None
+            try:
+                for g in range(chains):
+                    st = main if g == 0 else side[g - 1]
+                    if g > 0:
+                        st.wait_event(fork)
+                    with torch.cuda.stream(st):
+                        self._frontend_chain(x[bounds[g]:bounds[g + 1]], pk, feat[bounds[g] * t:bounds[g + 1] * t], g)
+            finally:
+                if prev_limit is not None:
+                    ops.set_sm_limit(prev_limit)
+            for g in range(1, chains):
+                ev = torch.cuda.Event()
+                ev.record(side[g - 1])
+                main.wait_event(ev)
         return feat
 
     def forward(self, x):

@@ -42,7 +42,10 @@ def graph_time(fn, reps=30):
 
 with torch.no_grad():
     feat = fe(x)
-print(f"frontend (prep+stem+trunk+pool+dropout): {graph_time(lambda: fe(x)):.1f} us")
+for ch, lim in ((1, 0),) + (((2, 0), (2, 74), (4, 0)) if os.environ.get("FE_SWEEP") else ()):
+    fe.parallel_chains, fe.chain_sm_limit = ch, lim
+    print(f"frontend (prep+stem+trunk+pool+dropout), {ch} chains, SM limit {lim}: {graph_time(lambda: fe(x)):.1f} us")
+fe.parallel_chains, fe.chain_sm_limit = int(os.environ.get("FE_CHAINS", 1)), int(os.environ.get("FE_LIMIT", 0))
 for cl, mc in (("16", "1"), ("8", "1")):
     os.environ["SBLK_ENC_STACK_CL"], os.environ["SBLK_ENC_STACK_MC"] = cl, mc
     enc.fused_stack = True
