@@ -196,7 +196,7 @@ def run_b200_arm(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sblk_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
-    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    from sbl_for_multilingual_lip_reading_b200 import ops, sharding, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
     from sbl_for_multilingual_lip_reading_b200.runner import VisualEncoderPlan
     from sbl_for_multilingual_lip_reading_b200.video_frontend import visual_frontend
@@ -251,11 +251,7 @@ def run_b200_arm(args):
     evs = [one_device_step(args.warmup + i, True) for i in range(args.steps)]
     barrier()
     sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
+    dev_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
     value = world * B * args.steps / (dev_ms * 1e-3)
 
     # ---- end-to-end run (host buffers, H2D + D2H inside the timed region) --------------------
