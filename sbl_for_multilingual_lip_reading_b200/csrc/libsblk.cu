@@ -380,6 +380,28 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
   p.H = H; p.W = W; p.relu = relu; p.has_res = residual ? 1 : 0;
   p.bias = bias;
   const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
+  p.dbg = nullptr;
+  if (getenv("SBLK_FLAT_STAMPS")) {   // profiling aid: per-tile clock stamps of CTA 0, printed after a synchronise
+    static unsigned long long* d_dbg = nullptr;
+    const int tiles0 = (p.num_tiles + pairs - 1) / pairs;
+    if (!d_dbg) cudaMalloc(&d_dbg, 4096 * 16 * 8);
+    cudaMemsetAsync(d_dbg, 0, 4096 * 16 * 8, stream);
+    p.dbg = d_dbg;
+    int rc2 = launch(sblk::flatconv2_kernel<CB>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, true,
+                     "flatconv2_kernel", tmX, tmW, tmR, tmO, p);
+    cudaStreamSynchronize(stream);
+    static unsigned long long h[4096 * 16];
+    cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const unsigned long long t0 = h[0];
+    fprintf(stderr, "[flatconv2<%d> stamps, CTA 0, cycles since first] tile: mma(wait_a wait_acc issue_done) "
+            "epi(top bar tfull res released bar2 stored)\n", CB);
+    for (int t = 0; t < tiles0 && t < 40; ++t) {
+      fprintf(stderr, "%3d:", t);
+      for (int k = 0; k < 11; ++k) fprintf(stderr, " %7lld", h[t * 16 + k] ? (long long)(h[t * 16 + k] - t0) : -1LL);
+      fprintf(stderr, "\n");
+    }
+    return rc2;
+  }
   return launch(sblk::flatconv2_kernel<CB>, dim3(2 * pairs), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, true,
                 "flatconv2_kernel", tmX, tmW, tmR, tmO, p);
 }

@@ -17,8 +17,8 @@
 //     ReLU and the halo mask happen in fp32 in place (one rounding to bf16), and the tile leaves with a TMA store.
 //   * the epilogue is two independent groups of 4 warps working on alternate tiles (own staging buffer each), so the
 //     TMEM-load -> math -> store latency chain of one tile overlaps the next tile's.
-// Roles (352 threads): warp 0 activation / residual loader, warp 1 MMA issuer (leader CTA) + TMEM owner,
-// warps 2-9 epilogue, warp 10 filter loader.  Barrier protocol as in sblk_igemm2.cuh (full barriers in the leader).
+// Roles: warp 0 activation loader, warp 1 MMA issuer (leader CTA) + TMEM owner, 8 (C = 128) or 12 (C = 64) epilogue
+// warps, then the filter loader warp and the store + residual warp.  Barrier protocol as in sblk_igemm2.cuh (full barriers in the leader).
 #pragma once
 #include "sblk_common.cuh"
 #include "sblk_igemm2.cuh"
@@ -49,8 +49,13 @@ struct Fc2Cfg {
   static constexpr int SMEM_BYTES = OFF_R + R_BUFS * R_BYTES + 1024;
   static constexpr int ACC_STAGES = 4;
   static constexpr int TMEM_COLS = ACC_STAGES * C;                // 256 / 512
-  static constexpr int EPI_WARPS = 8;                             // two groups of 4 (one TMEM lane quarter each)
-  static constexpr int THREADS = 64 + EPI_WARPS * 32 + 32;        // + filter loader warp
+  // epilogue groups of 4 warps (one TMEM lane quarter each) working on successive tiles.  Two are enough: the C = 64
+  // kernel is SHARED-MEMORY-BANDWIDTH bound (per 128-row tile the 36 N=64 MMAs fetch 180 KB of operands, the
+  // residual / staging / TMA traffic adds 88 KB: ~2100 cycles at 128 B/clk vs ~2550 measured), so a third group
+  // (measured: 36.4 vs 35.5 us) only adds contention
+  static constexpr int EPI_GROUPS = 2;
+  static constexpr int EPI_WARPS = 4 * EPI_GROUPS;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32 + 64;        // + filter loader warp + residual loader warp
 };
 
 // shared -> global TMA store of one box (bulk async group of the issuing thread)
@@ -62,6 +67,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* d, const void* s
 }
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
@@ -75,6 +81,7 @@ struct FlatConv2Params {
   int relu;
   int has_res;
   const float* bias;           // [C] folded BN shift
+  unsigned long long* dbg;     // profiling aid (SBLK_FLAT_STAMPS=1): per-tile clock64 stamps of CTA 0, or nullptr
 };
 
 template <int CB>
@@ -94,8 +101,8 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __shared__ uint64_t a_empty[A_STAGES];     // both CTAs: slot released by the MMAs (multicast commit)
   __shared__ uint64_t b_full[B_SLOTS];       // leader: filter k-block halves of both CTAs landed (resident: slot 0 only)
   __shared__ uint64_t b_empty[B_SLOTS];      // both CTAs (streaming only)
-  __shared__ uint64_t r_full[Cfg::R_BUFS];   // local: residual tile landed
-  __shared__ uint64_t r_empty[Cfg::R_BUFS];  // local: epilogue finished storing from the buffer
+  __shared__ uint64_t r_full[Cfg::R_BUFS];   // local: staging tile may be used (residual landed / previous store read out)
+  __shared__ uint64_t s_ready[Cfg::R_BUFS];  // local: the 4 warps of an epilogue group finished writing the tile
   __shared__ uint64_t tfull_bar[ACC_STAGES];
   __shared__ uint64_t tempty_bar[ACC_STAGES];   // leader: 4 epilogue warps (one group) x 2 CTAs
   __shared__ uint32_t tmem_base_slot;
@@ -137,12 +144,12 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
     for (int i = 0; i < Cfg::R_BUFS; ++i) {
       mbar_init(&r_full[i], 1);
-      mbar_init(&r_empty[i], 1);
+      mbar_init(&s_ready[i], 4);
     }
 #pragma unroll
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], Cfg::EPI_WARPS);
+      mbar_init(&tempty_bar[i], 8);   // the 4 warps of one epilogue group x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -164,7 +171,6 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t phase = 0;
     for (int tile = tile_begin; tile < tile_end; ++tile) {
       const int row0 = tile * 256 + static_cast<int>(rank) * Cfg::TILE_M;   // first output row of this CTA
-      const int j = tile - tile_begin;
       mbar_wait(&a_empty[stage], phase ^ 1u, 0x0701);
       uint8_t* a_dst = smem + Cfg::OFF_A + stage * Cfg::A_STAGE_BYTES;
       const uint32_t bar = mapa_u32(smem_u32(&a_full[stage]), 0);
@@ -176,24 +182,54 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       __syncwarp();
       if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
-      if (p.has_res) {
-        const int rb = j % Cfg::R_BUFS;                              // staging buffer (group j & 1 owns the rb & 1 == j & 1 ones)
-        mbar_wait(&r_empty[rb], (static_cast<uint32_t>(j / Cfg::R_BUFS) & 1u) ^ 1u, 0x0702);
-        uint8_t* r_dst = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&r_full[rb], Cfg::R_BYTES);
-#pragma unroll
-          for (int cb = 0; cb < CB; ++cb)
-            tma_load_2d(r_dst + cb * Cfg::R_BOX_BYTES, &tmR, &r_full[rb], cb * 64, row0);
-        }
-        __syncwarp();
-      }
     }
     for (int i = 0; i < A_STAGES; ++i) {   // drain (see sblk_igemm2.cuh)
       mbar_wait(&a_empty[stage], phase ^ 1u, 0x0703);
       if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
     }
-  } else if (warp == 10) {
+  } else if (warp == 3 + Cfg::EPI_WARPS) {
+    // ------------------------------------------------ store + residual warp (both CTAs).  One lane owns every TMA store
+    // of the CTA (bulk async-groups are per thread) and recycles the staging tiles: as soon as a store has been READ
+    // out of shared memory the tile is handed back — with the residual of its next user already requested (has_res) or
+    // as a plain arrive.  Nothing in the epilogue warps ever waits for a store, and a residual load is in flight two
+    // (C = 64) tiles ahead of its use.  (Clock stamps before: the MMA issuer idled ~40 % on a_full because residual
+    // waits sat in the activation loader's in-order loop, and the epilogue groups idled on their own store reads.)
+    grid_dep_wait();
+    if (lane == 0) {
+      constexpr int R_BUFS = Cfg::R_BUFS;
+      constexpr int LAG = R_BUFS / 2 - 1;      // stores allowed to be still reading when the next one is issued
+      auto recycle = [&](int j_next) {         // staging tile j_next % R_BUFS is free again: prepare it for tile j_next
+        if (j_next >= my_cnt) return;
+        const int rb = j_next % R_BUFS;
+        if (p.has_res) {
+          const int row0 = (tile_begin + j_next) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
+          uint8_t* r_dst = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
+          mbar_arrive_expect_tx(&r_full[rb], Cfg::R_BYTES);
+#pragma unroll
+          for (int cb = 0; cb < CB; ++cb)
+            tma_load_2d(r_dst + cb * Cfg::R_BOX_BYTES, &tmR, &r_full[rb], cb * 64, row0);
+        } else {
+          mbar_arrive(&r_full[rb]);
+        }
+      };
+      if (p.has_res)
+        for (int j = 0; j < R_BUFS; ++j) recycle(j);   // first round: the tiles are free, only the residuals are missing
+      for (int j = 0; j < my_cnt; ++j) {
+        const int rb = j % R_BUFS;
+        const int row0 = (tile_begin + j) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
+        mbar_wait(&s_ready[rb], static_cast<uint32_t>(j / R_BUFS) & 1u, 0x0702);
+        const uint8_t* stg = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb)        // rows past the end of the tensor are clipped by TMA
+          tma_store_2d(&tmO, stg + cb * Cfg::R_BOX_BYTES, cb * 64, row0);
+        bulk_commit_group();
+        if (LAG == 1) bulk_wait_group_read1(); else bulk_wait_group_read0();
+        if (j >= LAG) recycle(j - LAG + R_BUFS);
+      }
+      bulk_wait_group0();                      // all output bytes are in global memory before the CTA retires
+    }
+    __syncwarp();
+  } else if (warp == 2 + Cfg::EPI_WARPS) {
     // ------------------------------------------------ filter loader (both CTAs): own half of the output channels
     const int n0 = static_cast<int>(rank) * Cfg::BH;
     if (Cfg::B_RESIDENT) {
@@ -242,9 +278,13 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap_off[t] = static_cast<uint32_t>(((t / 3) * Wp + (t % 3)) * 8);
       if (Cfg::B_RESIDENT) mbar_wait(&b_full[0], 0, 0x0706);
+      unsigned long long* const dbg = (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
       for (int tile = tile_begin; tile < tile_end; ++tile) {
+        if (dbg) dbg[(tile - tile_begin) * 16 + 0] = clock64();
         mbar_wait(&a_full[stage], phase, 0x0707);
+        if (dbg) dbg[(tile - tile_begin) * 16 + 1] = clock64();
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1u, 0x0708);
+        if (dbg) dbg[(tile - tile_begin) * 16 + 2] = clock64();
         tc_fence_after_sync();
         const uint64_t da0 = make_desc_sw128(smem_base + Cfg::OFF_A + stage * Cfg::A_STAGE_BYTES);
         const uint32_t da0_lo = static_cast<uint32_t>(da0);
@@ -281,6 +321,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           umma2_commit_mc(&a_empty[stage]);
         }
         __syncwarp();
+        if (dbg) dbg[(tile - tile_begin) * 16 + 3] = clock64();
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
         if (++stage == A_STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -295,10 +336,9 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int grp = ew >> 2;                   // epilogue group = staging buffer
     const int quarter = warp & 3;
     const int arow = quarter * 32 + lane;      // output row of this thread inside the CTA's 128-row tile
-    const bool store_thread = (ew & 3) == 0 && lane == 0;
     const int Hp = p.H + 1;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
-    for (int j = grp; j < my_cnt; j += 2) {
+    for (int j = grp; j < my_cnt; j += Cfg::EPI_GROUPS) {
       const int tile = tile_begin + j;
       const int row0 = tile * 256 + static_cast<int>(rank) * Cfg::TILE_M;
       const int acc = j & (ACC_STAGES - 1);
@@ -306,68 +346,74 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int rb = j % Cfg::R_BUFS;
       const uint32_t rphase = static_cast<uint32_t>(j / Cfg::R_BUFS) & 1u;
       uint8_t* stg = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
-      // the store thread gets here only after the previous TMA store of this buffer finished reading it
-      named_bar_sync(1 + grp, 128);
+      unsigned long long* const dbg =
+          (p.dbg != nullptr && blockIdx.x == 0 && (ew & 3) == 0 && lane == 0) ? p.dbg + j * 16 : nullptr;
+      if (dbg) dbg[5] = clock64();
       mbar_wait(&tfull_bar[acc], acc_phase, 0x070a);
       tc_fence_after_sync();
-      if (p.has_res) mbar_wait(&r_full[rb], rphase, 0x070b);
+      if (dbg) dbg[6] = clock64();
+      // the staging tile is usable: residual landed (has_res), or its previous store has been read out (first round of a
+      // residual-free conv: nothing to wait for, hence the inverted parity)
+      mbar_wait(&r_full[rb], p.has_res ? rphase : (rphase ^ 1u), 0x070b);
+      if (dbg) dbg[7] = clock64();
       const int m = row0 + arow;
       const int R = m / Wp;
       const int cpos = m - R * Wp;
       const bool valid = cpos >= 1 && cpos <= p.W && R >= 1 && ((R - 1) % Hp) < p.H;   // else: halo row -> zeros
 #pragma unroll 1
-      for (int c32 = 0; c32 < C / 32; ++c32) {
-        const int col0 = c32 * 32;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                               static_cast<uint32_t>(acc * C + col0), v);
+      for (int c64 = 0; c64 < C / 64; ++c64) {
+        // both 32-column halves of the 64-channel block are requested before the first is used
+        uint32_t v2[2][32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(acc * C + c64 * 64);
+        tmem_ld_32x32b_x32(taddr, v2[0]);
+        tmem_ld_32x32b_x32(taddr + 32u, v2[1]);
         tmem_ld_wait();
-        uint8_t* rowp = stg + (col0 >> 6) * Cfg::R_BOX_BYTES + arow * 128;
+        uint8_t* rowp = stg + c64 * Cfg::R_BOX_BYTES + arow * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[col0 + 8 * q]);
-          const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[col0 + 8 * q + 4]);
-          float f[8];
-          f[0] = __uint_as_float(v[8 * q + 0]) + b0.x; f[1] = __uint_as_float(v[8 * q + 1]) + b0.y;
-          f[2] = __uint_as_float(v[8 * q + 2]) + b0.z; f[3] = __uint_as_float(v[8 * q + 3]) + b0.w;
-          f[4] = __uint_as_float(v[8 * q + 4]) + b1.x; f[5] = __uint_as_float(v[8 * q + 5]) + b1.y;
-          f[6] = __uint_as_float(v[8 * q + 6]) + b1.z; f[7] = __uint_as_float(v[8 * q + 7]) + b1.w;
-          const int cc = ((col0 & 63) >> 3) + q;                     // 16-byte chunk inside the 128-byte row block
-          uint4* slot = reinterpret_cast<uint4*>(rowp + ((cc ^ (arow & 7)) << 4));
-          if (p.has_res) {
-            const uint4 r4 = *slot;
-            f[0] += bf16_lo(r4.x); f[1] += bf16_hi(r4.x); f[2] += bf16_lo(r4.y); f[3] += bf16_hi(r4.y);
-            f[4] += bf16_lo(r4.z); f[5] += bf16_hi(r4.z); f[6] += bf16_lo(r4.w); f[7] += bf16_hi(r4.w);
-          }
-          if (p.relu) {
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t (&v)[32] = v2[hh];
+          const int col0 = c64 * 64 + hh * 32;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+          for (int q = 0; q < 4; ++q) {
+            const float4 b0 = *reinterpret_cast<const float4*>(&bias_s[col0 + 8 * q]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&bias_s[col0 + 8 * q + 4]);
+            float f[8];
+            f[0] = __uint_as_float(v[8 * q + 0]) + b0.x; f[1] = __uint_as_float(v[8 * q + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * q + 2]) + b0.z; f[3] = __uint_as_float(v[8 * q + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * q + 4]) + b1.x; f[5] = __uint_as_float(v[8 * q + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * q + 6]) + b1.z; f[7] = __uint_as_float(v[8 * q + 7]) + b1.w;
+            const int cc = hh * 4 + q;                               // 16-byte chunk inside the 128-byte row block
+            uint4* slot = reinterpret_cast<uint4*>(rowp + ((cc ^ (arow & 7)) << 4));
+            if (p.has_res) {
+              const uint4 r4 = *slot;
+              f[0] += bf16_lo(r4.x); f[1] += bf16_hi(r4.x); f[2] += bf16_lo(r4.y); f[3] += bf16_hi(r4.y);
+              f[4] += bf16_lo(r4.z); f[5] += bf16_hi(r4.z); f[6] += bf16_lo(r4.w); f[7] += bf16_hi(r4.w);
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.0f);
+            }
+            uint4 o;
+            o.x = pack_bf16x2(f[0], f[1]);
+            o.y = pack_bf16x2(f[2], f[3]);
+            o.z = pack_bf16x2(f[4], f[5]);
+            o.w = pack_bf16x2(f[6], f[7]);
+            if (!valid) o = make_uint4(0u, 0u, 0u, 0u);   // halo positions stay zero for the next conv
+            *slot = o;
           }
-          uint4 o;
-          o.x = pack_bf16x2(f[0], f[1]);
-          o.y = pack_bf16x2(f[2], f[3]);
-          o.z = pack_bf16x2(f[4], f[5]);
-          o.w = pack_bf16x2(f[6], f[7]);
-          if (!valid) o = make_uint4(0u, 0u, 0u, 0u);   // halo positions stay zero for the next conv
-          *slot = o;
         }
       }
       // the accumulator is consumed: hand it back to the MMA issuer (leader's barrier)
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_leader + static_cast<uint32_t>(acc * 8));
+      if (dbg) dbg[8] = clock64();
       fence_proxy_async_smem();               // generic-proxy tile writes -> visible to the TMA store
-      named_bar_sync(1 + grp, 128);
-      if (store_thread) {
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb)        // rows past the end of the tensor are clipped by TMA
-          tma_store_2d(&tmO, stg + cb * Cfg::R_BOX_BYTES, cb * 64, row0);
-        bulk_commit_group();
-        bulk_wait_group_read0();               // staging tile read out: the buffer may be refilled
-        if (p.has_res) mbar_arrive(&r_empty[rb]);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_ready[rb]);   // 4 warps -> the store warp issues the tile's TMA store
+      if (dbg) dbg[9] = clock64();
     }
-    if (store_thread) bulk_wait_group0();      // all output bytes are in global memory before the CTA retires
   }
 
   tc_fence_before_sync();
