@@ -538,10 +538,32 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn2 ? bn2 / 2 : bn)};
     if ((rc = encode_tiled(&tmB, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     sblk::IgemmParams p;
-    p.splits = 1; p.split_stride = 0; p.flat_out = flat_out;
+    p.splits = 1; p.split_stride = 0; p.flat_out = flat_out; p.dbg = nullptr; p.staged = 0;
     p.bias2 = bias_ds;
     p.out2_bf16 = static_cast<__nv_bfloat16*>(out_ds);
     p.debug_mode = 0;
+    // profiling aid (SBLK_IGEMM2_STAMPS=1): run the CTA-pair launch with clock stamps of CTA 0 and print them
+    auto with_stamps = [&](auto&& do_launch, int tiles2, int pairs) -> int {
+      if (!getenv("SBLK_IGEMM2_STAMPS")) return do_launch();
+      static unsigned long long* d_dbg = nullptr;
+      if (!d_dbg) cudaMalloc(&d_dbg, 64 * 8);
+      cudaMemsetAsync(d_dbg, 0, 64 * 8, static_cast<cudaStream_t>(stream));
+      p.dbg = d_dbg;
+      const int rc2 = do_launch();
+      cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+      unsigned long long h[64];
+      cudaMemcpy(h, d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      auto rel = [&](int i) { return h[i] ? static_cast<long long>(h[i] - h[0]) : -1LL; };
+      const int nkb = R * S * (Cin / 64);
+      fprintf(stderr, "[igemm2 stamps CTA0, cycles since entry; Cout %d, %d pair tiles on %d pairs, %d k-blocks, staged %d] "
+              "first tile: mma issued %lld, acc ready %lld, epilogue done %lld | last tile: mma issued %lld, acc ready "
+              "%lld, epilogue done %lld | kernel end %lld | k-block arrival every 8:", Cout, tiles2, pairs, nkb, p.staged,
+              rel(1), rel(3), rel(4), rel(2), rel(5), rel(6), rel(7));
+      for (int i = 8; i < 8 + (nkb + 7) / 8 && i < 64; ++i) fprintf(stderr, " %lld", rel(i));
+      fprintf(stderr, "\n");
+      p.dbg = nullptr;
+      return rc2;
+    };
     if (wp_ds) {
       // fused 1x1 downsample branch: its [Cout][Cin] filter rides along with the centre-tap k-blocks
       CUtensorMap tmB2;
@@ -555,9 +577,14 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
       if (bn2) {
         const int tiles2 = ((M + 255) / 256) * (Cout / 128);
         const int pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
-        return launch(sblk::igemm2_kernel<128, true, true>, dim3(2 * pairs), dim3(192),
-                      sblk::Igemm2Cfg<128, true>::SMEM_BYTES, static_cast<cudaStream_t>(stream), true,
-                      "igemm2_kernel<128,dual>", tmA, tmB, tmB2, p);
+        // staged coalesced epilogue stores (they take the place of the last ring stage); measured in the whole graph:
+        // frontend 607 us (always staged) vs 644 us (never); SBLK_IGEMM2_STAGED=0/1 overrides for A/B timing
+        p.staged = 1;
+        if (const char* e = getenv("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
+        return with_stamps([&]() {
+          return launch(sblk::igemm2_kernel<128, true, true>, dim3(2 * pairs), dim3(sblk::Igemm2Cfg<128, true>::THREADS),
+                        sblk::Igemm2Cfg<128, true>::SMEM_BYTES, static_cast<cudaStream_t>(stream), true,
+                        "igemm2_kernel<128,dual>", tmA, tmB, tmB2, p); }, tiles2, pairs);
       }
       const int tiles = m_tiles * (Cout / 128);
       const int grid = tiles < sms ? tiles : sms;
@@ -573,10 +600,15 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     if (bn2) {
       const int tiles2 = ((M + 255) / 256) * (Cout / bn2);
       const int pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
-      if (bn2 == 256)
-        return launch(sblk::igemm2_kernel<256, true>, dim3(2 * pairs), dim3(192), sblk::Igemm2Cfg<256>::SMEM_BYTES,
-                      static_cast<cudaStream_t>(stream), true, "igemm2_kernel<256>", tmA, tmB, tmB, p);
-      return launch(sblk::igemm2_kernel<128, true>, dim3(2 * pairs), dim3(192), sblk::Igemm2Cfg<128>::SMEM_BYTES,
+      p.staged = 1;
+      if (const char* e = getenv("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
+      if (bn2 == 256) {
+        return with_stamps([&]() {
+          return launch(sblk::igemm2_kernel<256, true>, dim3(2 * pairs), dim3(sblk::Igemm2Cfg<256>::THREADS),
+                        sblk::Igemm2Cfg<256>::SMEM_BYTES, static_cast<cudaStream_t>(stream), true, "igemm2_kernel<256>",
+                        tmA, tmB, tmB, p); }, tiles2, pairs);
+      }
+      return launch(sblk::igemm2_kernel<128, true>, dim3(2 * pairs), dim3(sblk::Igemm2Cfg<128>::THREADS), sblk::Igemm2Cfg<128>::SMEM_BYTES,
                     static_cast<cudaStream_t>(stream), true, "igemm2_kernel<128>", tmA, tmB, tmB, p);
     }
     return launch_igemm<true>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
@@ -640,7 +672,7 @@ static int gemm_impl(const void* a, const void* w, const float* bias, const void
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
-  p.splits = splits; p.flat_out = 0;
+  p.splits = splits; p.flat_out = 0; p.dbg = nullptr; p.staged = 0;
   p.split_stride = static_cast<long long>(M) * N;
   return launch_igemm<false>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
 }

@@ -43,6 +43,10 @@ struct IgemmParams {
   // CTA-pair kernel only: write out / out2 into the zero-haloed flat layout of sblk_flatconv.cuh (halo rows are not
   // touched: the caller keeps them zero), output pixel (f, y, x) -> row (f*(P+1) + 1 + y)*(Q+2) + 1 + x
   int flat_out;
+  unsigned long long* dbg;         // profiling aid (SBLK_IGEMM2_STAMPS=1): clock64 stamps of CTA 0, or nullptr
+  // CTA-pair kernel only: 1 = epilogue stores go through per-warp staging tiles (coalesced rows) that take the place of
+  // the last ring stage; 0 = direct per-thread stores and the full ring (L2-latency-bound shapes need every stage)
+  int staged;
 };
 
 template <int BLOCK_N, bool DUAL = false>

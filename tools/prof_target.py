@@ -57,6 +57,14 @@ if what == "forward":
             out, = enc(fe(x), [29] * 32)
     torch.cuda.synchronize()
     print("done forward", float(out.abs().mean()))
+if what == "dual4":
+    # strided block head of layer4: conv3x3 s2 + 1x1 downsample in one pass (6x6x256 -> 3x3x512)
+    x = torch.randn(928, 6, 6, 256, generator=g).to(bf).to(dev)
+    wa = (torch.randn(512, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).to(bf).to(dev)
+    wb = (torch.randn(512, 1, 1, 256, generator=g) / 16).to(bf).to(dev)
+    bz = torch.zeros(512, device=dev)
+    for _ in range(iters):
+        ops.conv2d_dual(x, wa, bz, wb, bz, stride=2)
 if what == "stack":
     # the one-launch encoder stack alone, BASELINE configs[1] shape
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
