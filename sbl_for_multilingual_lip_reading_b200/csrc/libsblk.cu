@@ -289,6 +289,19 @@ int sblk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
                 static_cast<__nv_bfloat16*>(dst), n / 4);
 }
 
+int sblk_l2_prefetch(const void* ptr, long long bytes, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!ptr || bytes <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / empty range");
+  const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(a & ~static_cast<uintptr_t>(127));
+  const long long lines = (static_cast<long long>(a - reinterpret_cast<uintptr_t>(base)) + bytes + 127) / 128;
+  long long grid = (lines + 255) / 256;
+  if (grid > 2 * sms) grid = 2 * sms;
+  return launch(sblk::l2_prefetch_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "l2_prefetch_kernel", base, lines);
+}
+
 long long sblk_prep_clip_elems(int N, int T) {
   using namespace sblk::c3d;
   if (N <= 0 || T <= 0) return -1;

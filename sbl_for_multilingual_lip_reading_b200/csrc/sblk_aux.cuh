@@ -133,6 +133,17 @@ cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ 
   }
 }
 
+// L2 prefetch of a read-only range (packed weights of the layers that run later in the same forward): one
+// prefetch.global.L2 per 128-byte line, no registers / shared memory to speak of, so the few CTAs co-reside with the
+// persistent conv kernels.  The bench flushes L2 between steps, so without it every kernel's first weight tiles (and the
+// whole dependent chain of the encoder stack) pay DRAM latency.
+__global__ void __launch_bounds__(256)
+l2_prefetch_kernel(const uint8_t* __restrict__ base, long long lines) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < lines;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + i * 128));
+}
+
 // --------------------------------------------------------------------------------------------
 // Global average pool: bf16 NHWC [F, HW, C] -> fp32 [F, C] (+ optional bf16 copy).
 // Reference: ResNet.avgpool + view, SBL/transformer/video_frontend.py:87-88.

@@ -124,6 +124,17 @@ def cast_bf16(x, out=None):
     return out
 
 
+def l2_prefetch(tensors):
+    """Hint: pull the storage of every (CUDA, contiguous) tensor in `tensors` into L2 on the current stream."""
+    lib = _lib.load()
+    for t in tensors:
+        if t is None or t.numel() == 0:
+            continue
+        if not t.is_cuda or not t.is_contiguous():
+            raise RuntimeError("l2_prefetch: expected contiguous CUDA tensors")
+        _lib.check(lib.sblk_l2_prefetch(t.data_ptr(), t.numel() * t.element_size(), _stream()), "sblk_l2_prefetch")
+
+
 # ------------------------------------------------------------------------------------ frontend
 def prep_clip(x, out=None):
     """x fp32 [N,1,T,88,88] (or [N,T,88,88]) -> (flat bf16 row-Toeplitz clip, N, T) for conv3d_bn_relu_pool."""

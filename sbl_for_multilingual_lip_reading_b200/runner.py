@@ -55,6 +55,11 @@ class VisualEncoderPlan:
     def _capture(self):
         torch.cuda.synchronize(self.device)
         with torch.no_grad():
+            # the frontend pulls the encoder's packed weights into L2 while its last layer runs (side stream)
+            if getattr(self.frontend, "l2_prefetch", False) and hasattr(self.encoder, "_get_packed"):
+                with torch.cuda.device(self.device):
+                    stk = self.encoder._get_packed().stacked
+                self.frontend.l2_prefetch_extra = [stk[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")]
             # warm-up on the capture stream: packs weights, sizes kernels, stages the lengths vector
             with torch.cuda.stream(self.compute):
                 for _ in range(2):

@@ -115,6 +115,11 @@ class Lipreading(nn.Module):
         self._streams = {}
         self.parallel_chains = 1     # > 1: clip groups as concurrent kernel chains (measured SLOWER on B200, see _frontend_forward)
         self.chain_sm_limit = 0      # > 0: each chain sizes its persistent grids for this many SMs
+        # L2 weight prefetch on a side stream (see _frontend_chain): layers 3-4 when layer 3 starts, and
+        # `l2_prefetch_extra` (a list of tensors: the encoder's packed weights, set by runner.VisualEncoderPlan) when
+        # layer 4 starts
+        self.l2_prefetch = True
+        self.l2_prefetch_extra = None
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
@@ -122,6 +127,7 @@ class Lipreading(nn.Module):
         st["_packed"] = None
         st["_flat_ws"] = {}
         st["_streams"] = {}
+        st["l2_prefetch_extra"] = None
         return st
 
     def __setstate__(self, st):
@@ -130,6 +136,8 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("_streams", {})
         self.__dict__.setdefault("parallel_chains", 1)
         self.__dict__.setdefault("chain_sm_limit", 0)
+        self.__dict__.setdefault("l2_prefetch", True)
+        self.__dict__.setdefault("l2_prefetch_extra", None)
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -221,7 +229,28 @@ class Lipreading(nn.Module):
         # layer1 / layer2 run on the zero-haloed flat layout (flat shifted-window kernels);
         # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
-        for (stride, w1, b1, w2, b2, ds) in pk.blocks:
+        pf_stream = None
+        for bi, (stride, w1, b1, w2, b2, ds) in enumerate(pk.blocks):
+            if self.l2_prefetch and chain == 0 and bi in (0, 4, 6):
+                # Weights of the layers still to come are pulled into L2 by a tiny kernel on a side stream while the
+                # current layer computes (layers 3-4 move few activation bytes, so the lines survive).  Benchmarks flush
+                # L2 between forwards and a serving loop evicts the 61 MB of weights with ~600 MB of activations per
+                # batch: without this, every kernel's first weight tiles and the encoder stack's whole dependent chain
+                # of weight loads pay DRAM latency.
+                if bi == 6:
+                    tensors = list(self.l2_prefetch_extra or ())
+                else:   # layers 1-2 (1.5 MB) while the stem runs, layers 3-4 (28 MB) when layer 3 starts
+                    tensors = [t_ for blk in (pk.blocks[:4] if bi == 0 else pk.blocks[4:])
+                               for t_ in (blk[1], blk[3]) + (tuple(blk[5][:1]) if blk[5] else ())]
+                if tensors:
+                    main = torch.cuda.current_stream()
+                    if pf_stream is None:
+                        pf_stream = self._side_streams(x.device, max(1, int(self.parallel_chains)))[-1]
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    pf_stream.wait_event(ev)
+                    with torch.cuda.stream(pf_stream):
+                        ops.l2_prefetch(tensors)
             if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
                 y = ops.conv3x3_flat(a, w1, b1, relu=True)
                 a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
@@ -237,6 +266,10 @@ class Lipreading(nn.Module):
                 y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a
             a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
         ops.avgpool(a, out_f32=feat_out)
+        if pf_stream is not None:   # join (graph capture needs every forked stream back; no data dependency)
+            ev = torch.cuda.Event()
+            ev.record(pf_stream)
+            torch.cuda.current_stream().wait_event(ev)
 
     def _side_streams(self, device, k):
         pool = self._streams.setdefault(str(device), [])
