@@ -60,6 +60,15 @@ long long sblk_prep_clip_elems(int N, int T);
  * replaces: the implicit zero padding / stride-2 window walk of nn.Conv3d(stride=(1,2,2), padding=(2,3,3)),
  * transformer/video_frontend.py:100 */
 int sblk_prep_clip(const float* x, void* x_prepped_bf16, int N, int T, void* stream);
+/* Fused input pipeline: raw uint8 gray frames [N, T_in, H0, W0] -> the prepped layout of
+ * sblk_prep_clip for clips of T_out >= T_in frames (trailing frames are zero padding in normalised space), cropping
+ * every frame to 88x88 at (crop_y0, crop_x0) or at the per-frame offsets crop_yx int32 [N*T_in][2] (y1, x1), and
+ * normalising through lut_bf16: 256 bf16 values, lut[u] = bf16((u / 255. - 0.413621) / 0.1700239) evaluated on the
+ * host.  Bit-identical to sblk_prep_clip of the reference-normalised fp32 clip.
+ * replaces: load_file / ColorNormalize / CenterCrop / RandomCrop / frame zero-padding of the reference loader,
+ * SBL/data_gen.py:122-125,276-296 ; SBL/cvtransforms.py:7-33,44-48 */
+int sblk_prep_clip_u8(const void* x_u8, const void* lut_bf16, const int* crop_yx, int crop_y0, int crop_x0, void* out,
+                      int N, int T_in, int T_out, int H0, int W0, void* stream);
 /* Conv3d + BN3d(eval) + ReLU + MaxPool3d((1,3,3),(1,2,2),(0,1,1)) + transpose(1,2).contiguous().view:
  * prepped clip -> bf16 NHWC [N*T,22,22,64] (flat_out = 0) or the flat layout below (flat_out = 1).
  * replaces: Lipreading.frontend3D and _frontend_forward's relayout, transformer/video_frontend.py:99-104,111-115 */

@@ -321,6 +321,26 @@ int sblk_prep_clip(const float* x, void* out, int N, int T, void* stream) {
                 static_cast<cudaStream_t>(stream), false, "prep_clip_kernel", x, static_cast<uint4*>(out), N, T);
 }
 
+int sblk_prep_clip_u8(const void* x_u8, const void* lut_bf16, const int* crop_yx, int crop_y0, int crop_x0, void* out,
+                      int N, int T_in, int T_out, int H0, int W0, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x_u8 || !lut_bf16 || !out) return fail(-1, "sblk_prep_clip_u8: null pointer");
+  if (N <= 0 || T_in <= 0 || T_out < T_in || H0 < 88 || W0 < 88)
+    return fail(-1, "sblk_prep_clip_u8: bad shape N=%d T_in=%d T_out=%d H0=%d W0=%d (T_out >= T_in, frames >= 88x88)", N,
+                T_in, T_out, H0, W0);
+  if (!crop_yx && (crop_y0 < 0 || crop_x0 < 0 || crop_y0 + 88 > H0 || crop_x0 + 88 > W0))
+    return fail(-1, "sblk_prep_clip_u8: crop offset (%d, %d) leaves the %dx%d frame", crop_y0, crop_x0, H0, W0);
+  if (!aligned16(out)) return fail(-1, "sblk_prep_clip_u8: output must be 16-byte aligned");
+  const long long rows = static_cast<long long>(N) * (T_out + 2 * sblk::c3d::TPAD) * 2 * sblk::c3d::PLANE_ROWS;
+  long long grid = (rows + 7) / 8;   // one warp per plane row, 8 warps per CTA
+  if (grid > static_cast<long long>(sms) * 8) grid = static_cast<long long>(sms) * 8;
+  return launch(sblk::prep_clip_u8_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "prep_clip_u8_kernel", static_cast<const uint8_t*>(x_u8),
+                static_cast<const uint16_t*>(lut_bf16), crop_yx, crop_y0, crop_x0, static_cast<uint4*>(out), N, T_in,
+                T_out, H0, W0);
+}
+
 int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bias, void* out, int N, int T,
                                  int flat_out, void* stream) {
   using namespace sblk::c3d;

@@ -180,6 +180,39 @@ def flat_rows(f, h, w):
     return int(_lib.load().sblk_flat_rows(f, h, w))
 
 
+def prep_clip_u8(x_u8, lut, t_out=None, crop=(4, 4), out=None):
+    """Raw uint8 gray frames [N,T_in,H0,W0] -> (prepped bf16 clip, N, T_out) for conv3d_bn_relu_pool, fusing the reference
+    loader's /255, ColorNormalize, 88x88 crop and frame zero-padding (data_gen.py:122-125,276-296).  `lut`: bf16 [256]
+    (synth.normalize_lut()).  `crop`: (y1, x1) for every frame (CenterCrop of 96x96 = (4, 4)) or an int32 CUDA tensor
+    [N*T_in, 2] of per-frame offsets (RandomCrop)."""
+    if not x_u8.is_cuda or x_u8.dtype != torch.uint8 or not x_u8.is_contiguous() or x_u8.dim() != 4:
+        raise RuntimeError("prep_clip_u8: expected a contiguous CUDA uint8 tensor [N,T,H0,W0] (no CPU fallback exists)")
+    _req(lut, BF16, "lut")
+    if lut.numel() != 256:
+        raise RuntimeError("prep_clip_u8: lut must hold 256 bf16 values")
+    n, t_in, h0, w0 = x_u8.shape
+    t_out = t_in if t_out is None else int(t_out)
+    crop_t, cy, cx = None, 0, 0
+    if torch.is_tensor(crop):
+        _req(crop, torch.int32, "crop")
+        if tuple(crop.shape) != (n * t_in, 2):
+            raise RuntimeError(f"prep_clip_u8: per-frame crop must be int32 [{n * t_in}, 2]")
+        crop_t = crop
+    else:
+        cy, cx = int(crop[0]), int(crop[1])
+    elems = int(_lib.load().sblk_prep_clip_elems(n, t_out))
+    if elems <= 0:
+        raise RuntimeError(f"prep_clip_u8: bad clip shape N={n} T={t_out}")
+    if out is None:
+        out = torch.empty((elems,), dtype=BF16, device=x_u8.device)
+    _req(out, BF16, "out")
+    if out.numel() < elems:
+        raise RuntimeError(f"prep_clip_u8: output needs {elems} bf16 elements, got {out.numel()}")
+    _call("sblk_prep_clip_u8", f"prep_u8 N={n} T={t_out}", 0, x_u8.numel() + 2 * elems, _p(x_u8), _p(lut), _p(crop_t), cy,
+          cx, _p(out), n, t_in, t_out, h0, w0, _stream())
+    return out, n, t_out
+
+
 def conv3d_bn_relu_pool(xp, wp, bias, out=None, flat=False):
     """prepped clip (out, N, T) of prep_clip -> bf16 NHWC [N*T,22,22,64], or FlatActs when flat=True."""
     xp, n, t = xp

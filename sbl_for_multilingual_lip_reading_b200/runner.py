@@ -21,7 +21,7 @@ from . import ops
 
 
 class VisualEncoderPlan:
-    def __init__(self, frontend, encoder, n, t, device=None, slots=2, pdl=True, lengths=None):
+    def __init__(self, frontend, encoder, n, t, device=None, slots=2, pdl=True, lengths=None, u8_input=None):
         self.frontend, self.encoder = frontend, encoder
         self.n, self.t, self.slots = int(n), int(t), int(slots)
         self.device = torch.device(device if device is not None else "cuda")
@@ -35,8 +35,16 @@ class VisualEncoderPlan:
             self.compute = torch.cuda.Stream()
             self.copy_in = torch.cuda.Stream()
             self.copy_out = torch.cuda.Stream()
-            self.x = [torch.zeros((self.n, 1, self.t, 88, 88), dtype=torch.float32, device=self.device)
-                      for _ in range(self.slots)]
+            # u8_input = (T_in, H0, W0): the plan takes the loader's raw uint8 frames and runs the fused input pipeline
+            # (Lipreading.forward_u8: /255, normalise, centre-crop, pad to t frames) instead of fp32 clips
+            self.u8_input = None if u8_input is None else tuple(int(v) for v in u8_input)
+            if self.u8_input is None:
+                self.x = [torch.zeros((self.n, 1, self.t, 88, 88), dtype=torch.float32, device=self.device)
+                          for _ in range(self.slots)]
+            else:
+                t_in, h0, w0 = self.u8_input
+                self.x = [torch.zeros((self.n, t_in, h0, w0), dtype=torch.uint8, device=self.device)
+                          for _ in range(self.slots)]
             self.out = [None] * self.slots
             self.graphs = [None] * self.slots
             self.ev_in = [torch.cuda.Event() for _ in range(self.slots)]
@@ -48,7 +56,11 @@ class VisualEncoderPlan:
 
     # -------------------------------------------------------------------------------------------
     def _forward_eager(self, x):
-        feat = self.frontend(x)
+        if self.u8_input is not None:
+            _, h0, w0 = self.u8_input
+            feat = self.frontend.forward_u8(x, frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
+        else:
+            feat = self.frontend(x)
         out, = self.encoder(feat, self.lengths)
         return out
 

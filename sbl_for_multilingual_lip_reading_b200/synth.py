@@ -153,3 +153,22 @@ def structured_clips(n, t, seed=11):
         u8 = ((img * 0.25 + 0.45).clamp(0, 1) * 255).round()
         clips.append(((u8 / 255.0 - 0.413621) / 0.1700239).unsqueeze(0))
     return torch.stack(clips).contiguous()
+
+
+NORM_MEAN, NORM_STD = 0.413621, 0.1700239   # ColorNormalize, cvtransforms.py:44-48
+
+
+def normalize_lut():
+    """bf16 [256]: lut[u] = bf16(float32((u / 255. - mean) / std)), evaluated in float64 then cast to float32 exactly like
+    the reference loader does (np.load(...) / 255. -> ColorNormalize -> float32 tensor, data_gen.py:122-125,276-296);
+    used by the fused uint8 input path (ops.prep_clip_u8)."""
+    import numpy as np
+    u = np.arange(256, dtype=np.uint8)
+    v = ((u / 255.) - NORM_MEAN) / NORM_STD          # float64, as numpy computes it in the reference
+    return torch.from_numpy(v.astype(np.float32)).to(torch.bfloat16)
+
+
+def synthetic_u8_clips(n, t, h0=96, w0=96, seed=21):
+    """Raw loader-shaped clips: uint8 gray [n, t, h0, w0] (the reference's .npy files are [29, 96, 96] uint8)."""
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, 256, (n, t, h0, w0), generator=gen, dtype=torch.int32).to(torch.uint8)

@@ -113,6 +113,7 @@ class Lipreading(nn.Module):
         self._packed = None
         self._flat_ws = {}
         self._streams = {}
+        self._lut = {}
         self.parallel_chains = 1     # > 1: clip groups as concurrent kernel chains (measured SLOWER on B200, see _frontend_forward)
         self.chain_sm_limit = 0      # > 0: each chain sizes its persistent grids for this many SMs
         # L2 weight prefetch on a side stream (see _frontend_chain): layers 3-4 when layer 3 starts, and
@@ -127,6 +128,7 @@ class Lipreading(nn.Module):
         st["_packed"] = None
         st["_flat_ws"] = {}
         st["_streams"] = {}
+        st["_lut"] = {}
         st["l2_prefetch_extra"] = None
         return st
 
@@ -134,6 +136,7 @@ class Lipreading(nn.Module):
         self.__dict__.update(st)
         self.__dict__.setdefault("_flat_ws", {})
         self.__dict__.setdefault("_streams", {})
+        self.__dict__.setdefault("_lut", {})
         self.__dict__.setdefault("parallel_chains", 1)
         self.__dict__.setdefault("chain_sm_limit", 0)
         self.__dict__.setdefault("l2_prefetch", True)
@@ -222,10 +225,11 @@ class Lipreading(nn.Module):
             x = x.float()
         return x.contiguous()
 
-    def _frontend_chain(self, x, pk, feat_out, chain):
+    def _frontend_chain(self, x, pk, feat_out, chain, prep=ops.prep_clip):
         """prep -> Conv3d stem -> ResNet-18 trunk -> average pool for the clips of `x`, on the current stream; writes
-        feat_out [n*T, 512] fp32."""
-        xp = ops.prep_clip(x)
+        feat_out [n*T, 512] fp32.  `prep` turns `x` into the stem's prepped layout (fp32 clips: ops.prep_clip; raw
+        uint8 frames: ops.prep_clip_u8 with the normalisation table / crop / frame padding bound in)."""
+        xp = prep(x)
         # layer1 / layer2 run on the zero-haloed flat layout (flat shifted-window kernels);
         # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
@@ -277,7 +281,7 @@ class Lipreading(nn.Module):
             pool.append(torch.cuda.Stream(device=device))
         return pool[:k]
 
-    def _frontend_forward(self, x):
+    def _frontend_forward(self, x, prep=ops.prep_clip, frames=None):
         """reference :111-117 — returns pooled features [N*T,512] fp32 (before the always-on dropout).
 
         `parallel_chains` > 1 splits the batch into contiguous clip groups whose kernel chains run on separate streams
@@ -285,14 +289,17 @@ class Lipreading(nn.Module):
         sized for `chain_sm_limit` SMs.  Measured on B200 at the BASELINE batch (32 x 29 frames, graph replay): 1 chain
         638 us, 2 chains 694 us, 2 chains x 74 SMs 704 us, 4 chains 792 us — the trunk kernels already fill the machine,
         so concurrency only adds per-kernel fixed cost; the default stays 1 (the option is kept for small-SM parts)."""
-        x = self._check_input(x)
+        if frames is None:
+            x = self._check_input(x)
+            n, t = x.shape[0], x.shape[2]
+        else:           # raw uint8 frames, already validated by forward_u8
+            n, t = x.shape[0], frames
         pk = self._get_packed()
-        n, t = x.shape[0], x.shape[2]
         with torch.cuda.device(x.device):
             feat = torch.empty((n * t, self.inputDim), dtype=torch.float32, device=x.device)
             chains = max(1, min(int(self.parallel_chains), n // 8))
             if chains == 1:
-                self._frontend_chain(x, pk, feat, 0)
+                self._frontend_chain(x, pk, feat, 0, prep)
                 return feat
             main = torch.cuda.current_stream()
             side = self._side_streams(x.device, chains - 1)
@@ -306,7 +313,8 @@ class Lipreading(nn.Module):
                     if g > 0:
                         st.wait_event(fork)
                     with torch.cuda.stream(st):
-                        self._frontend_chain(x[bounds[g]:bounds[g + 1]], pk, feat[bounds[g] * t:bounds[g + 1] * t], g)
+                        self._frontend_chain(x[bounds[g]:bounds[g + 1]], pk, feat[bounds[g] * t:bounds[g + 1] * t], g,
+                                             prep)
             finally:
                 if prev_limit is not None:
                     ops.set_sm_limit(prev_limit)
@@ -315,6 +323,41 @@ class Lipreading(nn.Module):
                 ev.record(side[g - 1])
                 main.wait_event(ev)
         return feat
+
+    def forward_u8(self, x_u8, frames=None, crop=(4, 4)):
+        """Fused input pipeline: raw uint8 gray frames [N, T_in, H0, W0] (the loader's .npy layout,
+        H0 = W0 = 96 for LRW) -> the same [N, frames, 512] features `forward` returns for the clip the reference loader
+        would have built on the CPU (/255, ColorNormalize, 88x88 crop at `crop`, zero-padding to `frames` frames:
+        data_gen.py:122-125,276-296; cvtransforms.py:7-48).  `crop`: (y1, x1) or an int32 CUDA tensor [N*T_in, 2] of
+        per-frame offsets (RandomCrop).  Bit-identical to forward(reference-normalised fp32 clip); 4x fewer host->device
+        bytes."""
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("Lipreading (libsblk): training-mode forward/backward is not implemented yet")
+        if not torch.is_tensor(x_u8) or x_u8.dtype != torch.uint8 or x_u8.dim() != 4:
+            raise RuntimeError("forward_u8 expects a uint8 tensor [N, T, H0, W0]")
+        if not x_u8.is_cuda:
+            raise RuntimeError("Lipreading (libsblk) runs on a B200 CUDA device only; no CPU fallback exists")
+        x_u8 = x_u8.contiguous()
+        t_out = x_u8.shape[1] if frames is None else int(frames)
+        if t_out < x_u8.shape[1]:
+            raise RuntimeError(f"forward_u8: frames={t_out} < clip length {x_u8.shape[1]}")
+        key = str(x_u8.device)
+        lut = self._lut.get(key)
+        if lut is None:
+            from . import synth
+            lut = self._lut[key] = synth.normalize_lut().to(x_u8.device)
+        if torch.is_tensor(crop):   # per-frame offsets are sliced with the clips when the batch is split into chains
+            crop = crop.to(device=x_u8.device, dtype=torch.int32).contiguous()
+            if self.parallel_chains != 1:
+                raise RuntimeError("forward_u8: per-frame crop offsets need parallel_chains == 1")
+
+        def prep(xs):
+            return ops.prep_clip_u8(xs, lut, t_out, crop)
+
+        feat = self._frontend_forward(x_u8, prep=prep, frames=t_out)
+        if self.always_on_dropout:
+            feat = F.dropout(feat, p=0.5)  # functional default training=True, exactly as reference :122
+        return feat.view(-1, t_out, self.inputDim)
 
     def forward(self, x):
         """reference :119-125."""

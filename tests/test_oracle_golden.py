@@ -119,3 +119,26 @@ def test_top1_labels_first_chunk():
     v, i = lc.topk(2, dim=1)
     close(v[:, 0] - v[:, 1], g["margin_centred"][:8], tol=1e-3)
     assert (i[:, 0].numpy() == g["top1_centred"][:8]).all()
+
+
+def test_input_pipeline_oracle_matches_reference_transforms():
+    """oracle/input_pipeline_oracle.py against tests/golden/input_pipeline.npz (the reference's cvtransforms functions):
+    eval path (centre crop, pad 29 -> 30) and train-style per-frame crops (offsets drawn like RandomCrop, pad -> 31)."""
+    import os
+    import random
+    from oracle import input_pipeline_oracle as P
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_pipeline.npz"))
+    u8 = synth.synthetic_u8_clips(1, 29, seed=21)[0].numpy()
+    assert np.array_equal(P.eval_clip(u8, 30), g["eval_T30"])
+    random.seed(5)
+    offs = []
+    for _ in range(29):            # cvtransforms.RandomCrop draws x1 then y1 for every frame
+        x1 = random.randint(0, 8)
+        y1 = random.randint(0, 8)
+        offs.append((y1, x1))
+    got = P.pad_frames(P.crop_at(P.load_and_normalize(u8), offs), 31)
+    assert np.array_equal(got, g["train_crop_T31"])
+    # the 256-entry table the CUDA path uses is the same arithmetic, rounded to bf16 once
+    lut = synth.normalize_lut().float().numpy()
+    ref = P.load_and_normalize(np.arange(256, dtype=np.uint8)).astype(np.float32)
+    assert np.array_equal(lut, torch.from_numpy(ref).to(torch.bfloat16).float().numpy())

@@ -321,6 +321,51 @@ def test_top1_class_identical_on_1000_synthetic_clips(frontend, encoder6, dev):
     assert same.mean() >= 0.6
 
 
+# ------------------------------------------------------------------ fused uint8 input pipeline
+def test_fused_u8_input_pipeline_is_bit_identical(frontend, dev, golden):
+    """sblk_prep_clip_u8 (raw uint8 frames -> /255 -> ColorNormalize -> 88x88 crop -> frame zero-padding -> prepped
+    layout) against sblk_prep_clip of the clip the reference loader builds on the CPU (golden from the reference's own
+    cvtransforms, tests/golden/input_pipeline.npz): the prepped buffers and the frontend features must be
+    bit-identical, for the eval path (centre crop) and for per-frame RandomCrop offsets."""
+    import os
+    import random
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_pipeline.npz"))
+    u8 = synth.synthetic_u8_clips(1, 29, seed=21).to(dev)
+    lut = synth.normalize_lut().to(dev)
+    ref30 = torch.from_numpy(g["eval_T30"]).view(1, 1, 30, 88, 88).to(dev)
+    def written(buf, n_, t_):   # the buffer ends with over-read slack that neither kernel writes
+        return buf[:n_ * (t_ + 4) * 2 * 2072 * 8]
+
+    a, _, _ = ops.prep_clip(ref30)
+    b, n, t = ops.prep_clip_u8(u8, lut, 30, (4, 4))
+    assert (n, t) == (1, 30) and torch.equal(written(a, 1, 30), written(b, 1, 30))
+    random.seed(5)
+    offs = []
+    for _ in range(29):
+        x1 = random.randint(0, 8)
+        y1 = random.randint(0, 8)
+        offs.append((y1, x1))
+    ref31 = torch.from_numpy(g["train_crop_T31"]).view(1, 1, 31, 88, 88).to(dev)
+    a, _, _ = ops.prep_clip(ref31)
+    b, _, _ = ops.prep_clip_u8(u8, lut, 31, torch.tensor(offs, dtype=torch.int32, device=dev))
+    assert torch.equal(written(a, 1, 31), written(b, 1, 31))
+    with torch.no_grad():
+        f_ref = frontend(ref30)
+        f_u8 = frontend.forward_u8(u8, frames=30)
+    assert f_u8.shape == (1, 30, 512) and torch.equal(f_ref, f_u8)
+    # a multi-clip batch, other raw sizes, error behaviour
+    u8b = synth.synthetic_u8_clips(3, 7, h0=100, w0=92, seed=3).to(dev)
+    from oracle import input_pipeline_oracle as P
+    refb = torch.from_numpy(np.stack([P.eval_clip(c, 9) for c in u8b.cpu().numpy()])).unsqueeze(1).to(dev)
+    with torch.no_grad():
+        assert torch.equal(frontend(refb), frontend.forward_u8(u8b, frames=9, crop=(6, 2)))
+    with pytest.raises(RuntimeError, match="crop offset"):
+        ops.prep_clip_u8(u8, lut, 30, (9, 4))
+    with pytest.raises(RuntimeError, match="frames="):
+        frontend.forward_u8(u8, frames=5)
+
+
 # ------------------------------------------------------------------ BASELINE-size properties
 def test_config2_batch_independence_and_determinism(frontend, encoder6, dev):
     """Config 2 (32 x 29 x 88 x 88): clips are independent in eval mode, so clip i of the
