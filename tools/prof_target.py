@@ -65,6 +65,14 @@ if what == "dual4":
     bz = torch.zeros(512, device=dev)
     for _ in range(iters):
         ops.conv2d_dual(x, wa, bz, wb, bz, stride=2)
+if what == "dual2":
+    # strided block head of layer2: conv3x3 s2 + 1x1 downsample in one pass (22x22x64 -> 11x11x128)
+    x = torch.randn(928, 22, 22, 64, generator=g).to(bf).to(dev)
+    wa = (torch.randn(128, 3, 3, 64, generator=g) / 24).to(bf).to(dev)
+    wb = (torch.randn(128, 1, 1, 64, generator=g) / 8).to(bf).to(dev)
+    bz = torch.zeros(128, device=dev)
+    for _ in range(iters):
+        ops.conv2d_dual(x, wa, bz, wb, bz, stride=2)
 if what == "stack":
     # the one-launch encoder stack alone, BASELINE configs[1] shape
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
