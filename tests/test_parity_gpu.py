@@ -443,3 +443,39 @@ def test_config2_flat_conv_properties(dev):
     want = torch.relu(conv + x.float().cpu().reshape(-1, 64)[idx].double())
     got = r.dense().reshape(-1, 64)[idx.to(dev)].float().cpu().double()
     assert ((got - want).norm() / want.norm()).item() < 5e-3
+
+
+# ------------------------------------------------------------------ nn.DataParallel (reference train.py:114-115)
+def test_data_parallel_two_gpus_matches_single_gpu():
+    """The reference wraps the model in nn.DataParallel (train.py:114-115): replicas run in worker THREADS on
+    different devices at the same time.  The drop-ins must give the single-GPU result (per-device library state,
+    caller's device and stream, per-replica packed-weight caches)."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading
+
+    class Path(torch.nn.Module):   # what Transformer.forward runs before the decoder (transformer.py:31-38)
+        def __init__(self):
+            super().__init__()
+            self.visual_frontend = Lipreading()
+            self.visual_frontend.load_state_dict(synth.frontend_state_dict(1))
+            self.visual_frontend.always_on_dropout = False
+            self.encoder = Encoder(512, 2, 8, 64, 64, 512, 2048)
+            self.encoder.load_state_dict(synth.encoder_state_dict(2, 2))
+
+        def forward(self, x):
+            feat = self.visual_frontend(x)
+            out, *_ = self.encoder(feat, [feat.size(1)] * feat.size(0))
+            return out
+
+    model = Path().to("cuda:0").eval()
+    x = synth.synthetic_clips(6, 5, seed=77).to("cuda:0")
+    with torch.no_grad():
+        single = model(x)
+        dp = torch.nn.DataParallel(model, device_ids=[0, 1])
+        for _ in range(2):
+            multi = dp(x)
+    assert multi.device == single.device and multi.shape == (6, 5, 512)
+    assert torch.equal(multi, single)
