@@ -48,9 +48,10 @@ int sblk_pack_conv2d(const float* w, const float* gamma, const float* beta, cons
                      float eps, void* w_packed_bf16, float* bias, int Co, int Ci, int R, int S, void* stream);
 /* fp32 -> bf16 cast of n elements (n % 4 == 0). Linear weights [out,in] are already K-major. */
 int sblk_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
-/* Hint: pull [ptr, ptr + bytes) into L2 (prefetch.global.L2 per 128-byte line; no data is produced).  Used on a side
- * stream for the packed weights of the layers that run later in the same forward. */
-int sblk_l2_prefetch(const void* ptr, long long bytes, void* stream);
+/* Hint: pull the n ranges [ptrs[i], ptrs[i] + bytes[i]) into L2 (prefetch.global.L2 per 128-byte line; no data is
+ * produced; ptrs / bytes are HOST arrays).  Used on a side stream for the packed weights of the layers that run later in
+ * the same forward. */
+int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, void* stream);
 
 /* ---- visual frontend ------------------------------------------------------------------------------ */
 /* Number of bf16 elements the prepped clip of sblk_prep_clip needs (includes the over-read slack). */

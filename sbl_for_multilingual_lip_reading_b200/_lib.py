@@ -43,7 +43,7 @@ SIGNATURES = {
     "sblk_pack_conv3d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "sblk_pack_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
-    "sblk_l2_prefetch": (_i, [_vp, _ll, _vp]),
+    "sblk_l2_prefetch": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_ll), _i, _vp]),
     "sblk_prep_clip_elems": (_ll, [_i, _i]),
     "sblk_prep_clip": (_i, [_vp, _vp, _i, _i, _vp]),
     "sblk_prep_clip_u8": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),

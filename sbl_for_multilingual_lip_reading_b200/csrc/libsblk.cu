@@ -289,17 +289,36 @@ int sblk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
                 static_cast<__nv_bfloat16*>(dst), n / 4);
 }
 
-int sblk_l2_prefetch(const void* ptr, long long bytes, void* stream) {
+int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
-  if (!ptr || bytes <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / empty range");
-  const uintptr_t a = reinterpret_cast<uintptr_t>(ptr);
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(a & ~static_cast<uintptr_t>(127));
-  const long long lines = (static_cast<long long>(a - reinterpret_cast<uintptr_t>(base)) + bytes + 127) / 128;
-  long long grid = (lines + 255) / 256;
-  if (grid > 2 * sms) grid = 2 * sms;
-  return launch(sblk::l2_prefetch_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "l2_prefetch_kernel", base, lines);
+  if (!ptrs || !bytes || n <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / no ranges");
+  // Measured on B200 (tools/exp/l2_prefetch_check.py and the whole-path graph): prefetch.global.L2 hints are DROPPED when
+  // tens of MB are requested in one burst (encoder stack after an L2 flush: cold 240 us, one 296-CTA burst 235 us,
+  // throttled hints or demand loads 223 us, warm 221 us), while demand loads running next to the persistent conv kernels
+  // slow the whole graph down (818 -> 980 us: their CTAs finish late and the join holds the encoder back).  One hint
+  // launch PER RANGE keeps the bursts small (launch gaps let the memory system drain) and costs nothing when a hint
+  // is dropped: whole path 820 -> 808 us.  SBLK_L2_PREFETCH_MODE / _CTAS override for experiments.
+  int cap = 2 * sms, mode = 0;
+  if (const char* e = getenv("SBLK_L2_PREFETCH_CTAS")) cap = atoi(e);
+  if (const char* e = getenv("SBLK_L2_PREFETCH_MODE")) mode = atoi(e);
+  for (int i = 0; i < n; ++i) {
+    if (!ptrs[i] || bytes[i] <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / empty range %d", i);
+    sblk::L2PrefetchRanges r;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(ptrs[i]);
+    const uintptr_t base = a & ~static_cast<uintptr_t>(127);
+    r.n = 1;
+    r.base[0] = reinterpret_cast<const uint8_t*>(base);
+    r.first_line[0] = 0;
+    r.first_line[1] = (static_cast<long long>(a - base) + bytes[i] + 127) / 128;
+    long long grid = (r.first_line[1] + 255) / 256;
+    if (grid > cap) grid = cap;
+    if (grid < 1) grid = 1;
+    if ((rc = launch(sblk::l2_prefetch_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+                     static_cast<cudaStream_t>(stream), false, "l2_prefetch_kernel", r, mode)))
+      return rc;
+  }
+  return 0;
 }
 
 long long sblk_prep_clip_elems(int N, int T) {

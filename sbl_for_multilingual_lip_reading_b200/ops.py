@@ -125,14 +125,17 @@ def cast_bf16(x, out=None):
 
 
 def l2_prefetch(tensors):
-    """Hint: pull the storage of every (CUDA, contiguous) tensor in `tensors` into L2 on the current stream."""
-    lib = _lib.load()
-    for t in tensors:
-        if t is None or t.numel() == 0:
-            continue
+    """Hint: pull the storage of every (CUDA, contiguous) tensor in `tensors` into L2 on the current stream (one launch
+    per 24 tensors)."""
+    ts = [t for t in tensors if t is not None and t.numel() > 0]
+    if not ts:
+        return
+    for t in ts:
         if not t.is_cuda or not t.is_contiguous():
             raise RuntimeError("l2_prefetch: expected contiguous CUDA tensors")
-        _lib.check(lib.sblk_l2_prefetch(t.data_ptr(), t.numel() * t.element_size(), _stream()), "sblk_l2_prefetch")
+    ptrs = (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    nbytes = (ctypes.c_longlong * len(ts))(*[t.numel() * t.element_size() for t in ts])
+    _lib.check(_lib.load().sblk_l2_prefetch(ptrs, nbytes, len(ts), _stream()), "sblk_l2_prefetch")
 
 
 # ------------------------------------------------------------------------------------ frontend

@@ -52,7 +52,7 @@ for cl, mc in (("16", "1"), ("8", "1")):
     enc.fused_stack = True
     print(f"encoder  (6 layers), one launch, cluster {cl} multicast {mc}: {graph_time(lambda: enc(feat, [T] * N)):.1f} us")
 os.environ.pop("SBLK_ENC_STACK_CL"); os.environ.pop("SBLK_ENC_STACK_MC")
-for pf in (False, True):
+for pf in (False, True, False, True, False, True):
     fe.l2_prefetch = pf
     fe.l2_prefetch_extra = [enc._get_packed().stacked[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")] if pf else None
     print(f"whole path (one-launch encoder), L2 weight prefetch {pf}: {graph_time(lambda: enc(fe(x), [T] * N)):.1f} us")
