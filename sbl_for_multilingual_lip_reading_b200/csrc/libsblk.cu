@@ -302,21 +302,27 @@ int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, voi
   int cap = 2 * sms, mode = 0;
   if (const char* e = getenv("SBLK_L2_PREFETCH_CTAS")) cap = atoi(e);
   if (const char* e = getenv("SBLK_L2_PREFETCH_MODE")) mode = atoi(e);
+  long long chunk_lines = (64ll << 20) / 128;   // one hint launch per range (<= 64 MB); smaller bursts only add launches (graph: 808 us per tensor, 816 at 4 MB, 871 at 1 MB)
+  if (const char* e = getenv("SBLK_L2_PREFETCH_CHUNK_KB")) chunk_lines = (static_cast<long long>(atoi(e)) << 10) / 128;
+  if (chunk_lines < 1) chunk_lines = 1;
   for (int i = 0; i < n; ++i) {
     if (!ptrs[i] || bytes[i] <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / empty range %d", i);
-    sblk::L2PrefetchRanges r;
     const uintptr_t a = reinterpret_cast<uintptr_t>(ptrs[i]);
     const uintptr_t base = a & ~static_cast<uintptr_t>(127);
-    r.n = 1;
-    r.base[0] = reinterpret_cast<const uint8_t*>(base);
-    r.first_line[0] = 0;
-    r.first_line[1] = (static_cast<long long>(a - base) + bytes[i] + 127) / 128;
-    long long grid = (r.first_line[1] + 255) / 256;
-    if (grid > cap) grid = cap;
-    if (grid < 1) grid = 1;
-    if ((rc = launch(sblk::l2_prefetch_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
-                     static_cast<cudaStream_t>(stream), false, "l2_prefetch_kernel", r, mode)))
-      return rc;
+    const long long lines = (static_cast<long long>(a - base) + bytes[i] + 127) / 128;
+    for (long long l0 = 0; l0 < lines; l0 += chunk_lines) {
+      sblk::L2PrefetchRanges r;
+      r.n = 1;
+      r.base[0] = reinterpret_cast<const uint8_t*>(base) + l0 * 128;
+      r.first_line[0] = 0;
+      r.first_line[1] = lines - l0 < chunk_lines ? lines - l0 : chunk_lines;
+      long long grid = (r.first_line[1] + 255) / 256;
+      if (grid > cap) grid = cap;
+      if (grid < 1) grid = 1;
+      if ((rc = launch(sblk::l2_prefetch_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+                       static_cast<cudaStream_t>(stream), false, "l2_prefetch_kernel", r, mode)))
+        return rc;
+    }
   }
   return 0;
 }
