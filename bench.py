@@ -246,6 +246,8 @@ def run_b200_arm(args):
     out_host = [torch.empty((B, T, 512), dtype=torch.float32).pin_memory() for _ in range(2)]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.empty((world * B, T, 512), dtype=torch.float32, device=dev) if world > 1 else None
+    # output gathering: one-shot peer-memory kernel over NVLink (sharding.P2PGather) or, with --gather nccl, NCCL
+    p2p = sharding.P2PGather(B * T * 512, dev) if (world > 1 and args.gather == "p2p") else None
 
     def barrier():
         if world > 1:
@@ -262,8 +264,11 @@ def run_b200_arm(args):
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(plan.compute)
             plan.graphs[s].replay()
-            if gathered is not None:
-                # output gathering (the DataParallel `gather` of the reference, train.py:115) over NCCL/NVLink
+            if p2p is not None:
+                # output gathering (the DataParallel `gather` of the reference, train.py:115): one kernel that stores
+                # this rank's block into every peer's buffer over NVLink and waits for all peers' blocks
+                p2p(plan.out[s].view(-1))
+            elif gathered is not None:
                 dist.all_gather_into_tensor(gathered, plan.out[s])
             e1.record(plan.compute)
         return e0, e1
@@ -410,7 +415,8 @@ def run_b200_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": dict(workload_config(args, world), host_numa_node_rank0=numa_node),
+            "config": dict(workload_config(args, world), host_numa_node_rank0=numa_node,
+                           gather=(args.gather if world > 1 else None)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 88 * 88 * 4,
                     "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -438,6 +444,8 @@ def main():
     ap.add_argument("--frames", type=int, default=29)
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU output gathering inside the step: one-shot peer-memory kernel (default) or NCCL")
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -210,6 +210,22 @@ typedef struct sblk_encoder_stack_args {
 long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
 int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);
 
+/* ---- one-shot all-gather of the per-GPU outputs over NVLink / NVSwitch peer memory (one process per GPU) ----------
+ * replaces: nn.DataParallel's gather of the replicas' outputs, SBL/train.py:114-115.
+ * sblk_p2p_alloc: cudaMalloc + zero a buffer of its own and return its 64-byte CUDA IPC handle (exchange it with the
+ * peers through any host channel); sblk_p2p_open maps a peer's handle; sblk_p2p_close unmaps (opened != 0) or frees.
+ * sblk_p2p_gather_fwd: ONE kernel stores the local block (bytes_per_rank, multiple of 16) into slot `rank` of every
+ * rank's gather buffer [world * bytes_per_rank], publishes flag[rank] = epoch in every rank's flag array
+ * (unsigned [world]) and returns only when all `world` flags of its own array carry `epoch` (ncclAllGather completion
+ * semantics).  peer_bufs_dev / peer_flags_dev: DEVICE arrays of `world` pointers (entry `rank` = the local buffers);
+ * counter_dev: device unsigned, zero-initialised; epoch must increase by one per call on every rank. */
+int sblk_p2p_alloc(long long bytes, void** dev_ptr, void* ipc_handle_64);
+int sblk_p2p_open(const void* ipc_handle_64, void** dev_ptr);
+int sblk_p2p_close(void* dev_ptr, int opened);
+int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, const void* const* peer_flags_dev,
+                        void* counter_dev, int rank, int world, long long bytes_per_rank, unsigned int epoch,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,10 @@ SIGNATURES = {
     "sblk_gemm_ln_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),
     "sblk_qkv_group_clips": (_i, [_i]),
     "sblk_qkv_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
+    "sblk_p2p_alloc": (_i, [_ll, ctypes.POINTER(_vp), _vp]),
+    "sblk_p2p_open": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "sblk_p2p_close": (_i, [_vp, _i]),
+    "sblk_p2p_gather_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, ctypes.c_uint, _vp]),
     "sblk_encoder_stack_workspace_bytes": (_ll, [_i, _i, _i]),
     "sblk_encoder_stack_fwd": (_i, [ctypes.POINTER(EncoderStackArgs), _vp]),
 }

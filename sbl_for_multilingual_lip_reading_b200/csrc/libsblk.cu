@@ -327,6 +327,63 @@ int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, voi
   return 0;
 }
 
+// ---- peer-memory plumbing for the one-shot output gather (one process per GPU) ------------------------------------
+int sblk_p2p_alloc(long long bytes, void** dev_ptr, void* ipc_handle_64) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (bytes <= 0 || !dev_ptr || !ipc_handle_64) return fail(-1, "sblk_p2p_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));   // a whole allocation of its own: IPC handles map bases
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(p2p buffer)");
+  e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemset(p2p buffer)");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "cudaIpcGetMemHandle"); }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(ipc_handle_64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+
+int sblk_p2p_open(const void* ipc_handle_64, void** dev_ptr) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!ipc_handle_64 || !dev_ptr) return fail(-1, "sblk_p2p_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle_64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaIpcOpenMemHandle");
+  *dev_ptr = p;
+  return 0;
+}
+
+int sblk_p2p_close(void* dev_ptr, int opened) {
+  if (!dev_ptr) return 0;
+  cudaError_t e = opened ? cudaIpcCloseMemHandle(dev_ptr) : cudaFree(dev_ptr);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "sblk_p2p_close");
+}
+
+int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, const void* const* peer_flags_dev,
+                        void* counter_dev, int rank, int world, long long bytes_per_rank, unsigned int epoch,
+                        void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!local || !peer_bufs_dev || !peer_flags_dev || !counter_dev) return fail(-1, "sblk_p2p_gather_fwd: null pointer");
+  if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(-1, "sblk_p2p_gather_fwd: bad rank %d / world %d", rank, world);
+  if (bytes_per_rank <= 0 || (bytes_per_rank & 15) || !aligned16(local))
+    return fail(-1, "sblk_p2p_gather_fwd: block must be a positive multiple of 16 bytes, 16-byte aligned");
+  const long long n16 = bytes_per_rank / 16;
+  long long grid = (n16 + 255) / 256;
+  if (grid > 32) grid = 32;   // 8192 threads x 16 B x `world` stores in flight: enough for NVLink, few SMs
+  return launch(sblk::p2p_gather_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "p2p_gather_kernel", static_cast<const uint4*>(local),
+                reinterpret_cast<uint4* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_bufs_dev))),
+                reinterpret_cast<unsigned int* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_flags_dev))),
+                static_cast<unsigned int*>(counter_dev), rank, world, n16, epoch);
+}
+
 long long sblk_prep_clip_elems(int N, int T) {
   using namespace sblk::c3d;
   if (N <= 0 || T <= 0) return -1;

@@ -479,3 +479,19 @@ def test_data_parallel_two_gpus_matches_single_gpu():
             multi = dp(x)
     assert multi.device == single.device and multi.shape == (6, 5, 512)
     assert torch.equal(multi, single)
+
+
+def test_p2p_gather_two_gpus():
+    """sblk_p2p_gather_fwd (one-shot all-gather over NVLink peer memory, CUDA IPC between the per-GPU processes)
+    against ncclAllGather on 2 GPUs, six steps with alternating buffers (tests/p2p_gather_worker.py under torchrun)."""
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(here, "p2p_gather_worker.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("p2p gather OK") == 2
