@@ -247,7 +247,17 @@ def run_b200_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = torch.empty((world * B, T, 512), dtype=torch.float32, device=dev) if world > 1 else None
     # output gathering: one-shot peer-memory kernel over NVLink (sharding.P2PGather) or, with --gather nccl, NCCL
-    p2p = sharding.P2PGather(B * T * 512, dev) if (world > 1 and args.gather == "p2p") else None
+    p2p, gather_mode = None, (args.gather if world > 1 else None)
+    if world > 1 and args.gather == "p2p":
+        err = None
+        try:
+            p2p = sharding.P2PGather(B * T * 512, dev)
+        except Exception as e:  # noqa: BLE001  (e.g. CUDA IPC not permitted in this container)
+            err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # the choice must be the same on every rank
+        if int(ok.item()) == 0:
+            p2p, gather_mode = None, f"nccl (peer-memory gather unavailable: {err})"
 
     def barrier():
         if world > 1:
@@ -416,7 +426,7 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), host_numa_node_rank0=numa_node,
-                           gather=(args.gather if world > 1 else None)),
+                           gather=gather_mode),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 88 * 88 * 4,
                     "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
