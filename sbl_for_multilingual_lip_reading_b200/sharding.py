@@ -72,28 +72,43 @@ class P2PGather:
             raise ValueError("P2PGather: the per-rank block must be a multiple of 16 bytes")
         lib = _lib.load()
         self._owned, self._opened = [], []
-        mine = []
+        # every step below is collective-safe: a rank that fails still takes part in the exchanges, then ALL ranks raise
+        mine, err = [], None
         with torch.cuda.device(self.device):
-            for nbytes in (self.world * self.block_bytes, self.world * self.block_bytes, 256, 256):   # 2 buffers, 2 flag arrays
-                ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
-                _lib.check(lib.sblk_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "sblk_p2p_alloc")
-                self._owned.append(ptr.value)
-                mine.append(bytes(handle))
+            try:
+                for nbytes in (self.world * self.block_bytes, self.world * self.block_bytes, 256, 256):   # 2 buffers, 2 flag arrays
+                    ptr, handle = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+                    _lib.check(lib.sblk_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "sblk_p2p_alloc")
+                    self._owned.append(ptr.value)
+                    mine.append(bytes(handle))
+            except Exception as e:  # noqa: BLE001
+                err, mine = e, None
             everyone = [None] * self.world
             dist.all_gather_object(everyone, mine, group=group)
+            if any(m is None for m in everyone):
+                self._release()
+                raise RuntimeError(f"P2PGather: peer-memory buffers could not be allocated on every rank ({err})")
             tables = []
-            for which in range(4):
-                ptrs = []
-                for r in range(self.world):
-                    if r == self.rank:
-                        ptrs.append(self._owned[which])
-                    else:
-                        ptr = ctypes.c_void_p()
-                        hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][which])
-                        _lib.check(lib.sblk_p2p_open(hb, ctypes.byref(ptr)), "sblk_p2p_open")
-                        self._opened.append(ptr.value)
-                        ptrs.append(ptr.value)
-                tables.append(torch.tensor(ptrs, dtype=torch.int64, device=self.device))
+            try:
+                for which in range(4):
+                    ptrs = []
+                    for r in range(self.world):
+                        if r == self.rank:
+                            ptrs.append(self._owned[which])
+                        else:
+                            ptr = ctypes.c_void_p()
+                            hb = (ctypes.c_ubyte * 64).from_buffer_copy(everyone[r][which])
+                            _lib.check(lib.sblk_p2p_open(hb, ctypes.byref(ptr)), "sblk_p2p_open")
+                            self._opened.append(ptr.value)
+                            ptrs.append(ptr.value)
+                    tables.append(torch.tensor(ptrs, dtype=torch.int64, device=self.device))
+            except Exception as e:  # noqa: BLE001
+                err = e
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if not all(oks):
+                self._release()
+                raise RuntimeError(f"P2PGather: peer buffers could not be mapped on every rank ({err})")
             self._buf_tables, self._flag_tables = tables[0:2], tables[2:4]
             self._counter = torch.zeros(1, dtype=torch.int32, device=self.device)
             self._views = [_DeviceBuffer(self._owned[i], self.world * self.local_elems).as_tensor(self.device)
@@ -116,16 +131,20 @@ class P2PGather:
         self._lib.check(rc, "sblk_p2p_gather_fwd")
         return self._views[b]
 
-    def close(self):
+    def _release(self):
         lib = self._lib.load()
-        torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
         for p in self._opened:
             lib.sblk_p2p_close(p, 1)
-        dist.barrier(group=self.group)
+        self._opened = []
+        dist.barrier(group=self.group)   # nobody frees a buffer a peer still has mapped
         for p in self._owned:
             lib.sblk_p2p_close(p, 0)
-        self._opened, self._owned = [], []
+        self._owned = []
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        self._release()
 
 
 class _DeviceBuffer:
