@@ -204,6 +204,7 @@ typedef struct sblk_encoder_stack_args {
   int N, T, n_layers, n_head, d_k, d_model, d_in, d_inner;
   float scale; /* 1 / temperature */
   float eps;   /* LayerNorm eps (shared by all LayerNorms of the stack) */
+  int cluster_size;   /* 0 = automatic (16 CTAs per clip group when <= 7 groups, else 8), or 8 / 16 */
   void* debug_stamps; /* NULL, or device uint64 [(1 + 4*n_layers)*8 + 2*groups]: per-stage clock64 stamps of CTA 0, then
                        * (start, end) globaltimer ns of every cluster (profiling aid) */
 } sblk_encoder_stack_args;

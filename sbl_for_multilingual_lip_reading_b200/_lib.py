@@ -28,7 +28,7 @@ class EncoderStackArgs(ctypes.Structure):
         "x_in", "w_in", "b_in", "ln_in_gamma", "ln_in_beta", "pe", "w_heads", "b_heads", "w_fc", "b_fc", "ln1_gamma",
         "ln1_beta", "w_1", "b_1", "w_2", "b_2", "ln2_gamma", "ln2_beta", "lengths", "out", "workspace")] +
         [(n, _i) for n in ("N", "T", "n_layers", "n_head", "d_k", "d_model", "d_in", "d_inner")] +
-        [("scale", _f), ("eps", _f), ("debug_stamps", _vp)])
+        [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp)])
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).

@@ -1050,7 +1050,7 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   // of the BASELINE batch in one wave).  SBLK_ENC_STACK_CL / SBLK_ENC_STACK_MC override for A/B timing.
   const int G = sblk_qkv_group_clips(T);
   const int groups = (N + G - 1) / G;
-  int cl = groups <= 7 ? 16 : 8;
+  int cl = a->cluster_size != 0 ? a->cluster_size : (groups <= 7 ? 16 : 8);
   bool mc = true;
   if (const char* e = getenv("SBLK_ENC_STACK_CL")) cl = atoi(e);
   if (const char* e = getenv("SBLK_ENC_STACK_MC")) mc = atoi(e) != 0;

@@ -113,6 +113,7 @@ class Encoder(nn.Module):
         self.parallel_chains = 4   # clip groups run as concurrent kernel chains (1 = single chain)
         self.fused_stack = True    # one-launch cluster kernel for the whole stack when the shape allows it
         self.fused_stack_max_groups = 12
+        self.split_clusters = True   # 8-11 clip groups: 7 as 16-CTA clusters + the rest as 8-CTA clusters, concurrently
 
     def __getstate__(self):
         st = self.__dict__.copy()
@@ -128,6 +129,7 @@ class Encoder(nn.Module):
         self.__dict__.setdefault("parallel_chains", 4)
         self.__dict__.setdefault("fused_stack", True)
         self.__dict__.setdefault("fused_stack_max_groups", 12)
+        self.__dict__.setdefault("split_clusters", True)
 
     # ------------------------------------------------------------------------------------------
     def _check_config(self):
@@ -293,9 +295,31 @@ class Encoder(nn.Module):
             if self._use_fused_stack(n, t, return_attns):
                 # the whole stack as ONE launch: a cluster per clip group, no inter-group synchronisation
                 stk = pk.stacked
-                ops.encoder_stack(ops.cast_bf16(x), stk, n, t, lengths=lengths,
-                                  scale=1.0 / self.layer_stack[0].slf_attn.temperature, eps=self.layer_norm_in.eps,
-                                  out=out)
+                scale = 1.0 / self.layer_stack[0].slf_attn.temperature
+                x16 = ops.cast_bf16(x)
+                g_clips = max(1, 128 // t)
+                groups = -(-n // g_clips)
+                if self.split_clusters and 7 < groups <= 11:
+                    # Only 7 clusters of 16 CTAs are co-resident on a B200, and 16-CTA clusters are the faster ones (each
+                    # CTA streams half the weights).  The first 7 clip groups run as 16-CTA clusters; the remaining 1-4
+                    # groups run at the same time, on a side stream, as 8-CTA clusters in the SMs the big clusters leave
+                    # free.  Both cluster sizes are bit-identical (tests), so nothing depends on the split.
+                    n0 = 7 * g_clips
+                    main = torch.cuda.current_stream()
+                    side = self._side_streams(x.device, 1)[0]
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    with torch.cuda.stream(side):
+                        ops.encoder_stack(x16[n0 * t:], stk, n - n0, t, lengths=None if lengths is None else lengths[n0:],
+                                          scale=scale, eps=self.layer_norm_in.eps, out=out[n0 * t:], cluster_size=8)
+                        ev2 = torch.cuda.Event()
+                        ev2.record(side)
+                    ops.encoder_stack(x16[:n0 * t], stk, n0, t, lengths=None if lengths is None else lengths[:n0],
+                                      scale=scale, eps=self.layer_norm_in.eps, out=out[:n0 * t], cluster_size=16)
+                    main.wait_event(ev2)
+                else:
+                    ops.encoder_stack(x16, stk, n, t, lengths=lengths, scale=scale, eps=self.layer_norm_in.eps, out=out)
                 return (out.view(n, t, self.d_model),)
             groups = 1 if return_attns else max(1, min(self.parallel_chains, n // 4))
             if groups == 1:

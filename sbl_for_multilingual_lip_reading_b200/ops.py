@@ -479,7 +479,8 @@ def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layer
             d_in % 128 == 0 and d_inner % 1024 == 0 and d_inner <= 2048)
 
 
-def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None):
+def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None,
+                  cluster_size=0):
     """The whole encoder stack in one launch.  x16 bf16 [n*t, d_in]; `stk` = dict of STACKED packed tensors
     (w_in, b_in, g_in, be_in, pe, w_heads, b_heads, w_fc, b_fc, g1, be1, w_1, b_1, w_2, b_2, g2, be2, n_layers, d_inner)
     -> fp32 [n*t, 512]."""
@@ -516,6 +517,7 @@ def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None,
     a.lengths, a.out, a.workspace = _p(lengths), _p(out), _p(workspace)
     a.N, a.T, a.n_layers, a.n_head, a.d_k, a.d_model, a.d_in, a.d_inner = n, t, nl, 8, 64, 512, d_in, d_inner
     a.scale, a.eps = scale, eps
+    a.cluster_size = int(cluster_size)   # 0 = automatic
     a.debug_stamps = _p(debug_stamps)   # optional int64 [1 + 4*n_layers, 8] device tensor (profiling aid)
     flops = 2 * m * 512 * d_in + nl * (2 * m * 512 * (4 * 512 + 2 * d_inner) + 4 * n * 8 * t * t * 64)
     wbytes = 2 * (512 * d_in + nl * (4 * 512 * 512 + 2 * 512 * d_inner))

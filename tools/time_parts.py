@@ -52,6 +52,9 @@ for cl, mc in (("16", "1"), ("8", "1")):
     enc.fused_stack = True
     print(f"encoder  (6 layers), one launch, cluster {cl} multicast {mc}: {graph_time(lambda: enc(feat, [T] * N)):.1f} us")
 os.environ.pop("SBLK_ENC_STACK_CL"); os.environ.pop("SBLK_ENC_STACK_MC")
+for sc in (False, True, False, True):
+    enc.split_clusters = sc
+    print(f"encoder  (6 layers), one launch, split clusters {sc}: {graph_time(lambda: enc(feat, [T] * N)):.1f} us")
 for pf in (False, True, False, True, False, True):
     fe.l2_prefetch = pf
     fe.l2_prefetch_extra = [enc._get_packed().stacked[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")] if pf else None
