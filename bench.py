@@ -225,7 +225,7 @@ def run_b200_arm(args):
 
     from sbl_for_multilingual_lip_reading_b200 import ops, sharding, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
-    from sbl_for_multilingual_lip_reading_b200.runner import VisualEncoderPlan
+    from sbl_for_multilingual_lip_reading_b200.runner import PipelinedVisualEncoderPlan, VisualEncoderPlan
     from sbl_for_multilingual_lip_reading_b200.video_frontend import visual_frontend
 
     ops.init()
@@ -237,7 +237,27 @@ def run_b200_arm(args):
     fe, enc = fe.to(dev).eval(), enc.to(dev).eval()
     torch.manual_seed(1234 + rank)
 
-    plan = VisualEncoderPlan(fe, enc, B, T, device=dev, slots=2, pdl=not args.no_pdl)
+    # Throughput plan: two-stage software pipeline (the encoder stack of batch i-1 co-runs with the clip prep + stem of
+    # batch i, runner.PipelinedVisualEncoderPlan); shapes it does not cover and --no-pipeline use the one-batch plan.
+    pipelined, pipeline_note = False, "off (--no-pipeline)"
+    plan = None
+    if not args.no_pipeline:
+        try:
+            plan = PipelinedVisualEncoderPlan(fe, enc, B, T, device=dev, pdl=not args.no_pdl)
+            pipelined = True
+            pipeline_note = (f"2-stage software pipeline: step i = encoder stack of batch i-1 (8-CTA clusters) next to clip "
+                             f"prep + Conv3d stem of batch i on {plan.head_sm_limit} SMs, then the trunk of batch i at "
+                             f"full width; value/e2e are steady-state throughput, `latency` is the unpipelined plan")
+        except RuntimeError as e:
+            pipeline_note = f"off ({e})"
+    plan_lat = VisualEncoderPlan(fe, enc, B, T, device=dev, slots=2, pdl=not args.no_pdl)
+    if plan is None:
+        plan = plan_lat
+
+    def make_plan(**kw):
+        if pipelined:
+            return PipelinedVisualEncoderPlan(fe, enc, B, T, device=dev, pdl=not args.no_pdl, **kw)
+        return VisualEncoderPlan(fe, enc, B, T, device=dev, slots=2, pdl=not args.no_pdl, **kw)
 
     # synthetic inputs: a pool of distinct batches (host pinned for e2e; device copies for the device-timed run)
     pool_n = 4
@@ -264,8 +284,9 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_device_step(i, timed):
-        """inputs already in HBM; L2 flushed before the timed part; returns (start, end) events."""
+    def one_device_step(i, timed, plan=plan):
+        """inputs already in HBM; L2 flushed before the timed part; returns (start, end) events.  With the pipelined plan
+        the step's output (gathered below) is the previous batch's: one frontend pass + one encoder pass per step."""
         s = i % plan.slots
         with torch.cuda.stream(plan.compute):
             plan.x[s].copy_(dev_pool[i % pool_n])
@@ -273,13 +294,13 @@ def run_b200_arm(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(plan.compute)
-            plan.graphs[s].replay()
+            out = plan.forward_device(s)
             if p2p is not None:
                 # output gathering (the DataParallel `gather` of the reference, train.py:115): one kernel that stores
                 # this rank's block into every peer's buffer over NVLink and waits for all peers' blocks
-                p2p(plan.out[s].view(-1))
+                p2p(out.view(-1))
             elif gathered is not None:
-                dist.all_gather_into_tensor(gathered, plan.out[s])
+                dist.all_gather_into_tensor(gathered, out)
             e1.record(plan.compute)
         return e0, e1
 
@@ -296,10 +317,25 @@ def run_b200_arm(args):
     dev_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
     value = world * B * args.steps / (dev_ms * 1e-3)
 
+    # ---- one-batch latency of the unpipelined plan (same timing rules; extra key, not the metric) ----------
+    latency = None
+    if pipelined:
+        for i in range(3):
+            one_device_step(i, False, plan_lat)
+        barrier()
+        lat_n = min(args.steps, 20)
+        evs_l = [one_device_step(3 + i, True, plan_lat) for i in range(lat_n)]
+        barrier()
+        lat_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs_l), dev) / lat_n
+        latency = {"ms_per_step": lat_ms, "clips_per_s": world * B / (lat_ms * 1e-3), "steps": lat_n,
+                   "plan": "VisualEncoderPlan (one batch per replay, nothing overlapped across batches)"}
+
     # ---- end-to-end run (host buffers, H2D + D2H inside the timed region) --------------------
     def e2e_steps(k):
         for i in range(k):
             plan.submit_host(host_pool[i % pool_n], out_host[i % 2])
+        if pipelined:   # k inputs in, the k outputs OF THOSE inputs out: the last batch's encoder runs here
+            plan.drain(out_host[k % 2])
         plan.synchronize()
 
     e2e_steps(max(args.warmup, 3))
@@ -322,12 +358,14 @@ def run_b200_arm(args):
     # instead of 31 KB) and /255, ColorNormalize, centre crop are done by the clip-prep kernel ----------------------
     e2e_u8 = None
     if not args.no_u8:
-        plan8 = VisualEncoderPlan(fe, enc, B, T, device=dev, slots=2, pdl=not args.no_pdl, u8_input=(T, 96, 96))
+        plan8 = make_plan(u8_input=(T, 96, 96))
         host_u8 = [synth.synthetic_u8_clips(B, T, seed=300 + 17 * rank + i).pin_memory() for i in range(pool_n)]
 
         def u8_steps(k):
             for i in range(k):
                 plan8.submit_host(host_u8[i % pool_n], out_host[i % 2])
+            if pipelined:
+                plan8.drain(out_host[k % 2])
             plan8.synchronize()
 
         u8_steps(max(args.warmup, 3))
@@ -347,6 +385,9 @@ def run_b200_arm(args):
     if rank == 0:
         peaks = load_peaks()
         prev_pdl = ops.set_pdl(False)
+        prev_cl = enc.stack_cluster_size
+        if pipelined:
+            enc.stack_cluster_size = 8   # the launch the timed region uses (one launch, 8-CTA clusters)
         agg = {}
         passes = 5
         with torch.no_grad():
@@ -364,6 +405,7 @@ def run_b200_arm(args):
                     a["ms"] += r["start"].elapsed_time(r["end"])
                     a["launches"] += 1
         ops.set_pdl(bool(prev_pdl))
+        enc.stack_cluster_size = prev_cl
         total_ms = sum(a["ms"] for a in agg.values()) / passes
         rows = sorted(agg.items(), key=lambda kv: -kv[1]["ms"])
         breakdown = []
@@ -426,13 +468,14 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), host_numa_node_rank0=numa_node,
-                           gather=gather_mode),
+                           gather=gather_mode, pipeline=pipeline_note),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 88 * 88 * 4,
                     "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
                     "timing": "wall clock, synchronize on both sides, double-buffered H2D/compute/D2H",
                     "result_checksum": checksum},
             "e2e_u8": e2e_u8,
+            "latency": latency,
             "gpu_launches": plan.launches_per_forward * args.steps,
             "gpu_launches_per_step": plan.launches_per_forward,
         }
@@ -454,6 +497,8 @@ def main():
     ap.add_argument("--frames", type=int, default=29)
     ap.add_argument("--layers", type=int, default=6)
     ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="time the one-batch plan instead of the two-stage software pipeline")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU output gathering inside the step: one-shot peer-memory kernel (default) or NCCL")
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")

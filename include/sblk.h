@@ -52,6 +52,12 @@ int sblk_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stre
  * produced; ptrs / bytes are HOST arrays).  Used on a side stream for the packed weights of the layers that run later in
  * the same forward. */
 int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, void* stream);
+/* Co-scheduling gate for two concurrent kernel chains (runner.PipelinedVisualEncoderPlan: the encoder stack of batch
+ * i-1 next to the clip prep + stem of batch i).  Enqueues a one-thread kernel that returns once `count` more CTAs have
+ * bumped gate[0] (sblk_encoder_stack_args.resident_counter) than gate[1] accounts for, or after timeout_us; gate[1] then
+ * advances by `count`.  Kernels enqueued behind it on `stream` therefore start only when the other chain's clusters have
+ * been placed.  A scheduling hint only: results never depend on it.  No reference counterpart. */
+int sblk_gate_wait(void* gate_u32x2, int count, int timeout_us, void* stream);
 
 /* ---- visual frontend ------------------------------------------------------------------------------ */
 /* Number of bf16 elements the prepped clip of sblk_prep_clip needs (includes the over-read slack). */
@@ -207,6 +213,8 @@ typedef struct sblk_encoder_stack_args {
   int cluster_size;   /* 0 = automatic (16 CTAs per clip group when <= 7 groups, else 8), or 8 / 16 */
   void* debug_stamps; /* NULL, or device uint64 [(1 + 4*n_layers)*8 + 2*groups]: per-stage clock64 stamps of CTA 0, then
                        * (start, end) globaltimer ns of every cluster (profiling aid) */
+  void* resident_counter; /* NULL, or device uint32[2] (zero-initialised once): every CTA adds 1 to word 0 when it starts
+                           * running, i.e. when its cluster owns its SMs (see sblk_gate_wait) */
 } sblk_encoder_stack_args;
 long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
 int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);

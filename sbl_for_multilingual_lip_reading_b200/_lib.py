@@ -28,7 +28,7 @@ class EncoderStackArgs(ctypes.Structure):
         "x_in", "w_in", "b_in", "ln_in_gamma", "ln_in_beta", "pe", "w_heads", "b_heads", "w_fc", "b_fc", "ln1_gamma",
         "ln1_beta", "w_1", "b_1", "w_2", "b_2", "ln2_gamma", "ln2_beta", "lengths", "out", "workspace")] +
         [(n, _i) for n in ("N", "T", "n_layers", "n_head", "d_k", "d_model", "d_in", "d_inner")] +
-        [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp)])
+        [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp), ("resident_counter", _vp)])
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).
@@ -44,6 +44,7 @@ SIGNATURES = {
     "sblk_pack_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
     "sblk_l2_prefetch": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_ll), _i, _vp]),
+    "sblk_gate_wait": (_i, [_vp, _i, _i, _vp]),
     "sblk_prep_clip_elems": (_ll, [_i, _i]),
     "sblk_prep_clip": (_i, [_vp, _vp, _i, _i, _vp]),
     "sblk_prep_clip_u8": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),

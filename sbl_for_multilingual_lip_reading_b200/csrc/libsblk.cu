@@ -327,6 +327,16 @@ int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, voi
   return 0;
 }
 
+int sblk_gate_wait(void* gate_u32x2, int count, int timeout_us, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!gate_u32x2 || count <= 0 || timeout_us < 0) return fail(-1, "sblk_gate_wait: bad arguments");
+  if (reinterpret_cast<uintptr_t>(gate_u32x2) % 8 != 0) return fail(-1, "sblk_gate_wait: gate must be 8-byte aligned");
+  return launch(sblk::gate_wait_kernel, dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream), false,
+                "gate_wait_kernel", static_cast<unsigned int*>(gate_u32x2), static_cast<unsigned int>(count),
+                static_cast<unsigned long long>(timeout_us) * 1000ull);
+}
+
 // ---- peer-memory plumbing for the one-shot output gather (one process per GPU) ------------------------------------
 int sblk_p2p_alloc(long long bytes, void** dev_ptr, void* ipc_handle_64) {
   int sms, rc;
@@ -1069,6 +1079,7 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   p.x16 = ws; p.att16 = ws + M * 512; p.h16 = ws + M * 1024;
   p.scale = a->scale; p.eps = a->eps;
   p.dbg = static_cast<unsigned long long*>(a->debug_stamps);
+  p.resident = static_cast<unsigned int*>(a->resident_counter);
 
   CUtensorMap tm[9];
   const cuuint32_t a_rows = mc ? static_cast<cuuint32_t>(128 / cl) : 128u;

@@ -428,4 +428,25 @@ add_layernorm512_kernel(const LnParams p) {
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// Co-scheduling gate (one thread): returns once `count` more CTAs have bumped gate[0] than the running target gate[1]
+// records, or after timeout_ns (the gate only ORDERS the placement of two concurrent kernel chains; results never depend
+// on it, so giving up is safe).  gate[1] advances by `count` either way, so late arrivals of this round are accounted for
+// when the next round starts (rounds are stream-ordered: all CTAs of a round have run before the next gate launch).
+__global__ void gate_wait_kernel(unsigned int* gate, unsigned int count, unsigned long long timeout_ns) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned int target = gate[1] + count;
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gate) : "memory");
+    if (static_cast<int>(v - target) >= 0) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > timeout_ns) break;
+    __nanosleep(200);
+  }
+  gate[1] = target;
+}
+
 }  // namespace sblk

@@ -58,6 +58,7 @@ struct EncStackParams {
   float scale;               // 1 / temperature
   float eps;                 // LayerNorm eps (all three LayerNorms of the reference use the default 1e-5)
   unsigned long long* dbg;   // optional [stages][8] clock64 stamps of cluster 0 / CTA 0 (profiling aid), or nullptr
+  unsigned int* resident;    // optional: every CTA adds 1 when it starts running (sblk_gate_wait: co-scheduling hint)
 };
 
 template <int CL>
@@ -223,6 +224,9 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   };
 
   if (threadIdx.x == 0) {
+    // a running CTA means its whole cluster has been placed; a gate kernel on another stream (sblk_gate_wait) holds a
+    // co-running kernel chain back until every cluster of this launch owns its SMs
+    if (p.resident != nullptr) atomicAdd(p.resident, 1u);
     tma_prefetch_desc(&tmXin); tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmAtt); tma_prefetch_desc(&tmH);
     tma_prefetch_desc(&tmWin); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWfc); tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);

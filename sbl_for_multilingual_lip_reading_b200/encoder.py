@@ -114,12 +114,15 @@ class Encoder(nn.Module):
         self.fused_stack = True    # one-launch cluster kernel for the whole stack when the shape allows it
         self.fused_stack_max_groups = 12
         self.split_clusters = True   # 8-11 clip groups: 7 as 16-CTA clusters + the rest as 8-CTA clusters, concurrently
+        self.stack_cluster_size = 0  # 0 = automatic; 8 / 16 force the cluster size of the one-launch stack (disables the split)
+        self._resident_counter = None   # int32 [2] CUDA tensor while runner.PipelinedVisualEncoderPlan captures (ops.gate_wait)
 
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_packed"] = None
         st["_len_cache"] = {}
         st["_streams"] = {}
+        st["_resident_counter"] = None
         return st
 
     def __setstate__(self, st):
@@ -130,6 +133,8 @@ class Encoder(nn.Module):
         self.__dict__.setdefault("fused_stack", True)
         self.__dict__.setdefault("fused_stack_max_groups", 12)
         self.__dict__.setdefault("split_clusters", True)
+        self.__dict__.setdefault("stack_cluster_size", 0)
+        self.__dict__.setdefault("_resident_counter", None)
 
     # ------------------------------------------------------------------------------------------
     def _check_config(self):
@@ -299,7 +304,7 @@ class Encoder(nn.Module):
                 x16 = ops.cast_bf16(x)
                 g_clips = max(1, 128 // t)
                 groups = -(-n // g_clips)
-                if self.split_clusters and 7 < groups <= 11:
+                if self.split_clusters and self.stack_cluster_size == 0 and 7 < groups <= 11:
                     # Only 7 clusters of 16 CTAs are co-resident on a B200, and 16-CTA clusters are the faster ones (each
                     # CTA streams half the weights).  The first 7 clip groups run as 16-CTA clusters; the remaining 1-4
                     # groups run at the same time, on a side stream, as 8-CTA clusters in the SMs the big clusters leave
@@ -319,7 +324,8 @@ class Encoder(nn.Module):
                                       scale=scale, eps=self.layer_norm_in.eps, out=out[:n0 * t], cluster_size=16)
                     main.wait_event(ev2)
                 else:
-                    ops.encoder_stack(x16, stk, n, t, lengths=lengths, scale=scale, eps=self.layer_norm_in.eps, out=out)
+                    ops.encoder_stack(x16, stk, n, t, lengths=lengths, scale=scale, eps=self.layer_norm_in.eps, out=out,
+                                      cluster_size=self.stack_cluster_size, resident_counter=self._resident_counter)
                 return (out.view(n, t, self.d_model),)
             groups = 1 if return_attns else max(1, min(self.parallel_chains, n // 4))
             if groups == 1:

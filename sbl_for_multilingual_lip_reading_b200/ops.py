@@ -138,6 +138,16 @@ def l2_prefetch(tensors):
     _lib.check(_lib.load().sblk_l2_prefetch(ptrs, nbytes, len(ts), _stream()), "sblk_l2_prefetch")
 
 
+def gate_wait(gate, count, timeout_us=300):
+    """Co-scheduling hint: hold the current stream until `count` more CTAs of a kernel launched with
+    `resident_counter=gate` (encoder_stack) have started running, or `timeout_us` passed.  gate: int32 [2] CUDA tensor,
+    zero-initialised once and then owned by the pair of launches."""
+    _req(gate, torch.int32, "gate")
+    if gate.numel() < 2:
+        raise RuntimeError("gate_wait: gate must hold two int32 words")
+    _lib.check(_lib.load().sblk_gate_wait(_p(gate), int(count), int(timeout_us), _stream()), "sblk_gate_wait")
+
+
 # ------------------------------------------------------------------------------------ frontend
 def prep_clip(x, out=None):
     """x fp32 [N,1,T,88,88] (or [N,T,88,88]) -> (flat bf16 row-Toeplitz clip, N, T) for conv3d_bn_relu_pool."""
@@ -480,7 +490,7 @@ def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layer
 
 
 def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None,
-                  cluster_size=0):
+                  cluster_size=0, resident_counter=None):
     """The whole encoder stack in one launch.  x16 bf16 [n*t, d_in]; `stk` = dict of STACKED packed tensors
     (w_in, b_in, g_in, be_in, pe, w_heads, b_heads, w_fc, b_fc, g1, be1, w_1, b_1, w_2, b_2, g2, be2, n_layers, d_inner)
     -> fp32 [n*t, 512]."""
@@ -519,8 +529,9 @@ def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None,
     a.scale, a.eps = scale, eps
     a.cluster_size = int(cluster_size)   # 0 = automatic
     a.debug_stamps = _p(debug_stamps)   # optional int64 [1 + 4*n_layers, 8] device tensor (profiling aid)
+    a.resident_counter = _p(resident_counter)   # optional int32 [2] device tensor (co-scheduling gate, see gate_wait)
     flops = 2 * m * 512 * d_in + nl * (2 * m * 512 * (4 * 512 + 2 * d_inner) + 4 * n * 8 * t * t * 64)
     wbytes = 2 * (512 * d_in + nl * (4 * 512 * 512 + 2 * 512 * d_inner))
-    _call("sblk_encoder_stack_fwd", f"encoder stack L={nl} T={t}", flops, wbytes + m * (2 * d_in + 4 * 512),
+    _call("sblk_encoder_stack_fwd", f"encoder stack L={nl} T={t} N={n}", flops, wbytes + m * (2 * d_in + 4 * 512),
           ctypes.byref(a), _stream())
     return out

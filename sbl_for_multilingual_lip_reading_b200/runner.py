@@ -10,6 +10,9 @@ graph per input slot (streams + graphs instead of a tracing compiler) and expose
                              double-buffered so the PCIe copy of clip batch i+1 overlaps the compute of batch i
                              (bench `e2e`)
 
+`PipelinedVisualEncoderPlan` is the throughput form of the same plan: a two-stage software pipeline in which the
+(latency-bound, 64-SM) encoder stack of batch i-1 runs next to the clip prep + Conv3d stem of batch i.
+
 The modules stay ordinary drop-ins: a plan is an optional accelerator around them, owning only torch tensors,
 streams and graphs.
 """
@@ -77,15 +80,15 @@ class VisualEncoderPlan:
                 for _ in range(2):
                     self._forward_eager(self.x[0])
             self.compute.synchronize()
-            pool = None
+            # One private memory pool PER graph: with a shared pool the static output of one slot may alias an
+            # intermediate buffer of the other slot's graph, and submit_host lets the device->host copy of slot s overlap
+            # the replay of slot s^1 (a few hundred MB per pool; HBM is not the constraint here).
             for s in range(self.slots):
                 g = torch.cuda.CUDAGraph()
                 before = ops.launch_count()
-                with torch.cuda.graph(g, stream=self.compute, pool=pool):
+                with torch.cuda.graph(g, stream=self.compute):
                     self.out[s] = self._forward_eager(self.x[s])
                 self.launches_per_forward = ops.launch_count() - before
-                if pool is None:
-                    pool = g.pool()
                 self.graphs[s] = g
         torch.cuda.synchronize(self.device)
         for ev in self.ev_out + self.ev_done:
@@ -126,3 +129,129 @@ class VisualEncoderPlan:
 
     def close(self):
         ops.set_pdl(bool(self._prev_pdl))
+
+
+class PipelinedVisualEncoderPlan(VisualEncoderPlan):
+    """Two-stage software pipeline over consecutive clip batches (steady-state throughput; one batch of extra latency).
+
+    The one-launch encoder stack is a dependent chain of 25 small GEMM stages: at the BASELINE batch it holds 8 clusters
+    of 8 CTAs (64 of the 148 SMs) for ~0.2 ms at 10 % of the tensor peak, while the frontend kernels fill the machine.
+    Replay i of this plan therefore runs
+
+        encoder(features of batch i-1)   on a side stream, 8-CTA clusters           ||
+        clip prep + Conv3d stem (+ the first `head_blocks` residual blocks) of batch i, persistent grids sized for the
+        SMs the encoder leaves free (`head_sm_limit`)
+
+    joins, and runs the rest of the trunk of batch i at full width.  A one-thread gate kernel (`ops.gate_wait`) holds
+    the head back until every encoder cluster has been placed, so the two chains never fight over SM placement.
+    Results are bit-identical to the unpipelined plan (same kernels; the grid size of a persistent kernel does not change
+    any tile's arithmetic).  `forward_device(slot)` / `submit_host` return the output of the PREVIOUS batch; `drain()`
+    finishes the last one."""
+
+    def __init__(self, frontend, encoder, n, t, device=None, pdl=True, lengths=None, u8_input=None,
+                 head_sm_limit=None, head_blocks=0, gate=True, gate_timeout_us=300):
+        self.head_sm_limit, self.head_blocks = head_sm_limit, int(head_blocks)
+        self.use_gate, self.gate_timeout_us = bool(gate), int(gate_timeout_us)
+        super().__init__(frontend, encoder, n, t, device=device, slots=2, pdl=pdl, lengths=lengths, u8_input=u8_input)
+
+    def _capture(self):
+        fe, enc = self.frontend, self.encoder
+        dev = self.device
+        g_clips = max(1, 128 // self.t)
+        groups = -(-self.n // g_clips)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        if not enc._use_fused_stack(self.n, self.t, False) or 8 * groups > sms - 16:
+            raise RuntimeError("PipelinedVisualEncoderPlan needs the one-launch encoder stack on 8-CTA clusters "
+                               f"({groups} clip groups on {sms} SMs); use VisualEncoderPlan for this shape")
+        enc_ctas = 8 * groups
+        if self.head_sm_limit is None:
+            self.head_sm_limit = (sms - enc_ctas) & ~1
+        torch.cuda.synchronize(dev)
+        self.enc_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.gate = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.feat = [torch.zeros((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev) for _ in range(2)]
+        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap)
+        try:
+            with torch.no_grad():
+                stk = enc._get_packed().stacked
+                if getattr(fe, "l2_prefetch", False):
+                    fe.l2_prefetch_extra = [stk[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")]
+                enc.stack_cluster_size = 8
+                with torch.cuda.stream(self.compute):   # warm-up: packs weights, sizes kernels, stages the lengths
+                    for _ in range(2):
+                        self._forward_eager(self.x[0])
+                self.compute.synchronize()
+                for s in range(2):   # one private pool per graph (see VisualEncoderPlan._capture)
+                    g = torch.cuda.CUDAGraph()
+                    before = ops.launch_count()
+                    with torch.cuda.graph(g, stream=self.compute):
+                        main = torch.cuda.current_stream()
+                        fork, done = torch.cuda.Event(), torch.cuda.Event()
+                        fork.record(main)
+                        self.enc_stream.wait_event(fork)
+                        with torch.cuda.stream(self.enc_stream):
+                            enc._resident_counter = self.gate if self.use_gate else None
+                            self.out[s ^ 1], = enc(self.feat[s ^ 1], self.lengths)
+                            enc._resident_counter = None
+                            done.record(self.enc_stream)
+                        if self.use_gate:
+                            ops.gate_wait(self.gate, enc_ctas, self.gate_timeout_us)
+                        fe._overlap = (self.head_sm_limit, self.head_blocks, lambda: main.wait_event(done))
+                        if self.u8_input is not None:
+                            _, h0, w0 = self.u8_input
+                            f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
+                        else:
+                            f = fe(self.x[s])
+                        fe._overlap = None
+                        self.feat[s].copy_(f)
+                    self.launches_per_forward = ops.launch_count() - before
+                    self.graphs[s] = g
+        finally:
+            enc.stack_cluster_size, enc._resident_counter, fe._overlap = saved
+        torch.cuda.synchronize(dev)
+        for ev in self.ev_out + self.ev_done:
+            ev.record(torch.cuda.current_stream(dev))
+
+    def forward_device(self, slot=0):
+        """Replay step `slot`: frontend of x[slot] next to the encoder of the batch replayed before it (the other slot).
+        Returns that PREVIOUS batch's static output tensor [N,T,d_model] fp32."""
+        with torch.cuda.stream(self.compute):
+            self.graphs[slot].replay()
+        return self.out[slot ^ 1]
+
+    def submit_host(self, x_host, out_host):
+        """One pipelined step: x_host (pinned) -> device; out_host (pinned) receives the output of the batch submitted
+        by the PREVIOUS call (of the warm-up / zero features on the first call).  Returns the completion event."""
+        s = self._i % 2
+        self._i += 1
+        self.copy_in.wait_event(self.ev_done[s])
+        with torch.cuda.stream(self.copy_in):
+            self.x[s].copy_(x_host, non_blocking=True)
+            self.ev_in[s].record(self.copy_in)
+        self.compute.wait_event(self.ev_in[s])
+        self.compute.wait_event(self.ev_out[s])   # out[s ^ 1] of this graph's previous replay has left the device
+        with torch.cuda.stream(self.compute):
+            self.graphs[s].replay()
+            self.ev_done[s].record(self.compute)
+        self.copy_out.wait_event(self.ev_done[s])
+        with torch.cuda.stream(self.copy_out):
+            out_host.copy_(self.out[s ^ 1], non_blocking=True)
+            self.ev_out[s].record(self.copy_out)
+        return self.ev_out[s]
+
+    def drain(self, out_host=None):
+        """Encoder of the last submitted batch (eager, on the compute stream).  Returns its device output; also copies it
+        to `out_host` when given."""
+        s = (self._i - 1) % 2
+        enc = self.encoder
+        saved = enc.stack_cluster_size
+        with torch.no_grad(), torch.cuda.stream(self.compute):
+            self.compute.wait_event(self.ev_out[s ^ 1])
+            try:
+                enc.stack_cluster_size = 8
+                out, = enc(self.feat[s], self.lengths)
+            finally:
+                enc.stack_cluster_size = saved
+            if out_host is not None:
+                out_host.copy_(out, non_blocking=True)
+        return out

@@ -121,6 +121,11 @@ class Lipreading(nn.Module):
         # layer 4 starts
         self.l2_prefetch = True
         self.l2_prefetch_extra = None
+        # (sm_limit, head_blocks, join) set by runner.PipelinedVisualEncoderPlan while it captures: the clip prep, the stem
+        # and the first `head_blocks` residual blocks size their persistent grids for `sm_limit` SMs because another
+        # kernel chain (the previous batch's encoder stack) co-runs on the other SMs; `join()` is called once the head
+        # is enqueued and makes the current stream wait for that chain before the full-width kernels start
+        self._overlap = None
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
@@ -130,6 +135,7 @@ class Lipreading(nn.Module):
         st["_streams"] = {}
         st["_lut"] = {}
         st["l2_prefetch_extra"] = None
+        st["_overlap"] = None
         return st
 
     def __setstate__(self, st):
@@ -141,6 +147,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("chain_sm_limit", 0)
         self.__dict__.setdefault("l2_prefetch", True)
         self.__dict__.setdefault("l2_prefetch_extra", None)
+        self.__dict__.setdefault("_overlap", None)
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -229,12 +236,27 @@ class Lipreading(nn.Module):
         """prep -> Conv3d stem -> ResNet-18 trunk -> average pool for the clips of `x`, on the current stream; writes
         feat_out [n*T, 512] fp32.  `prep` turns `x` into the stem's prepped layout (fp32 clips: ops.prep_clip; raw
         uint8 frames: ops.prep_clip_u8 with the normalisation table / crop / frame padding bound in)."""
+        ov = self._overlap if chain == 0 else None
+        head = {"limit": ops.set_sm_limit(ov[0])} if ov is not None else None
+        try:
+            self._frontend_chain_body(x, pk, feat_out, chain, prep, ov, head)
+        finally:
+            if head is not None and "limit" in head:
+                ops.set_sm_limit(head.pop("limit"))
+
+    def _frontend_chain_body(self, x, pk, feat_out, chain, prep, ov, head):
+        def end_head():   # back to full-width grids; the co-running chain must be finished before they start
+            ops.set_sm_limit(head.pop("limit"))
+            ov[2]()
+
         xp = prep(x)
         # layer1 / layer2 run on the zero-haloed flat layout (flat shifted-window kernels);
         # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
         pf_stream = None
         for bi, (stride, w1, b1, w2, b2, ds) in enumerate(pk.blocks):
+            if ov is not None and bi == ov[1]:
+                end_head()
             if self.l2_prefetch and chain == 0 and bi in (0, 4, 6):
                 # Weights of the layers still to come are pulled into L2 by a tiny kernel on a side stream while the
                 # current layer computes (layers 3-4 move few activation bytes, so the lines survive).  Benchmarks flush
@@ -269,6 +291,8 @@ class Lipreading(nn.Module):
             else:
                 y, res = ops.conv2d(a, w1, b1, stride=stride, relu=True), a
             a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
+        if ov is not None and ov[1] >= len(pk.blocks):
+            end_head()
         ops.avgpool(a, out_f32=feat_out)
         if pf_stream is not None:   # join (graph capture needs every forked stream back; no data dependency)
             ev = torch.cuda.Event()

@@ -383,6 +383,76 @@ def test_config2_batch_independence_and_determinism(frontend, encoder6, dev):
     assert rel_fro(out[16:], part) < 1e-6
 
 
+@pytest.mark.parametrize("n,t,lens", [(32, 29, None), (8, 40, None), (6, 29, [29, 11, 29, 3, 20, 29])])
+def test_pipelined_plan_is_bit_identical_to_eager_modules(frontend, encoder6, dev, n, t, lens):
+    """runner.PipelinedVisualEncoderPlan (the encoder stack of batch i-1 co-running with the clip prep + stem of batch i
+    on the SMs it leaves free, ordered by the sblk_gate_wait kernel) must return, one step late, exactly what the
+    drop-in modules return for each batch: same kernels, only grid sizes and scheduling differ.  Shapes: BASELINE
+    configs[1], the configs[2] per-GPU shard (8 clips x 40 frames), a ragged-length batch.  Also through submit_host
+    (pinned host in / out) and drain()."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.runner import PipelinedVisualEncoderPlan
+    lens = [t] * n if lens is None else lens
+    xs = [synth.synthetic_clips(n, t, seed=50 + i) for i in range(4)]
+    with torch.no_grad():
+        want = [encoder6(frontend(x.to(dev)), lens)[0].cpu() for x in xs]
+    plan = PipelinedVisualEncoderPlan(frontend, encoder6, n, t, device=dev, lengths=lens)
+    try:
+        # device-resident inputs
+        got = []
+        for i, x in enumerate(xs):
+            with torch.cuda.stream(plan.compute):
+                plan.x[i % 2].copy_(x.to(dev))
+                prev = plan.forward_device(i % 2)
+                if i > 0:
+                    got.append(prev.clone())
+            plan.compute.synchronize()
+        plan._i = len(xs)
+        last = plan.drain()
+        plan.compute.synchronize()
+        got.append(last.clone())
+        torch.cuda.synchronize(dev)
+        for i in range(len(xs)):
+            assert torch.equal(got[i].cpu(), want[i]), f"device path, batch {i}"
+        assert int(plan.gate[0]) == int(plan.gate[1]) > 0   # every encoder CTA reported in, every gate accounted for
+        # host path: k inputs in, the k outputs of those inputs out (shifted by one call, the last one by drain)
+        plan._i = 0
+        hin = [x.pin_memory() for x in xs]
+        hout = [torch.empty((n, t, 512), dtype=torch.float32).pin_memory() for _ in range(len(xs) + 1)]
+        for i in range(len(xs)):
+            plan.submit_host(hin[i], hout[i])
+        plan.drain(hout[len(xs)])
+        plan.synchronize()
+        for i in range(len(xs)):
+            assert torch.equal(hout[i + 1], want[i]), f"host path, batch {i}"
+    finally:
+        plan.close()
+    # the modules are left as they were
+    assert encoder6.stack_cluster_size == 0 and encoder6._resident_counter is None and frontend._overlap is None
+
+
+def test_gate_wait_times_out_and_rejects_bad_arguments(dev):
+    """sblk_gate_wait is a scheduling hint: with nobody bumping the counter it must give up after its timeout (not
+    hang) and still advance its target word; bad arguments fail loudly."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    gate = torch.zeros(2, dtype=torch.int32, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ops.gate_wait(gate, 64, timeout_us=200)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    assert gate.tolist() == [0, 64]
+    assert 0.15 < e0.elapsed_time(e1) < 50.0
+    gate[0] = 128   # already satisfied: returns at once
+    ops.gate_wait(gate, 64, timeout_us=10_000_000)
+    torch.cuda.synchronize(dev)
+    assert gate.tolist() == [128, 128]
+    with pytest.raises(RuntimeError):
+        ops.gate_wait(gate, 0)
+    with pytest.raises(RuntimeError):
+        ops.gate_wait(torch.zeros(2, dtype=torch.float32, device=dev), 8)
+
+
 def test_config2_linearity_of_conv_stage(frontend, dev):
     """conv(a*x) = a*conv(x) for a power-of-two a (exact in bf16/fp32 without bias/ReLU clipping):
     checks the implicit GEMM at the full layer-1 size M = 928*22*22."""

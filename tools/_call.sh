@@ -1,4 +1,2 @@
-python bench.py > gpurun_out/bench_r1q.json 2> gpurun_out/bench_r1q.err
-python tools/prof_target.py forward 2 > gpurun_out/plain_fwd.log 2>&1 && ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1q.csv python tools/prof_target.py forward 2 > gpurun_out/ncu_fwd.log 2>&1
-python tools/prof_target.py flat 3 > gpurun_out/plain_flat2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:flatconv2 -s 1 -c 1 -f -o gpurun_out/prof_flat2_r1c python tools/prof_target.py flat 3 > gpurun_out/ncu_flat2.log 2>&1
-python tools/prof_target.py l4conv 3 > gpurun_out/plain_l4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:igemm2 -s 1 -c 1 -f -o gpurun_out/prof_l4conv_r1d python tools/prof_target.py l4conv 3 > gpurun_out/ncu_l4.log 2>&1
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1u.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_r1u.log
+timeout 300 python bench.py > gpurun_out/bench_r1u.json 2> gpurun_out/bench_r1u.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1u.err; head -c 600 gpurun_out/bench_r1u.json
