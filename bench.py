@@ -387,7 +387,7 @@ def run_b200_arm(args):
         prev_pdl = ops.set_pdl(False)
         prev_cl = enc.stack_cluster_size
         if pipelined:
-            enc.stack_cluster_size = 8   # the launch the timed region uses (one launch, 8-CTA clusters)
+            enc.stack_cluster_size = plan.enc_cluster   # the launch the timed region uses (one launch, one cluster size)
         agg = {}
         passes = 5
         with torch.no_grad():

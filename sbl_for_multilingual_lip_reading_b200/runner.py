@@ -149,8 +149,11 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
     finishes the last one."""
 
     def __init__(self, frontend, encoder, n, t, device=None, pdl=True, lengths=None, u8_input=None,
-                 head_sm_limit=None, head_blocks=0, gate=True, gate_timeout_us=300):
-        self.head_sm_limit, self.head_blocks = head_sm_limit, int(head_blocks)
+                 head_sm_limit=None, head_blocks=None, gate=True, gate_timeout_us=300, enc_cluster=None):
+        # head_blocks: residual blocks (after prep + stem) that run next to the encoder on `head_sm_limit` SMs; None =
+        # automatic (see _capture).  enc_cluster: CTAs per encoder cluster (8 or 16), None = 8.
+        self.enc_cluster = enc_cluster
+        self.head_sm_limit, self.head_blocks = head_sm_limit, head_blocks
         self.use_gate, self.gate_timeout_us = bool(gate), int(gate_timeout_us)
         super().__init__(frontend, encoder, n, t, device=device, slots=2, pdl=pdl, lengths=lengths, u8_input=u8_input)
 
@@ -160,12 +163,22 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         g_clips = max(1, 128 // self.t)
         groups = -(-self.n // g_clips)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        if not enc._use_fused_stack(self.n, self.t, False) or 8 * groups > sms - 16:
-            raise RuntimeError("PipelinedVisualEncoderPlan needs the one-launch encoder stack on 8-CTA clusters "
-                               f"({groups} clip groups on {sms} SMs); use VisualEncoderPlan for this shape")
-        enc_ctas = 8 * groups
+        if self.enc_cluster is None:
+            # 8-CTA clusters leave the most SMs to the co-running frontend (measured at 8 clips x 40 frames: 375 us per
+            # step with clusters of 8 against 401 us with 16, 511 us unpipelined)
+            self.enc_cluster = 8
+        cl = int(self.enc_cluster)
+        if cl not in (8, 16) or not enc._use_fused_stack(self.n, self.t, False) or cl * groups > sms - 16:
+            raise RuntimeError("PipelinedVisualEncoderPlan needs the one-launch encoder stack in one wave of clusters "
+                               f"({groups} clip groups x {cl} CTAs on {sms} SMs); use VisualEncoderPlan for this shape")
+        enc_ctas = cl * groups
         if self.head_sm_limit is None:
             self.head_sm_limit = (sms - enc_ctas) & ~1
+        if self.head_blocks is None:
+            # BASELINE-sized batches: only prep + stem fit next to the ~0.2 ms encoder (measured, tools/exp/
+            # pipeline_probe.py); small latency-bound batches: the whole frontend co-runs with it
+            self.head_blocks = 0 if self.n * self.t > 512 else 8
+        self.head_blocks = int(self.head_blocks)
         torch.cuda.synchronize(dev)
         self.enc_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.gate = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -176,7 +189,7 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                 stk = enc._get_packed().stacked
                 if getattr(fe, "l2_prefetch", False):
                     fe.l2_prefetch_extra = [stk[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")]
-                enc.stack_cluster_size = 8
+                enc.stack_cluster_size = cl
                 with torch.cuda.stream(self.compute):   # warm-up: packs weights, sizes kernels, stages the lengths
                     for _ in range(2):
                         self._forward_eager(self.x[0])
@@ -248,7 +261,7 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         with torch.no_grad(), torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_out[s ^ 1])
             try:
-                enc.stack_cluster_size = 8
+                enc.stack_cluster_size = int(self.enc_cluster)
                 out, = enc(self.feat[s], self.lengths)
             finally:
                 enc.stack_cluster_size = saved

@@ -45,12 +45,16 @@ plain = VisualEncoderPlan(fe, enc, N, T, device=dev)
 # ---- timing ----
 med, best = time_plan(plain)
 print(f"plain plan (split clusters {enc.split_clusters}): median {med:.1f} us  best {best:.1f} us")
-for limit, blocks, gate in ((None, 0, True), (None, 0, False), (74, 0, True), (100, 0, True), (148, 0, True), (None, 1, True)):
+variants = [(None, 0, True, None), (None, 0, False, None), (74, 0, True, None), (148, 0, True, None), (None, 1, True, None)]
+if N * T <= 512:
+    variants = [(None, hb, True, cl) for cl in (16, 8) for hb in (0, 2, 4, 8)] + [(148, 8, True, 16), (None, 8, False, 16)]
+for limit, blocks, gate, cl in variants:
     try:
-        p = PipelinedVisualEncoderPlan(fe, enc, N, T, device=dev, head_sm_limit=limit, head_blocks=blocks, gate=gate)
+        p = PipelinedVisualEncoderPlan(fe, enc, N, T, device=dev, head_sm_limit=limit, head_blocks=blocks, gate=gate,
+                                       enc_cluster=cl)
         med, best = time_plan(p)
-        print(f"pipelined head_sm_limit={p.head_sm_limit} head_blocks={blocks} gate={gate}: median {med:.1f} us  "
-              f"best {best:.1f} us  ({N / med * 1e6:.0f} clips/s)")
+        print(f"pipelined cl={p.enc_cluster} head_sm_limit={p.head_sm_limit} head_blocks={blocks} gate={gate}: median "
+              f"{med:.1f} us  best {best:.1f} us  ({N / med * 1e6:.0f} clips/s)")
         del p
     except Exception as e:  # noqa: BLE001
-        print(f"pipelined limit={limit} blocks={blocks} gate={gate}: FAILED {e}")
+        print(f"pipelined cl={cl} limit={limit} blocks={blocks} gate={gate}: FAILED {e}")
