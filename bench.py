@@ -214,6 +214,11 @@ def run_b200_arm(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 arm has no CPU fallback (use --impl reference)")
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner ignores
+    # NCCL_DEBUG_FILE) is sent to stderr by pointing fd 1 at fd 2 for the whole run; the line goes to the saved fd
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
@@ -284,9 +289,23 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def one_device_step(i, timed, plan=plan):
+    def gather_outputs(out):
+        if p2p is not None:
+            # output gathering (the DataParallel `gather` of the reference, train.py:115): one kernel that stores this
+            # rank's block into every peer's buffer over NVLink and waits for all peers' blocks
+            p2p(out.view(-1))
+        elif gathered is not None:
+            dist.all_gather_into_tensor(gathered, out)
+
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    pending = [None]
+
+    def one_device_step(i, timed, plan=plan, defer_gather=pipelined and world > 1 and not args.inline_gather):
         """inputs already in HBM; L2 flushed before the timed part; returns (start, end) events.  With the pipelined plan
-        the step's output (gathered below) is the previous batch's: one frontend pass + one encoder pass per step."""
+        the step's output is the previous batch's: one frontend pass + one encoder pass per step.  Multi-GPU: every step
+        contains exactly one output gather inside its event pair — in stream after the replay, or (pipelined plan) the
+        gather of the PREVIOUS step's output on a side stream next to this step's replay, so that a rank waiting for
+        its peers' blocks keeps computing (the output buffer it reads is not written by this replay)."""
         s = i % plan.slots
         with torch.cuda.stream(plan.compute):
             plan.x[s].copy_(dev_pool[i % pool_n])
@@ -294,15 +313,25 @@ def run_b200_arm(args):
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(plan.compute)
+            if defer_gather and pending[0] is not None:
+                gather_stream.wait_event(e0)
+                with torch.cuda.stream(gather_stream):
+                    gather_outputs(pending[0])
             out = plan.forward_device(s)
-            if p2p is not None:
-                # output gathering (the DataParallel `gather` of the reference, train.py:115): one kernel that stores
-                # this rank's block into every peer's buffer over NVLink and waits for all peers' blocks
-                p2p(out.view(-1))
-            elif gathered is not None:
-                dist.all_gather_into_tensor(gathered, out)
+            if defer_gather:
+                plan.compute.wait_stream(gather_stream)
+                pending[0] = out
+            else:
+                gather_outputs(out)
             e1.record(plan.compute)
         return e0, e1
+
+    def flush_pending_gather():
+        """the last deferred gather (every rank issues the same number of gathers)"""
+        if pending[0] is not None:
+            with torch.cuda.stream(plan.compute):
+                gather_outputs(pending[0])
+            pending[0] = None
 
     sampler = ClockSampler(local_rank)
 
@@ -314,6 +343,8 @@ def run_b200_arm(args):
     evs = [one_device_step(args.warmup + i, True) for i in range(args.steps)]
     barrier()
     sampler.stop()
+    flush_pending_gather()
+    barrier()
     dev_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev)
     value = world * B * args.steps / (dev_ms * 1e-3)
 
@@ -321,10 +352,10 @@ def run_b200_arm(args):
     latency = None
     if pipelined:
         for i in range(3):
-            one_device_step(i, False, plan_lat)
+            one_device_step(i, False, plan_lat, False)
         barrier()
         lat_n = min(args.steps, 20)
-        evs_l = [one_device_step(3 + i, True, plan_lat) for i in range(lat_n)]
+        evs_l = [one_device_step(3 + i, True, plan_lat, False) for i in range(lat_n)]
         barrier()
         lat_ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs_l), dev) / lat_n
         latency = {"ms_per_step": lat_ms, "clips_per_s": world * B / (lat_ms * 1e-3), "steps": lat_n,
@@ -468,7 +499,10 @@ def run_b200_arm(args):
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": dict(workload_config(args, world), host_numa_node_rank0=numa_node,
-                           gather=gather_mode, pipeline=pipeline_note),
+                           gather=gather_mode if world == 1 or not (pipelined and not args.inline_gather) else
+                           f"{gather_mode}, one gather per step inside its event pair: the previous step's output, on a "
+                           f"side stream next to this step's replay",
+                           pipeline=pipeline_note),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * T * 88 * 88 * 4,
                     "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -480,7 +514,8 @@ def run_b200_arm(args):
             "gpu_launches_per_step": plan.launches_per_forward,
         }
         line.update(line_extra)
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -501,6 +536,9 @@ def main():
                     help="time the one-batch plan instead of the two-stage software pipeline")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU output gathering inside the step: one-shot peer-memory kernel (default) or NCCL")
+    ap.add_argument("--inline-gather", action="store_true",
+                    help="multi-GPU, pipelined plan: gather each step's output in stream after the replay instead of on a "
+                         "side stream next to the following step's replay")
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -1,2 +1,2 @@
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1u.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_r1u.log
-timeout 300 python bench.py > gpurun_out/bench_r1u.json 2> gpurun_out/bench_r1u.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1u.err; head -c 600 gpurun_out/bench_r1u.json
+N=${1:-2}
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_r1w_n$N.json 2> gpurun_out/bench_r1w_n$N.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r1w_n$N.err; wc -l gpurun_out/bench_r1w_n$N.json; head -c 250 gpurun_out/bench_r1w_n$N.json
