@@ -446,24 +446,38 @@ def run_b200_arm(args):
                               "avg_us": round(per * 1e3, 2), "share": round(a["ms"] / passes / total_ms, 4),
                               "tflops": round(a["flops"] / (per * 1e-3) / 1e12, 1) if a["flops"] else None,
                               "gbs": round(a["bytes"] / (per * 1e-3) / 1e9, 1)})
-        (name, tag), a = rows[0]
-        per_s = a["ms"] / a["launches"] * 1e-3
-        traffic = None
+        traffic_table = {}
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get(f"{name}|{tag}")
+                    traffic_table = json.load(f)
             except Exception:
-                traffic = None
-        if a["flops"]:
-            ach, peak = a["flops"] / per_s / 1e12, float(peaks["bf16_tflops"])
-            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
-        else:
-            ach, peak = a["bytes"] / per_s / 1e9, float(peaks["hbm_gbs"])
-            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
-        roof.update({"traffic": traffic, "kernel": name, "case": tag, "avg_launch_us": per_s * 1e6,
-                     "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json burst figure: kernel timed alone)"})
+                traffic_table = {}
+
+        def roofline_of(row):
+            (name, tag), a = row
+            per_s = a["ms"] / a["launches"] * 1e-3
+            if a["flops"]:
+                ach, peak = a["flops"] / per_s / 1e12, float(peaks["bf16_tflops"])
+                roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+            else:
+                ach, peak = a["bytes"] / per_s / 1e9, float(peaks["hbm_gbs"])
+                roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+            roof.update({"traffic": traffic_table.get(f"{name}|{tag}"), "kernel": name, "case": tag,
+                         "avg_launch_us": per_s * 1e6, "launches_per_step": a["launches"] // passes,
+                         "peak_source": peaks["_source"] + " (MEASURED_PEAKS.json burst figure: kernel timed alone)"})
+            return roof
+
+        roof = roofline_of(rows[0])
+        if pipelined and rows[0][0][0] == "sblk_encoder_stack_fwd":
+            # in the pipelined plan the stack runs on the side stream next to the next batch's prep + stem: the largest
+            # kernel group of the step's critical path is reported as well
+            roof["note"] = ("latency-bound dependent chain (25 GEMM stages on 64 SMs); overlapped with the next batch's "
+                            "clip prep + stem by the pipelined plan, see roofline_critical_path and path")
+            nxt = [r for r in rows if r[0][0] != "sblk_encoder_stack_fwd"]
+            if nxt:
+                line_extra["roofline_critical_path"] = roofline_of(nxt[0])
         fpc = flops_per_clip(T, L)
         path_tf = value / world * fpc / 1e12
         line_extra["roofline"] = roof

@@ -116,6 +116,7 @@ class Encoder(nn.Module):
         self.split_clusters = True   # 8-11 clip groups: 7 as 16-CTA clusters + the rest as 8-CTA clusters, concurrently
         self.stack_cluster_size = 0  # 0 = automatic; 8 / 16 force the cluster size of the one-launch stack (disables the split)
         self._resident_counter = None   # int32 [2] CUDA tensor while runner.PipelinedVisualEncoderPlan captures (ops.gate_wait)
+        self._x16_override = None       # bf16 [N*T, d_input] copy of the input the plan has already made (skips the cast launch)
 
     def __getstate__(self):
         st = self.__dict__.copy()
@@ -123,6 +124,7 @@ class Encoder(nn.Module):
         st["_len_cache"] = {}
         st["_streams"] = {}
         st["_resident_counter"] = None
+        st["_x16_override"] = None
         return st
 
     def __setstate__(self, st):
@@ -135,6 +137,7 @@ class Encoder(nn.Module):
         self.__dict__.setdefault("split_clusters", True)
         self.__dict__.setdefault("stack_cluster_size", 0)
         self.__dict__.setdefault("_resident_counter", None)
+        self.__dict__.setdefault("_x16_override", None)
 
     # ------------------------------------------------------------------------------------------
     def _check_config(self):
@@ -301,7 +304,7 @@ class Encoder(nn.Module):
                 # the whole stack as ONE launch: a cluster per clip group, no inter-group synchronisation
                 stk = pk.stacked
                 scale = 1.0 / self.layer_stack[0].slf_attn.temperature
-                x16 = ops.cast_bf16(x)
+                x16 = self._x16_override if self._x16_override is not None else ops.cast_bf16(x)
                 g_clips = max(1, 128 // t)
                 groups = -(-n // g_clips)
                 if self.split_clusters and self.stack_cluster_size == 0 and 7 < groups <= 11:

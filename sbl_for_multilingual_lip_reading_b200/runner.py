@@ -182,8 +182,13 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         torch.cuda.synchronize(dev)
         self.enc_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.gate = torch.zeros(2, dtype=torch.int32, device=dev)
-        self.feat = [torch.zeros((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev) for _ in range(2)]
-        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap)
+        if getattr(fe, "parallel_chains", 1) != 1:
+            raise RuntimeError("PipelinedVisualEncoderPlan needs frontend.parallel_chains == 1")
+        # features cross the pipeline stages as the bf16 GEMM operand the encoder stack reads (the frontend's last launch
+        # is the cast, so the encoder branch of the next replay is the stack kernel alone); `feat` only carries the shape
+        self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
+        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override)
         try:
             with torch.no_grad():
                 stk = enc._get_packed().stacked
@@ -204,8 +209,9 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                         self.enc_stream.wait_event(fork)
                         with torch.cuda.stream(self.enc_stream):
                             enc._resident_counter = self.gate if self.use_gate else None
-                            self.out[s ^ 1], = enc(self.feat[s ^ 1], self.lengths)
-                            enc._resident_counter = None
+                            enc._x16_override = self.feat16[s ^ 1]
+                            self.out[s ^ 1], = enc(self.feat, self.lengths)
+                            enc._resident_counter = enc._x16_override = None
                             done.record(self.enc_stream)
                         if self.use_gate:
                             ops.gate_wait(self.gate, enc_ctas, self.gate_timeout_us)
@@ -216,11 +222,11 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                         else:
                             f = fe(self.x[s])
                         fe._overlap = None
-                        self.feat[s].copy_(f)
+                        ops.cast_bf16(f.view(self.n * self.t, fe.inputDim), out=self.feat16[s])
                     self.launches_per_forward = ops.launch_count() - before
                     self.graphs[s] = g
         finally:
-            enc.stack_cluster_size, enc._resident_counter, fe._overlap = saved
+            enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override = saved
         torch.cuda.synchronize(dev)
         for ev in self.ev_out + self.ev_done:
             ev.record(torch.cuda.current_stream(dev))
@@ -261,10 +267,10 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         with torch.no_grad(), torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_out[s ^ 1])
             try:
-                enc.stack_cluster_size = int(self.enc_cluster)
-                out, = enc(self.feat[s], self.lengths)
+                enc.stack_cluster_size, enc._x16_override = int(self.enc_cluster), self.feat16[s]
+                out, = enc(self.feat, self.lengths)
             finally:
-                enc.stack_cluster_size = saved
+                enc.stack_cluster_size, enc._x16_override = saved, None
             if out_host is not None:
                 out_host.copy_(out, non_blocking=True)
         return out
