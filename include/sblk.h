@@ -115,6 +115,11 @@ int sblk_conv2d_dual_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, co
 /* bf16 NHWC [F,HW,C] -> mean over HW: fp32 [F,C] and/or bf16 [F,C] (either may be NULL).
  * replaces: nn.AdaptiveAvgPool2d(1) + view, transformer/video_frontend.py:87-88 */
 int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);
+/* Same, times a per-element fp32 factor scale[F,C] (NULL = none): the always-on F.dropout(x, p=0.5) of
+ * Lipreading.forward (transformer/video_frontend.py:122) applied in the pooling pass, with the factor (mask / (1-p))
+ * drawn ahead of time by the caller; bit-identical to pooling followed by that dropout. */
+int sblk_avgpool_scale_fwd(const void* x_bf16, const float* scale, float* out_f32, void* out_bf16, int F, int HW, int C,
+                           void* stream);
 
 /* ---- transformer encoder -------------------------------------------------------------------------- */
 /* out = act(A[M,K] * W[N,K]^T + bias (+ residual_bf16)); bf16 operands, fp32 accumulate; writes bf16 and/or fp32.

@@ -55,6 +55,7 @@ SIGNATURES = {
     "sblk_conv2d_dual_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                         _vp]),
     "sblk_avgpool_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sblk_avgpool_scale_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "sblk_gemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "sblk_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

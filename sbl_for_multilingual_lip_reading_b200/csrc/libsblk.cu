@@ -824,15 +824,23 @@ int sblk_gemm_splitk_fwd(const void* a, const void* w, const float* bias, float*
   return gemm_impl(a, w, bias, nullptr, nullptr, out_partials, M, N, K, 0, splits, stream, "sblk_gemm_splitk_fwd");
 }
 
-int sblk_avgpool_fwd(const void* x, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream) {
+int sblk_avgpool_scale_fwd(const void* x, const float* scale, float* out_f32, void* out_bf16, int F, int HW, int C,
+                           void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || (!out_f32 && !out_bf16)) return fail(-1, "sblk_avgpool_fwd: null pointer");
   if (F <= 0 || HW <= 0 || C <= 0 || (C & 1)) return fail(-1, "sblk_avgpool_fwd: bad shape F=%d HW=%d C=%d", F, HW, C);
+  if ((reinterpret_cast<uintptr_t>(x) & 3u) || (scale && (reinterpret_cast<uintptr_t>(scale) & 7u)) ||
+      (out_f32 && (reinterpret_cast<uintptr_t>(out_f32) & 7u)) || (reinterpret_cast<uintptr_t>(out_bf16) & 3u))
+    return fail(-1, "sblk_avgpool_fwd: misaligned pointer");
   const long long items = static_cast<long long>(F) * (C / 2);
   return launch(sblk::avgpool_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "avgpool_kernel", static_cast<const __nv_bfloat16*>(x),
+                static_cast<cudaStream_t>(stream), false, "avgpool_kernel", static_cast<const __nv_bfloat16*>(x), scale,
                 out_f32, static_cast<__nv_bfloat16*>(out_bf16), F, HW, C);
+}
+
+int sblk_avgpool_fwd(const void* x, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream) {
+  return sblk_avgpool_scale_fwd(x, nullptr, out_f32, out_bf16, F, HW, C, stream);
 }
 
 int sblk_sum_layernorm_fwd(const float* x_parts, int nparts, const float* bias, const float* residual,

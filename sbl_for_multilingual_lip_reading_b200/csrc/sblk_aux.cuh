@@ -295,12 +295,14 @@ p2p_gather_kernel(const uint4* __restrict__ local, uint4* const* __restrict__ pe
 }
 
 // --------------------------------------------------------------------------------------------
-// Global average pool: bf16 NHWC [F, HW, C] -> fp32 [F, C] (+ optional bf16 copy).
+// Global average pool: bf16 NHWC [F, HW, C] -> fp32 [F, C] (+ optional bf16 copy), optionally times a per-element
+// fp32 factor [F, C] (the always-on dropout of Lipreading.forward, video_frontend.py:122, with its mask * 1/(1-p)
+// drawn ahead of time: mean * (mask * 2) == (mean * mask) * 2 bit for bit).
 // Reference: ResNet.avgpool + view, SBL/transformer/video_frontend.py:87-88.
 // One thread per (frame, channel pair).
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out_f32,
+avgpool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, float* __restrict__ out_f32,
                __nv_bfloat16* __restrict__ out_bf16, int F, int HW, int C) {
   const int C2 = C >> 1;
   const long long total = static_cast<long long>(F) * C2;
@@ -318,6 +320,11 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out_f32,
     }
     a *= inv;
     b *= inv;
+    if (scale != nullptr) {
+      const float2 m = __ldg(reinterpret_cast<const float2*>(scale) + i);
+      a *= m.x;
+      b *= m.y;
+    }
     if (out_f32 != nullptr) reinterpret_cast<float2*>(out_f32)[i] = make_float2(a, b);
     if (out_bf16 != nullptr) reinterpret_cast<uint32_t*>(out_bf16)[i] = pack_bf16x2(a, b);
   }

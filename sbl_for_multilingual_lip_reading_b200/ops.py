@@ -339,16 +339,20 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     return out
 
 
-def avgpool(x, want_f32=True, want_bf16=False, out_f32=None):
-    _req(x, BF16, "x"); _req(out_f32, F32, "out_f32")
+def avgpool(x, want_f32=True, want_bf16=False, out_f32=None, out_bf16=None, scale=None):
+    """bf16 NHWC [F, ..., C] -> (fp32 [F, C] | None, bf16 [F, C] | None) mean over the pixels, optionally times the
+    fp32 factor `scale` [F, C] (dropout mask / (1 - p) drawn ahead of time)."""
+    _req(x, BF16, "x"); _req(out_f32, F32, "out_f32"); _req(out_bf16, BF16, "out_bf16"); _req(scale, F32, "scale")
     f, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (f * c)
-    if out_f32 is not None and tuple(out_f32.shape) != (f, c):
-        raise RuntimeError(f"avgpool: out_f32 shape {tuple(out_f32.shape)} != {(f, c)}")
+    for name, t_ in (("out_f32", out_f32), ("out_bf16", out_bf16), ("scale", scale)):
+        if t_ is not None and t_.numel() != f * c:
+            raise RuntimeError(f"avgpool: {name} has {t_.numel()} elements, expected {f * c}")
     o32 = out_f32 if out_f32 is not None else (torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None)
-    o16 = torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None
-    _call("sblk_avgpool_fwd", f"avgpool HW={hw} C={c}", 0, 2 * x.numel() + (4 if want_f32 else 0) * f * c +
-          (2 if want_bf16 else 0) * f * c, _p(x), _p(o32), _p(o16), f, hw, c, _stream())
+    o16 = out_bf16 if out_bf16 is not None else (torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None)
+    _call("sblk_avgpool_scale_fwd", f"avgpool HW={hw} C={c}", 0, 2 * x.numel() + (4 if o32 is not None else 0) * f * c +
+          (2 if o16 is not None else 0) * f * c + (4 if scale is not None else 0) * f * c,
+          _p(x), _p(scale), _p(o32), _p(o16), f, hw, c, _stream())
     return o32, o16
 
 

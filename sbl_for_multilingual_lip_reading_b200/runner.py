@@ -184,11 +184,13 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         self.gate = torch.zeros(2, dtype=torch.int32, device=dev)
         if getattr(fe, "parallel_chains", 1) != 1:
             raise RuntimeError("PipelinedVisualEncoderPlan needs frontend.parallel_chains == 1")
-        # features cross the pipeline stages as the bf16 GEMM operand the encoder stack reads (the frontend's last launch
-        # is the cast, so the encoder branch of the next replay is the stack kernel alone); `feat` only carries the shape
+        # features cross the pipeline stages as the bf16 GEMM operand the encoder stack reads (written by the frontend's
+        # last launch — average pool x dropout factor — so the encoder branch of the next replay is the stack kernel
+        # alone); `feat` only carries the shape
         self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=torch.bfloat16, device=dev) for _ in range(2)]
         self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
-        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override)
+        self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
+        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail)
         try:
             with torch.no_grad():
                 stk = enc._get_packed().stacked
@@ -215,18 +217,23 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                             done.record(self.enc_stream)
                         if self.use_gate:
                             ops.gate_wait(self.gate, enc_ctas, self.gate_timeout_us)
+                        # the always-on dropout of Lipreading.forward (reference :122): its factor mask / (1 - p) is drawn
+                        # here, in front of the (non-critical) head, and applied by the pooling launch that ends the trunk
+                        scale = (torch.nn.functional.dropout(self._ones, p=0.5)
+                                 if getattr(fe, "always_on_dropout", True) else None)
+                        fe._tail = (scale, self.feat16[s])
                         fe._overlap = (self.head_sm_limit, self.head_blocks, lambda: main.wait_event(done))
                         if self.u8_input is not None:
                             _, h0, w0 = self.u8_input
                             f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
                         else:
                             f = fe(self.x[s])
-                        fe._overlap = None
-                        ops.cast_bf16(f.view(self.n * self.t, fe.inputDim), out=self.feat16[s])
+                        fe._overlap = fe._tail = None
+                        del f   # unwritten: the pooling launch wrote the bf16 features into feat16[s]
                     self.launches_per_forward = ops.launch_count() - before
                     self.graphs[s] = g
         finally:
-            enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override = saved
+            enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail = saved
         torch.cuda.synchronize(dev)
         for ev in self.ev_out + self.ev_done:
             ev.record(torch.cuda.current_stream(dev))

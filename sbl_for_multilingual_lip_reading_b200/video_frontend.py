@@ -126,6 +126,10 @@ class Lipreading(nn.Module):
         # kernel chain (the previous batch's encoder stack) co-runs on the other SMs; `join()` is called once the head
         # is enqueued and makes the current stream wait for that chain before the full-width kernels start
         self._overlap = None
+        # (scale | None, out_bf16) set by the same plan: the average pool writes mean * scale as bf16 straight into the
+        # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
+        # dropout of forward() moved off the critical path (bit-identical) — and forward() skips its own dropout
+        self._tail = None
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
@@ -136,6 +140,7 @@ class Lipreading(nn.Module):
         st["_lut"] = {}
         st["l2_prefetch_extra"] = None
         st["_overlap"] = None
+        st["_tail"] = None
         return st
 
     def __setstate__(self, st):
@@ -148,6 +153,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("l2_prefetch", True)
         self.__dict__.setdefault("l2_prefetch_extra", None)
         self.__dict__.setdefault("_overlap", None)
+        self.__dict__.setdefault("_tail", None)
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -293,7 +299,11 @@ class Lipreading(nn.Module):
             a = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=res)
         if ov is not None and ov[1] >= len(pk.blocks):
             end_head()
-        ops.avgpool(a, out_f32=feat_out)
+        tail = self._tail if chain == 0 else None
+        if tail is not None:
+            ops.avgpool(a, want_f32=False, out_bf16=tail[1], scale=tail[0])   # feat_out stays unwritten (plan-owned path)
+        else:
+            ops.avgpool(a, out_f32=feat_out)
         if pf_stream is not None:   # join (graph capture needs every forked stream back; no data dependency)
             ev = torch.cuda.Event()
             ev.record(pf_stream)
@@ -379,7 +389,7 @@ class Lipreading(nn.Module):
             return ops.prep_clip_u8(xs, lut, t_out, crop)
 
         feat = self._frontend_forward(x_u8, prep=prep, frames=t_out)
-        if self.always_on_dropout:
+        if self.always_on_dropout and self._tail is None:
             feat = F.dropout(feat, p=0.5)  # functional default training=True, exactly as reference :122
         return feat.view(-1, t_out, self.inputDim)
 
@@ -387,7 +397,7 @@ class Lipreading(nn.Module):
         """reference :119-125."""
         frameLen = x.size(2)
         feat = self._frontend_forward(x)
-        if self.always_on_dropout:
+        if self.always_on_dropout and self._tail is None:
             feat = F.dropout(feat, p=0.5)  # functional default training=True, exactly as reference :122
         return feat.view(-1, frameLen, self.inputDim)
 

@@ -431,6 +431,62 @@ def test_pipelined_plan_is_bit_identical_to_eager_modules(frontend, encoder6, de
     assert encoder6.stack_cluster_size == 0 and encoder6._resident_counter is None and frontend._overlap is None
 
 
+def test_avgpool_with_dropout_factor_matches_pool_then_dropout(dev):
+    """sblk_avgpool_scale_fwd: pooling times the pre-drawn dropout factor (F.dropout(ones) under the same seed draws the
+    same Philox mask as F.dropout(features)) is bit-identical to pooling followed by the reference's always-on
+    F.dropout(x, p=0.5) (video_frontend.py:122), in fp32 and in the bf16 copy the encoder reads."""
+    import torch.nn.functional as F
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(928, 3, 3, 512, generator=g).to(torch.bfloat16).to(dev)
+    pooled, _ = ops.avgpool(x)
+    torch.manual_seed(5)
+    want = F.dropout(pooled, p=0.5)
+    torch.manual_seed(5)
+    scale = F.dropout(torch.ones_like(pooled), p=0.5)
+    got32, got16 = ops.avgpool(x, want_f32=True, want_bf16=True, scale=scale)
+    torch.cuda.synchronize(dev)
+    assert 0.4 < (want == 0).float().mean().item() < 0.6
+    assert torch.equal(got32, want)
+    assert torch.equal(got16, ops.cast_bf16(want))
+    with pytest.raises(RuntimeError):
+        ops.avgpool(x, scale=scale[:10])
+
+
+def test_pipelined_plan_draws_a_fresh_dropout_mask_every_replay(encoder6, dev):
+    """With the reference's always-on dropout enabled the pipelined plan must still apply it (a new mask per replay,
+    about half of the features zeroed): same clip batch three times -> three different finite outputs, all different
+    from the dropout-free output."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.runner import PipelinedVisualEncoderPlan
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading
+    fe = Lipreading()
+    fe.load_state_dict(synth.frontend_state_dict(1))
+    fe = fe.to(dev).eval()
+    assert fe.always_on_dropout
+    x = synth.synthetic_clips(4, 29, seed=9).to(dev)
+    plan = PipelinedVisualEncoderPlan(fe, encoder6, 4, 29, device=dev)
+    outs = []
+    try:
+        with torch.cuda.stream(plan.compute):
+            for i in range(4):
+                plan.x[i % 2].copy_(x)
+                prev = plan.forward_device(i % 2)
+                if i > 0:
+                    outs.append(prev.clone())
+            zero_frac = (plan.feat16[0] == 0).float().mean().item()
+        plan.compute.synchronize()
+    finally:
+        plan.close()
+    fe.always_on_dropout = False
+    with torch.no_grad():
+        clean, = encoder6(fe(x), [29] * 4)
+    assert 0.45 < zero_frac < 0.55
+    for o in outs:
+        assert torch.isfinite(o).all() and not torch.equal(o, clean)
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+
+
 def test_gate_wait_times_out_and_rejects_bad_arguments(dev):
     """sblk_gate_wait is a scheduling hint: with nobody bumping the counter it must give up after its timeout (not
     hang) and still advance its target word; bad arguments fail loudly."""

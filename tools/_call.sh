@@ -1,3 +1,3 @@
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1x.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_r1x.log
-timeout 300 python bench.py > gpurun_out/bench_r1x.json 2> gpurun_out/bench_r1x.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1x.err; head -c 300 gpurun_out/bench_r1x.json; echo
-timeout 120 python tools/prof_target.py forward 2 > gpurun_out/plain_fwd.log 2>&1 && timeout 300 ncu --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1x.csv python tools/prof_target.py forward 2 > gpurun_out/ncu_fwd.log 2>&1; echo "ncu rc=$?"
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1y.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_r1y.log
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_r1y.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_r1y.log
+timeout 300 python bench.py > gpurun_out/bench_r1y.json 2> gpurun_out/bench_r1y.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1y.err; head -c 300 gpurun_out/bench_r1y.json; echo
