@@ -167,9 +167,15 @@ def run_reference_arm(args):
 
 
 def workload_config(args, world):
+    if (args.batch, args.frames) == (32, 29):
+        name, shape = "BASELINE configs[1]", "LRW-shaped"
+    elif (args.batch, args.frames) == (8, 40):
+        name, shape = "BASELINE configs[2] (batch 64 sharded across 8 B200: 8 clips per GPU)", "LRW-1000-shaped"
+    else:
+        name, shape = "custom shape", "LRW-style"
     return {
-        "workload": (f"BASELINE configs[1]: full visual encoder forward (Conv3d frontend + ResNet-18 trunk + "
-                     f"{args.layers}-layer transformer Encoder), LRW-shaped {args.frames}x88x88 gray clips, "
+        "workload": (f"{name}: full visual encoder forward (Conv3d frontend + ResNet-18 trunk + "
+                     f"{args.layers}-layer transformer Encoder), {shape} {args.frames}x88x88 gray clips, "
                      f"batch {args.batch} per B200"),
         "clips_per_gpu": args.batch, "frames": args.frames, "encoder_layers": args.layers,
         "global_batch": args.batch * world, "parallelism": f"dp{world}",
