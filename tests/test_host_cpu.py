@@ -153,6 +153,23 @@ def test_modules_pickle_roundtrip():
     for k, v in fe.state_dict().items():
         assert torch.equal(v, back["fe"].state_dict()[k])
     assert pickle.loads(pickle.dumps(enc)).n_layers == 2
+    # plan-owned hooks (runner.PipelinedVisualEncoderPlan) never travel with a checkpoint, and modules pickled before
+    # those attributes existed come back with the defaults
+    fe._overlap, fe._tail = (84, 0, None), (None, None)
+    enc._x16_override, enc._resident_counter, enc.stack_cluster_size = object, object, 8
+    fe2, enc2 = pickle.loads(pickle.dumps(fe)), pickle.loads(pickle.dumps(enc))
+    assert fe2._overlap is None and fe2._tail is None
+    assert enc2._x16_override is None and enc2._resident_counter is None and enc2.stack_cluster_size == 8
+    old_fe, old_enc = fe.__getstate__(), enc.__getstate__()
+    for k in ("_overlap", "_tail"):
+        old_fe.pop(k)
+    for k in ("_x16_override", "_resident_counter", "stack_cluster_size", "split_clusters"):
+        old_enc.pop(k)
+    fe3, enc3 = Lipreading.__new__(Lipreading), Encoder.__new__(Encoder)
+    fe3.__setstate__(old_fe); enc3.__setstate__(old_enc)
+    assert fe3._overlap is None and fe3._tail is None
+    assert enc3._x16_override is None and enc3.stack_cluster_size == 0 and enc3.split_clusters is True
+    fe._overlap = fe._tail = None
 
 
 def test_cpu_input_is_rejected_loudly():
