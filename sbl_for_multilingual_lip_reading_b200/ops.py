@@ -193,6 +193,16 @@ def flat_rows(f, h, w):
     return int(_lib.load().sblk_flat_rows(f, h, w))
 
 
+def flat_frames(x, f0, f1):
+    """Frames [f0, f1) of FlatActs `x` as FlatActs over a row slice of the same storage.  The layout is linear in the
+    frame index and consecutive frames share one zero halo row, so the slice is itself a valid zero-haloed flat buffer
+    (its first / last rows are the halo rows in front of frames f0 / f1)."""
+    if not 0 <= f0 < f1 <= x.f:
+        raise RuntimeError(f"flat_frames: bad frame range [{f0}, {f1}) of {x.f}")
+    r0 = f0 * (x.h + 1) * (x.w + 2)
+    return FlatActs(x.data[r0:r0 + ((f1 - f0) * (x.h + 1) + 1) * (x.w + 2)], f1 - f0, x.h, x.w)
+
+
 def prep_clip_u8(x_u8, lut, t_out=None, crop=(4, 4), out=None):
     """Raw uint8 gray frames [N,T_in,H0,W0] -> (prepped bf16 clip, N, T_out) for conv3d_bn_relu_pool, fusing the reference
     loader's /255, ColorNormalize, 88x88 crop and frame zero-padding (data_gen.py:122-125,276-296).  `lut`: bf16 [256]

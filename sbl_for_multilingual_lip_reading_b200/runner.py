@@ -149,7 +149,11 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
     finishes the last one."""
 
     def __init__(self, frontend, encoder, n, t, device=None, pdl=True, lengths=None, u8_input=None,
-                 head_sm_limit=None, head_blocks=None, gate=True, gate_timeout_us=300, enc_cluster=None):
+                 head_sm_limit=None, head_blocks=None, gate=True, gate_timeout_us=300, enc_cluster=None,
+                 head_frac=None):
+        # head_frac: fraction of the frames of the first conv after the head that still runs inside the head (limited
+        # width) — fills the time by which the encoder outlasts prep + stem; None = automatic, 0 = off
+        self.head_frac = head_frac
         # head_blocks: residual blocks (after prep + stem) that run next to the encoder on `head_sm_limit` SMs; None =
         # automatic (see _capture).  enc_cluster: CTAs per encoder cluster (8 or 16), None = 8.
         self.enc_cluster = enc_cluster
@@ -179,6 +183,11 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
             # pipeline_probe.py); small latency-bound batches: the whole frontend co-runs with it
             self.head_blocks = 0 if self.n * self.t > 512 else 8
         self.head_blocks = int(self.head_blocks)
+        if self.head_frac is None:
+            # measured at the BASELINE batch (tools/exp/pipeline_probe.py): 708.6 us (0) / 704.5 (0.3) / 700.4 (0.4) /
+            # 698.4 (0.5) / 698.4 (0.6) per step; the encoder outlasts prep + stem on 84 SMs by ~35 us
+            self.head_frac = 0.5 if self.head_blocks == 0 else 0.0
+        self.head_frac = float(self.head_frac)
         torch.cuda.synchronize(dev)
         self.enc_stream = torch.cuda.Stream(device=dev, priority=-1)
         self.gate = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -222,7 +231,8 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                         scale = (torch.nn.functional.dropout(self._ones, p=0.5)
                                  if getattr(fe, "always_on_dropout", True) else None)
                         fe._tail = (scale, self.feat16[s])
-                        fe._overlap = (self.head_sm_limit, self.head_blocks, lambda: main.wait_event(done))
+                        fe._overlap = (self.head_sm_limit, self.head_blocks, lambda: main.wait_event(done),
+                                       self.head_frac)
                         if self.u8_input is not None:
                             _, h0, w0 = self.u8_input
                             f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))

@@ -121,7 +121,7 @@ class Lipreading(nn.Module):
         # layer 4 starts
         self.l2_prefetch = True
         self.l2_prefetch_extra = None
-        # (sm_limit, head_blocks, join) set by runner.PipelinedVisualEncoderPlan while it captures: the clip prep, the stem
+        # (sm_limit, head_blocks, join[, head_frac]) set by runner.PipelinedVisualEncoderPlan while it captures: the clip prep, the stem
         # and the first `head_blocks` residual blocks size their persistent grids for `sm_limit` SMs because another
         # kernel chain (the previous batch's encoder stack) co-runs on the other SMs; `join()` is called once the head
         # is enqueued and makes the current stream wait for that chain before the full-width kernels start
@@ -261,7 +261,16 @@ class Lipreading(nn.Module):
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
         pf_stream = None
         for bi, (stride, w1, b1, w2, b2, ds) in enumerate(pk.blocks):
+            split = 0
             if ov is not None and bi == ov[1]:
+                # head_frac > 0: the first conv of this block is run in two frame ranges — the first one still inside
+                # the head (limited width, next to the other chain), the rest at full width — to use the time by which
+                # the other chain outlasts the head.  Frame ranges of the flat layout are independent (ops.flat_frames).
+                if len(ov) > 3 and ov[3] > 0 and isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
+                    split = min(a.f - 1, max(1, int(round(a.f * float(ov[3])))))
+                    y = ops.FlatActs(torch.empty_like(a.data), a.f, a.h, a.w)
+                    ops.conv3x3_flat(ops.flat_frames(a, 0, split), w1, b1, relu=True,
+                                     out=ops.flat_frames(y, 0, split).data)
                 end_head()
             if self.l2_prefetch and chain == 0 and bi in (0, 4, 6):
                 # Weights of the layers still to come are pulled into L2 by a tiny kernel on a side stream while the
@@ -284,7 +293,11 @@ class Lipreading(nn.Module):
                     with torch.cuda.stream(pf_stream):
                         ops.l2_prefetch(tensors)
             if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
-                y = ops.conv3x3_flat(a, w1, b1, relu=True)
+                if split:
+                    ops.conv3x3_flat(ops.flat_frames(a, split, a.f), w1, b1, relu=True,
+                                     out=ops.flat_frames(y, split, a.f).data)
+                else:
+                    y = ops.conv3x3_flat(a, w1, b1, relu=True)
                 a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
                 continue
             if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input

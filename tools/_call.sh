@@ -1,1 +1,3 @@
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 8 --steps 30 --warmup 5 --batch 8 --frames 40 > gpurun_out/bench_r1y_c3_n8.json 2> gpurun_out/bench_r1y_c3_n8.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r1y_c3_n8.err; head -c 300 gpurun_out/bench_r1y_c3_n8.json
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1z.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_r1z.log
+timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_r1z.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_r1z.log
+timeout 300 python bench.py > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1z.err; head -c 300 gpurun_out/bench_r1z.json; echo
