@@ -1,3 +1,2 @@
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r1z.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_r1z.log
-timeout 120 python __graft_entry__.py smoke > gpurun_out/smoke_r1z.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_r1z.log
-timeout 300 python bench.py > gpurun_out/bench_r1z.json 2> gpurun_out/bench_r1z.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_r1z.err; head -c 300 gpurun_out/bench_r1z.json; echo
+N=${1:-2}
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_r1z_n$N.json 2> gpurun_out/bench_r1z_n$N.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r1z_n$N.err; wc -l gpurun_out/bench_r1z_n$N.json; head -c 250 gpurun_out/bench_r1z_n$N.json
