@@ -191,3 +191,33 @@ def test_training_mode_is_rejected():
     fe = Lipreading().train()
     with pytest.raises(RuntimeError, match="training-mode"):
         fe(torch.zeros(1, 1, 2, 88, 88))
+
+
+def test_flat_frames_is_a_valid_flat_sub_buffer():
+    """ops.flat_frames (used to run a frame range of a flat conv inside the pipelined plan's head): frames [f0, f1) of the
+    zero-haloed flat layout are a row slice of the same storage that is itself a valid flat buffer — same pixels, halo
+    rows zero, size sblk_flat_rows(f1 - f0, H, W) — and the slices of a partition cover every row."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    f, h, w, c = 7, 5, 6, 8
+    rows = ops.flat_rows(f, h, w)
+    assert rows == (f * (h + 1) + 1) * (w + 2)
+    data = torch.zeros(rows, c)
+    dense = torch.randn(f, h, w, c)
+    v = data[(w + 2):(w + 2) + f * (h + 1) * (w + 2)].view(f, h + 1, w + 2, c)
+    v[:, :h, 1:w + 1, :] = dense
+    x = ops.FlatActs(data, f, h, w)
+    assert torch.equal(x.dense(), dense)
+    covered = torch.zeros(rows, dtype=torch.bool)
+    for f0, f1 in ((0, 3), (3, 4), (4, 7)):
+        sub = ops.flat_frames(x, f0, f1)
+        assert sub.data.shape[0] == ops.flat_rows(f1 - f0, h, w) and sub.data.is_contiguous()
+        assert sub.data.data_ptr() == data.data_ptr() + f0 * (h + 1) * (w + 2) * c * 4
+        assert torch.equal(sub.dense(), dense[f0:f1])
+        assert not sub.data[:w + 2].any() and not sub.data[-(w + 2):].any()   # halo rows in front of frames f0 / f1
+        r0 = f0 * (h + 1) * (w + 2)
+        covered[r0:r0 + sub.data.shape[0]] = True
+    assert covered.all()
+    with pytest.raises(RuntimeError):
+        ops.flat_frames(x, 3, 3)
+    with pytest.raises(RuntimeError):
+        ops.flat_frames(x, 0, 8)
