@@ -487,6 +487,31 @@ def test_pipelined_plan_draws_a_fresh_dropout_mask_every_replay(encoder6, dev):
     assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
 
 
+@pytest.mark.parametrize("c,h", [(64, 22), (128, 11)])
+def test_flat_conv_over_frame_ranges_is_bit_identical(dev, c, h):
+    """A flat 3x3 conv issued over frame ranges (ops.flat_frames; the pipelined plan runs half of layer1.0.conv1's frames
+    inside its head) writes exactly the bits of the whole-buffer launch, halo rows included, with and without residual."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    f = 61
+    rows = ops.flat_rows(f, h, h)
+    data = torch.zeros(rows, c, dtype=torch.bfloat16, device=dev)
+    v = data[(h + 2):(h + 2) + f * (h + 1) * (h + 2)].view(f, h + 1, h + 2, c)
+    v[:, :h, 1:h + 1, :] = torch.randn(f, h, h, c, generator=g).to(torch.bfloat16).to(dev)
+    x = ops.FlatActs(data, f, h, h)
+    w = ops.pack_flat_weight((torch.randn(c, 3, 3, c, generator=g) / (9 * c) ** 0.5).to(torch.bfloat16).to(dev))
+    bias = torch.randn(c, generator=g).to(dev)
+    for res in (None, x):
+        whole = ops.conv3x3_flat(x, w, bias, relu=True, residual=res)
+        parts = torch.full_like(data, float("nan"))
+        for f0, f1 in ((0, 17), (17, 18), (18, f)):
+            ops.conv3x3_flat(ops.flat_frames(x, f0, f1), w, bias, relu=True,
+                             residual=None if res is None else ops.flat_frames(res, f0, f1),
+                             out=ops.flat_frames(ops.FlatActs(parts, f, h, h), f0, f1).data)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(parts, whole.data)
+
+
 def test_gate_wait_times_out_and_rejects_bad_arguments(dev):
     """sblk_gate_wait is a scheduling hint: with nobody bumping the counter it must give up after its timeout (not
     hang) and still advance its target word; bad arguments fail loudly."""
