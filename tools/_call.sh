@@ -1,2 +1,3 @@
-N=${1:-2}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/bench_r1z_n$N.json 2> gpurun_out/bench_r1z_n$N.err; echo "bench rc=$?"; tail -2 gpurun_out/bench_r1z_n$N.err; wc -l gpurun_out/bench_r1z_n$N.json; head -c 250 gpurun_out/bench_r1z_n$N.json
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu_final.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/smoke_final.log
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; head -c 260 gpurun_out/bench_final.json; echo
