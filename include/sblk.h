@@ -9,7 +9,12 @@
  *   - return 0 = OK, < 0 = argument / shape / alignment error (unsupported configurations fail loudly,
  *     there is no CPU or library fallback), > 0 = cudaError_t of the failed launch
  *   - sblk_last_error() returns a thread-local description of the last failure
- *   - activations are bf16 NHWC / row-major, accumulation and normalisation are fp32
+ *   - convolutional activations / weights are bf16 (NHWC / K-major); the transformer encoder's 16-bit operands
+ *     ("enc16": x_in, every encoder weight, the qkv / attention / hidden workspaces) are IEEE fp16 when
+ *     sblk_enc16_format() == 1 (default build) and bf16 when it is 0 — same bytes, same tcgen05 kind::f16 rate,
+ *     3 more mantissa bits for LayerNorm-bounded values; accumulation, normalisation and the residual stream are fp32.
+ *     Parameters documented as "bf16" in the encoder section below mean "enc16".
+ *   - sblk_set_pdl / sblk_set_sm_limit are per calling host thread (nn.DataParallel replicas launch from worker threads)
  */
 #ifndef SBLK_H_
 #define SBLK_H_
@@ -18,7 +23,7 @@
 extern "C" {
 #endif
 
-#define SBLK_VERSION 100
+#define SBLK_VERSION 200
 
 int sblk_version(void);
 const char* sblk_last_error(void);
@@ -26,7 +31,8 @@ const char* sblk_last_error(void);
 int sblk_init(void);
 /* Device-side pipeline watchdog word (0 = never fired); survives a trapped launch. */
 unsigned int sblk_watchdog_code(void);
-/* Enable (1) / disable (0) programmatic dependent launch between consecutive kernels. Returns previous value. */
+/* Enable (1) / disable (0) programmatic dependent launch for the CALLING THREAD's subsequent launches (a CUDA graph
+ * keeps whatever was set while it was captured).  Returns the previous value. */
 int sblk_set_pdl(int enable);
 /* Size the persistent grids of the calling thread's subsequent launches for at most max_sms SMs (rounded down to an
  * even count; 0 = all SMs).  Used to run independent kernel chains (halves of a clip batch) concurrently on disjoint
@@ -48,6 +54,10 @@ int sblk_pack_conv2d(const float* w, const float* gamma, const float* beta, cons
                      float eps, void* w_packed_bf16, float* bias, int Co, int Ci, int R, int S, void* stream);
 /* fp32 -> bf16 cast of n elements (n % 4 == 0). Linear weights [out,in] are already K-major. */
 int sblk_cast_f32_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* 16-bit operand format of the transformer-encoder entry points: 1 = IEEE fp16 (default), 0 = bf16. */
+int sblk_enc16_format(void);
+/* fp32 -> enc16 cast of n elements (n % 4 == 0; fp16 conversions saturate at +-65504): encoder weights and inputs. */
+int sblk_cast_f32_enc16(const float* src, void* dst_enc16, long long n, void* stream);
 /* Hint: pull the n ranges [ptrs[i], ptrs[i] + bytes[i]) into L2 (prefetch.global.L2 per 128-byte line; no data is
  * produced; ptrs / bytes are HOST arrays).  Used on a side stream for the packed weights of the layers that run later in
  * the same forward. */
@@ -117,9 +127,10 @@ int sblk_conv2d_dual_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, co
 int sblk_avgpool_fwd(const void* x_bf16, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream);
 /* Same, times a per-element fp32 factor scale[F,C] (NULL = none): the always-on F.dropout(x, p=0.5) of
  * Lipreading.forward (transformer/video_frontend.py:122) applied in the pooling pass, with the factor (mask / (1-p))
- * drawn ahead of time by the caller; bit-identical to pooling followed by that dropout. */
-int sblk_avgpool_scale_fwd(const void* x_bf16, const float* scale, float* out_f32, void* out_bf16, int F, int HW, int C,
-                           void* stream);
+ * drawn ahead of time by the caller; bit-identical to pooling followed by that dropout.  out16_enc != 0 writes the
+ * 16-bit output in the encoder's operand format (it is then x_in of sblk_encoder_stack_fwd) instead of bf16. */
+int sblk_avgpool_scale_fwd(const void* x_bf16, const float* scale, float* out_f32, void* out_16, int F, int HW, int C,
+                           int out16_enc, void* stream);
 
 /* ---- transformer encoder -------------------------------------------------------------------------- */
 /* out = act(A[M,K] * W[N,K]^T + bias (+ residual_bf16)); bf16 operands, fp32 accumulate; writes bf16 and/or fp32.
@@ -220,6 +231,8 @@ typedef struct sblk_encoder_stack_args {
                        * (start, end) globaltimer ns of every cluster (profiling aid) */
   void* resident_counter; /* NULL, or device uint32[2] (zero-initialised once): every CTA adds 1 to word 0 when it starts
                            * running, i.e. when its cluster owns its SMs (see sblk_gate_wait) */
+  int no_multicast;   /* 0 = activation tiles are loaded once per cluster and TMA-multicast (default); 1 = every CTA loads
+                       * its own copy (bit-identical; A/B timing and tests) */
 } sblk_encoder_stack_args;
 long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
 int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);

@@ -28,7 +28,8 @@ class EncoderStackArgs(ctypes.Structure):
         "x_in", "w_in", "b_in", "ln_in_gamma", "ln_in_beta", "pe", "w_heads", "b_heads", "w_fc", "b_fc", "ln1_gamma",
         "ln1_beta", "w_1", "b_1", "w_2", "b_2", "ln2_gamma", "ln2_beta", "lengths", "out", "workspace")] +
         [(n, _i) for n in ("N", "T", "n_layers", "n_head", "d_k", "d_model", "d_in", "d_inner")] +
-        [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp), ("resident_counter", _vp)])
+        [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp), ("resident_counter", _vp),
+         ("no_multicast", _i)])
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).
@@ -43,6 +44,8 @@ SIGNATURES = {
     "sblk_pack_conv3d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "sblk_pack_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_cast_f32_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    "sblk_enc16_format": (_i, []),
+    "sblk_cast_f32_enc16": (_i, [_vp, _vp, _ll, _vp]),
     "sblk_l2_prefetch": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_ll), _i, _vp]),
     "sblk_gate_wait": (_i, [_vp, _i, _i, _vp]),
     "sblk_prep_clip_elems": (_ll, [_i, _i]),
@@ -55,7 +58,7 @@ SIGNATURES = {
     "sblk_conv2d_dual_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                         _vp]),
     "sblk_avgpool_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
-    "sblk_avgpool_scale_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sblk_avgpool_scale_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_gemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_add_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "sblk_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp]),

@@ -15,7 +15,9 @@
 #include "sblk_igemm.cuh"
 #include "sblk_igemm2.cuh"
 #include "sblk_conv3d.cuh"
-#include "sblk_flatconv.cuh"
+#ifdef SBLK_DEBUG
+#include "sblk_flatconv.cuh"   // v1 single-CTA flat conv: A/B timing baseline only (SBLK_FLATCONV2=0)
+#endif
 #include "sblk_flatconv2.cuh"
 #include "sblk_aux.cuh"
 #include "sblk_attention.cuh"
@@ -27,8 +29,18 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-std::atomic<int> g_pdl{0};
+// Launch settings are per HOST THREAD (nn.DataParallel replicas launch from worker threads): a plan that
+// captures with PDL on, or sizes grids for a co-running chain, never changes what another thread's launches do.
+thread_local int g_pdl = 0;        // != 0: launches carry the programmatic-dependent-launch attribute
 thread_local int g_sm_limit = 0;   // > 0: size persistent grids for at most this many SMs (concurrent kernel chains)
+
+// Tuning / profiling switches read from the environment exist only in -DSBLK_DEBUG builds (tools/, experiments): the
+// release library never calls getenv and cannot be steered into its timing-experiment modes.
+#ifdef SBLK_DEBUG
+inline const char* dbg_env(const char* name) { return getenv(name); }
+#else
+inline const char* dbg_env(const char*) { return nullptr; }
+#endif
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -122,7 +134,9 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
+#ifdef SBLK_DEBUG
     if ((rc = set_smem(sblk::flatconv3x3_c64_kernel, sblk::fc::SMEM_BYTES))) return rc;
+#endif
     if ((rc = set_smem(sblk::flatconv2_kernel<1>, sblk::Fc2Cfg<1>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::flatconv2_kernel<2>, sblk::Fc2Cfg<2>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::gemm_ln512_kernel, sblk::gln::SMEM_BYTES))) return rc;
@@ -161,7 +175,7 @@ int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStr
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   int nattr = 0;
-  if (pdl_capable && g_pdl.load(std::memory_order_relaxed) != 0) {
+  if (pdl_capable && g_pdl != 0) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     nattr = 1;
@@ -192,7 +206,7 @@ template <bool IM2COL>
 int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::IgemmParams p, int num_sms,
                  cudaStream_t stream) {
   {
-    const char* dm = getenv("SBLK_IGEMM_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    const char* dm = dbg_env("SBLK_IGEMM_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
     p.debug_mode = dm ? atoi(dm) : 0;
   }
   const int m_tiles = (p.M + 127) / 128;
@@ -215,7 +229,7 @@ int launch_igemm(int bn, const CUtensorMap& tmA, const CUtensorMap& tmB, sblk::I
 
 // SBLK_CTA_PAIRS=0 routes every conv through the 1-CTA kernel (A/B timing experiments); default on.
 bool use_cta_pairs() {
-  const char* e = getenv("SBLK_CTA_PAIRS");
+  const char* e = dbg_env("SBLK_CTA_PAIRS");
   return e == nullptr || atoi(e) != 0;
 }
 
@@ -248,7 +262,11 @@ unsigned int sblk_watchdog_code(void) {
   return g_dev[dev].wd_host ? *reinterpret_cast<volatile unsigned int*>(g_dev[dev].wd_host) : 0u;
 }
 
-int sblk_set_pdl(int enable) { return g_pdl.exchange(enable ? 1 : 0); }
+int sblk_set_pdl(int enable) {
+  const int prev = g_pdl;
+  g_pdl = enable ? 1 : 0;
+  return prev;
+}
 int sblk_set_sm_limit(int max_sms) {
   const int prev = g_sm_limit;
   g_sm_limit = max_sms > 0 ? (max_sms & ~1) : 0;   // even: CTA-pair kernels take whole TPCs
@@ -278,15 +296,25 @@ int sblk_pack_conv2d(const float* w, const float* gamma, const float* beta, cons
                 static_cast<__nv_bfloat16*>(wp), bias, Co, Ci, R, S);
 }
 
-int sblk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+static int cast_impl(const float* src, void* dst, long long n, int fp16, void* stream, const char* who) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
-  if (!src || !dst) return fail(-1, "sblk_cast_f32_bf16: null pointer");
-  if (n <= 0 || (n & 3) != 0) return fail(-1, "sblk_cast_f32_bf16: n=%lld must be a positive multiple of 4", n);
-  if (!aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return fail(-1, "sblk_cast_f32_bf16: misaligned");
+  if (!src || !dst) return fail(-1, "%s: null pointer", who);
+  if (n <= 0 || (n & 3) != 0) return fail(-1, "%s: n=%lld must be a positive multiple of 4", who, n);
+  if (!aligned16(src) || (reinterpret_cast<uintptr_t>(dst) & 7u)) return fail(-1, "%s: misaligned", who);
   return launch(sblk::cast_f32_bf16_kernel, dim3(elementwise_grid(n / 4, 256, sms)), dim3(256), 0,
                 static_cast<cudaStream_t>(stream), false, "cast_f32_bf16_kernel", src,
-                static_cast<__nv_bfloat16*>(dst), n / 4);
+                static_cast<__nv_bfloat16*>(dst), n / 4, fp16);
+}
+
+int sblk_cast_f32_bf16(const float* src, void* dst, long long n, void* stream) {
+  return cast_impl(src, dst, n, 0, stream, "sblk_cast_f32_bf16");
+}
+
+int sblk_enc16_format(void) { return SBLK_ENC_FP16 ? 1 : 0; }
+
+int sblk_cast_f32_enc16(const float* src, void* dst, long long n, void* stream) {
+  return cast_impl(src, dst, n, SBLK_ENC_FP16 ? 1 : 0, stream, "sblk_cast_f32_enc16");
 }
 
 int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, void* stream) {
@@ -300,10 +328,10 @@ int sblk_l2_prefetch(const void* const* ptrs, const long long* bytes, int n, voi
   // launch PER RANGE keeps the bursts small (launch gaps let the memory system drain) and costs nothing when a hint
   // is dropped: whole path 820 -> 808 us.  SBLK_L2_PREFETCH_MODE / _CTAS override for experiments.
   int cap = 2 * sms, mode = 0;
-  if (const char* e = getenv("SBLK_L2_PREFETCH_CTAS")) cap = atoi(e);
-  if (const char* e = getenv("SBLK_L2_PREFETCH_MODE")) mode = atoi(e);
+  if (const char* e = dbg_env("SBLK_L2_PREFETCH_CTAS")) cap = atoi(e);
+  if (const char* e = dbg_env("SBLK_L2_PREFETCH_MODE")) mode = atoi(e);
   long long chunk_lines = (64ll << 20) / 128;   // one hint launch per range (<= 64 MB); smaller bursts only add launches (graph: 808 us per tensor, 816 at 4 MB, 871 at 1 MB)
-  if (const char* e = getenv("SBLK_L2_PREFETCH_CHUNK_KB")) chunk_lines = (static_cast<long long>(atoi(e)) << 10) / 128;
+  if (const char* e = dbg_env("SBLK_L2_PREFETCH_CHUNK_KB")) chunk_lines = (static_cast<long long>(atoi(e)) << 10) / 128;
   if (chunk_lines < 1) chunk_lines = 1;
   for (int i = 0; i < n; ++i) {
     if (!ptrs[i] || bytes[i] <= 0) return fail(-1, "sblk_l2_prefetch: null pointer / empty range %d", i);
@@ -457,7 +485,7 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   p.out = static_cast<__nv_bfloat16*>(out);
   p.flat_out = flat_out ? 1 : 0;
   {
-    const char* dm = getenv("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    const char* dm = dbg_env("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
     p.debug_mode = dm ? atoi(dm) : 0;
   }
   const int units = p.frames * 2;
@@ -506,7 +534,7 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
   p.bias = bias;
   const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
   p.dbg = nullptr;
-  if (getenv("SBLK_FLAT_STAMPS")) {   // profiling aid: per-tile clock stamps of CTA 0, printed after a synchronise
+  if (dbg_env("SBLK_FLAT_STAMPS")) {   // profiling aid: per-tile clock stamps of CTA 0, printed after a synchronise
     static unsigned long long* d_dbg = nullptr;
     const int tiles0 = (p.num_tiles + pairs - 1) / pairs;
     if (!d_dbg) cudaMalloc(&d_dbg, 4096 * 16 * 8);
@@ -534,7 +562,9 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
 
 int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                          int H, int W, int C, int relu, void* stream) {
+#ifdef SBLK_DEBUG
   using namespace sblk::fc;
+#endif
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !wp || !bias || !out) return fail(-1, "sblk_flatconv3x3_fwd: null pointer");
@@ -546,8 +576,11 @@ int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const
     return fail(-1, "sblk_flatconv3x3_fwd: pointers must be 16-byte aligned");
   const long long rows = sblk_flat_rows(F, H, W);
   if (rows > 0x7fffffffLL - 1024) return fail(-1, "sblk_flatconv3x3_fwd: problem too large");
-  const char* v2 = getenv("SBLK_FLATCONV2");   // 0 = single-CTA kernel for C == 64 (A/B timing experiments)
   if (C == 128) return launch_flatconv2<2>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+#ifndef SBLK_DEBUG
+  return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+#else
+  const char* v2 = dbg_env("SBLK_FLATCONV2");   // 0 = v1 single-CTA kernel for C == 64 (A/B timing experiments)
   if (v2 == nullptr || atoi(v2) != 0)
     return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
   CUtensorMap tmX, tmW, tmR;
@@ -575,12 +608,13 @@ int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const
   p.has_res = residual ? 1 : 0;
   p.out = static_cast<__nv_bfloat16*>(out);
   {
-    const char* dm = getenv("SBLK_FLAT_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    const char* dm = dbg_env("SBLK_FLAT_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
     p.debug_mode = dm ? atoi(dm) : 0;
   }
   const int grid = p.num_tiles < sms ? p.num_tiles : sms;
   return launch(sblk::flatconv3x3_c64_kernel, dim3(grid), dim3(THREADS), SMEM_BYTES,
                 static_cast<cudaStream_t>(stream), true, "flatconv3x3_c64_kernel", tmX, tmW, tmR, p);
+#endif
 }
 
 static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
@@ -663,13 +697,13 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn2 ? bn2 / 2 : bn)};
     if ((rc = encode_tiled(&tmB, wp, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
     sblk::IgemmParams p;
-    p.splits = 1; p.split_stride = 0; p.flat_out = flat_out; p.dbg = nullptr; p.staged = 0;
+    p.splits = 1; p.split_stride = 0; p.flat_out = flat_out; p.dbg = nullptr; p.staged = 0; p.fp16 = 0;
     p.bias2 = bias_ds;
     p.out2_bf16 = static_cast<__nv_bfloat16*>(out_ds);
     p.debug_mode = 0;
     // profiling aid (SBLK_IGEMM2_STAMPS=1): run the CTA-pair launch with clock stamps of CTA 0 and print them
     auto with_stamps = [&](auto&& do_launch, int tiles2, int pairs) -> int {
-      if (!getenv("SBLK_IGEMM2_STAMPS")) return do_launch();
+      if (!dbg_env("SBLK_IGEMM2_STAMPS")) return do_launch();
       static unsigned long long* d_dbg = nullptr;
       if (!d_dbg) cudaMalloc(&d_dbg, 64 * 8);
       cudaMemsetAsync(d_dbg, 0, 64 * 8, static_cast<cudaStream_t>(stream));
@@ -705,7 +739,7 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
         // staged coalesced epilogue stores (they take the place of the last ring stage); measured in the whole graph:
         // frontend 607 us (always staged) vs 644 us (never); SBLK_IGEMM2_STAGED=0/1 overrides for A/B timing
         p.staged = 1;
-        if (const char* e = getenv("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
+        if (const char* e = dbg_env("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
         return with_stamps([&]() {
           return launch(sblk::igemm2_kernel<128, true, true>, dim3(2 * pairs), dim3(sblk::Igemm2Cfg<128, true>::THREADS),
                         sblk::Igemm2Cfg<128, true>::SMEM_BYTES, static_cast<cudaStream_t>(stream), true,
@@ -726,7 +760,7 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
       const int tiles2 = ((M + 255) / 256) * (Cout / bn2);
       const int pairs = tiles2 < sms / 2 ? tiles2 : sms / 2;
       p.staged = 1;
-      if (const char* e = getenv("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
+      if (const char* e = dbg_env("SBLK_IGEMM2_STAGED")) p.staged = atoi(e) != 0;
       if (bn2 == 256) {
         return with_stamps([&]() {
           return launch(sblk::igemm2_kernel<256, true>, dim3(2 * pairs), dim3(sblk::Igemm2Cfg<256>::THREADS),
@@ -780,7 +814,7 @@ static int gemm_impl(const void* a, const void* w, const float* bias, const void
   const int m_tiles = (M + 127) / 128;
   int bn = pick_block_n_linear(m_tiles, N, splits, sms);
   {
-    const char* e = getenv("SBLK_GEMM_BN");   // tuning experiments only
+    const char* e = dbg_env("SBLK_GEMM_BN");   // tuning experiments only
     if (e && atoi(e) > 0 && N % atoi(e) == 0) bn = atoi(e);
   }
   {
@@ -797,7 +831,7 @@ static int gemm_impl(const void* a, const void* w, const float* bias, const void
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
-  p.splits = splits; p.flat_out = 0; p.dbg = nullptr; p.staged = 0;
+  p.splits = splits; p.flat_out = 0; p.dbg = nullptr; p.staged = 0; p.fp16 = SBLK_ENC_FP16 ? 1 : 0;
   p.split_stride = static_cast<long long>(M) * N;
   return launch_igemm<false>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
 }
@@ -825,7 +859,7 @@ int sblk_gemm_splitk_fwd(const void* a, const void* w, const float* bias, float*
 }
 
 int sblk_avgpool_scale_fwd(const void* x, const float* scale, float* out_f32, void* out_bf16, int F, int HW, int C,
-                           void* stream) {
+                           int out16_enc, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || (!out_f32 && !out_bf16)) return fail(-1, "sblk_avgpool_fwd: null pointer");
@@ -836,11 +870,11 @@ int sblk_avgpool_scale_fwd(const void* x, const float* scale, float* out_f32, vo
   const long long items = static_cast<long long>(F) * (C / 2);
   return launch(sblk::avgpool_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
                 static_cast<cudaStream_t>(stream), false, "avgpool_kernel", static_cast<const __nv_bfloat16*>(x), scale,
-                out_f32, static_cast<__nv_bfloat16*>(out_bf16), F, HW, C);
+                out_f32, static_cast<__nv_bfloat16*>(out_bf16), F, HW, C, (out16_enc && SBLK_ENC_FP16) ? 1 : 0);
 }
 
 int sblk_avgpool_fwd(const void* x, float* out_f32, void* out_bf16, int F, int HW, int C, void* stream) {
-  return sblk_avgpool_scale_fwd(x, nullptr, out_f32, out_bf16, F, HW, C, stream);
+  return sblk_avgpool_scale_fwd(x, nullptr, out_f32, out_bf16, F, HW, C, 0, stream);
 }
 
 int sblk_sum_layernorm_fwd(const float* x_parts, int nparts, const float* bias, const float* residual,
@@ -859,7 +893,7 @@ int sblk_sum_layernorm_fwd(const float* x_parts, int nparts, const float* bias, 
   sblk::LnParams p;
   p.x = x_parts; p.nparts = nparts; p.part_stride = static_cast<long long>(M) * D; p.bias = bias;
   p.residual = residual; p.gamma = gamma; p.beta = beta; p.pe = pe; p.lengths = lengths;
-  p.out_f32 = out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.M = M; p.T = T; p.eps = eps;
+  p.out_f32 = out_f32; p.out_bf16 = static_cast<sblk::enc16_t*>(out_bf16); p.M = M; p.T = T; p.eps = eps;
   // one warp per row; 4 rows per CTA so that the BASELINE 928 tokens spread over all SMs
   const int rows_per_block = 4;
   int grid = (M + rows_per_block - 1) / rows_per_block;
@@ -885,8 +919,8 @@ int sblk_attention_fwd(const void* qkv, void* out, float* probs, const int* leng
   if (T > 128) return fail(-1, "sblk_attention_fwd: T=%d > 128 not implemented", T);
   if (!aligned16(qkv)) return fail(-1, "sblk_attention_fwd: qkv must be 16-byte aligned");
   sblk::AttnParams p;
-  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
-  p.out = static_cast<__nv_bfloat16*>(out);
+  p.qkv = static_cast<const sblk::enc16_t*>(qkv);
+  p.out = static_cast<sblk::enc16_t*>(out);
   p.probs = probs; p.lengths = lengths; p.N = N; p.T = T; p.H = H; p.scale = scale;
   const int pairs = N * H;
   const dim3 grid((pairs + sblk::ATTN_WARPS - 1) / sblk::ATTN_WARPS), block(sblk::ATTN_WARPS * 32);
@@ -930,7 +964,7 @@ int sblk_gemm_ln_fwd(const void* a, const void* w, const float* bias, const floa
   }
   sblk::GemmLnParams p;
   p.M = M; p.K = K; p.T = T; p.bias = bias; p.residual = residual; p.gamma = gamma; p.beta = beta; p.pe = pe;
-  p.lengths = lengths; p.out_f32 = out_f32; p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); p.eps = eps;
+  p.lengths = lengths; p.out_f32 = out_f32; p.out_bf16 = static_cast<sblk::enc16_t*>(out_bf16); p.eps = eps;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   return launch(sblk::gemm_ln512_kernel, dim3(CLUSTER * m_tiles), dim3(THREADS), SMEM_BYTES,
                 static_cast<cudaStream_t>(stream), true, "gemm_ln512_kernel", tmA, tmB, p);
@@ -973,7 +1007,7 @@ int sblk_qkv_attention_fwd(const void* x, const void* w_heads, const float* bias
   }
   sblk::QkvAttnParams p;
   p.N = N; p.T = T; p.H = H; p.G = sblk_qkv_group_clips(T); p.K = K; p.bias = bias_heads; p.lengths = lengths;
-  p.out = static_cast<__nv_bfloat16*>(out); p.scale = scale;
+  p.out = static_cast<sblk::enc16_t*>(out); p.scale = scale;
   const dim3 grid((N + p.G - 1) / p.G, H), block(THREADS);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (T <= 32) return launch(sblk::qkv_attention_kernel<4>, grid, block, SMEM_BYTES, s, true, "qkv_attention_kernel<4>", tmA, tmB, p);
@@ -1011,14 +1045,14 @@ static int launch_encoder_stack(const CUtensorMap* tm, const sblk::EncStackParam
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   int nattr = 1;
-  if (g_pdl.load(std::memory_order_relaxed) != 0) {
+  if (g_pdl != 0) {
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     nattr = 2;
   }
   cfg.attrs = attr;
   cfg.numAttrs = nattr;
-  if (getenv("SBLK_ENC_STACK_VERBOSE")) {
+  if (dbg_env("SBLK_ENC_STACK_VERBOSE")) {
     int ncl = -1;
     cudaError_t oe = cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg);
     fprintf(stderr, "[libsblk] encoder_stack CL=%d: max active clusters %d (%s), grid %d CTAs\n", CL, ncl,
@@ -1065,19 +1099,17 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   }
   // Cluster size: 16 CTAs per clip group stream the least weight bytes per SM, but only 7 clusters of 16 are ever
   // co-resident on a B200 (measured: GPC granularity), so batches with more groups use clusters of 8 (all 8 groups
-  // of the BASELINE batch in one wave).  SBLK_ENC_STACK_CL / SBLK_ENC_STACK_MC override for A/B timing.
+  // of the BASELINE batch in one wave).  args.cluster_size / args.no_multicast select the variants explicitly.
   const int G = sblk_qkv_group_clips(T);
   const int groups = (N + G - 1) / G;
   int cl = a->cluster_size != 0 ? a->cluster_size : (groups <= 7 ? 16 : 8);
-  bool mc = true;
-  if (const char* e = getenv("SBLK_ENC_STACK_CL")) cl = atoi(e);
-  if (const char* e = getenv("SBLK_ENC_STACK_MC")) mc = atoi(e) != 0;
-  if (cl != 8 && cl != 16) return fail(-1, "sblk_encoder_stack_fwd: SBLK_ENC_STACK_CL must be 8 or 16");
+  const bool mc = a->no_multicast == 0;
+  if (cl != 8 && cl != 16) return fail(-1, "sblk_encoder_stack_fwd: cluster_size must be 0 (automatic), 8 or 16");
   if (d_inner % (64 * cl) != 0 || d_inner / cl > (cl == 16 ? 192 : 256))
     return fail(-1, "sblk_encoder_stack_fwd: d_inner=%d not supported by the fused stack (d_inner %% %d == 0, "
                 "d_inner / %d <= %d)", d_inner, 64 * cl, cl, cl == 16 ? 192 : 256);
   const long long M = static_cast<long long>(N) * T;
-  __nv_bfloat16* ws = static_cast<__nv_bfloat16*>(a->workspace);
+  sblk::enc16_t* ws = static_cast<sblk::enc16_t*>(a->workspace);
   sblk::EncStackParams p;
   p.N = N; p.T = T; p.G = G; p.L = L; p.M = static_cast<int>(M); p.d_in = d_in; p.d_inner = d_inner;
   p.b_in = a->b_in; p.g_in = a->ln_in_gamma; p.be_in = a->ln_in_beta; p.pe = a->pe;

@@ -3,17 +3,17 @@
 // split / merge around it in MultiHeadAttention.forward, attention.py:41-55:
 //   attn = softmax(Q K^T / sqrt(d_k) masked_fill(key >= length, -inf)) ; out = attn V
 // One WARP per (clip, head): Q, K, V of the head are staged in (warp-private, XOR-swizzled) shared memory, S = Q K^T
-// and O = P V run on warp-level tensor-core MMAs (m16n8k16 bf16, fp32 accumulate; 0.05 % of the encoder's FLOPs, far
+// and O = P V run on warp-level tensor-core MMAs (m16n8k16 on the encoder's 16-bit operand format, fp32 accumulate; 0.05 % of the encoder's FLOPs, far
 // too small for a tcgen05 tile), the softmax lives in the accumulator registers (fp32, quad-shuffle max / sum), and P is
-// fed to the second MMA as a bf16 hi + lo pair so the probabilities keep fp32-level accuracy.
+// fed to the second MMA as a 16-bit hi + lo pair so the probabilities keep fp32-level accuracy.
 #pragma once
 #include "sblk_common.cuh"
 
 namespace sblk {
 
 struct AttnParams {
-  const __nv_bfloat16* qkv;  // [N*T, 3*H*64] : q | k | v, head h at columns h*64 inside each third
-  __nv_bfloat16* out;        // [N*T, H*64]   : heads concatenated (== permute(1,2,0,3).view(b, lq, -1))
+  const enc16_t* qkv;  // [N*T, 3*H*64] : q | k | v, head h at columns h*64 inside each third
+  enc16_t* out;        // [N*T, H*64]   : heads concatenated (== permute(1,2,0,3).view(b, lq, -1))
   float* probs;              // optional [H*N, T, T], batch index h*N + b (attention.py:45,52), or nullptr
   const int* lengths;        // optional [N] valid key counts, or nullptr (= all T)
   int N, T, H;
@@ -29,9 +29,9 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
 }
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+__device__ __forceinline__ void mma_e16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+  asm volatile(SBLK_MMA_SYNC_E16 " {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
                "{%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -40,7 +40,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint3
 constexpr int ATTN_WARPS = 2;
 
 // One 16-query tile of one (clip, head): S = Q K^T (tensor cores), masked fp32 softmax in the accumulator registers,
-// O = P V with P as bf16 hi + lo, bf16 store.  Q / K / V are bf16 tiles in shared memory with 128-byte rows (64
+// O = P V with P as hi + lo, 16-bit store.  Q / K / V are 16-bit (enc16_t) tiles in shared memory with 128-byte rows (64
 // features), 16-byte chunk c of ABSOLUTE row r stored at chunk c ^ (r & 7).  qrow0 = absolute row of this tile's first
 // query, krow0 = absolute row of the clip's key 0; rows [krow0, krow0 + 8 NT) must hold finite values.
 //   out_clip  : &out[(b*T) * ld_out + h*64]          (row q of the clip at + q * ld_out)
@@ -48,7 +48,7 @@ constexpr int ATTN_WARPS = 2;
 template <int NT>
 __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, uint32_t sV_u, int qrow0, int krow0,
                                                 int q_first, int T, int len, float scale, int lane,
-                                                __nv_bfloat16* out_clip, int ld_out, float* probs_clip) {
+                                                enc16_t* out_clip, int ld_out, float* probs_clip) {
   constexpr int D = 64;
   constexpr int KT = NT / 2;             // 16-key tiles for P V
   const int g = lane >> 2;       // fragment row within an 8-row group
@@ -72,8 +72,8 @@ __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, ui
       const int c = 2 * kk + ((lane >> 3) & 1);
       uint32_t b0, b1, b2, b3;
       ldmatrix_x4(sK_u + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
-      mma_bf16_16816(s[2 * j2], a0, a1, a2, a3, b0, b1);
-      mma_bf16_16816(s[2 * j2 + 1], a0, a1, a2, a3, b2, b3);
+      mma_e16_16816(s[2 * j2], a0, a1, a2, a3, b0, b1);
+      mma_e16_16816(s[2 * j2 + 1], a0, a1, a2, a3, b2, b3);
     }
   }
   // ---- masked softmax over keys (rows g and g + 8 of this tile), fp32
@@ -128,7 +128,7 @@ __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, ui
       }
     }
   }
-  // ---- O = P V with P as bf16 hi + lo
+  // ---- O = P V with P as hi + lo
   float o[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
@@ -140,11 +140,8 @@ __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, ui
       // A-fragment register r: (row g | g+8, keys 16kt + 2tq.. | +8) == accumulator regs of key tiles 2kt, 2kt+1
       const float x = s[2 * kt + (r >> 1)][(r & 1) * 2 + 0];
       const float y = s[2 * kt + (r >> 1)][(r & 1) * 2 + 1];
-      const __nv_bfloat162 hh = __floats2bfloat162_rn(x, y);
-      const float2 hf = __bfloat1622float2(hh);
-      const __nv_bfloat162 ll = __floats2bfloat162_rn(x - hf.x, y - hf.y);
-      hi[r] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[r] = *reinterpret_cast<const uint32_t*>(&ll);
+      hi[r] = pack_e16x2(x, y);
+      lo[r] = pack_e16x2(x - e16_lo(hi[r]), y - e16_hi(hi[r]));
     }
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
@@ -153,10 +150,10 @@ __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, ui
       const int c = 2 * n2 + (lane >> 4);
       uint32_t b0, b1, b2, b3;
       ldmatrix_x4_trans(sV_u + row * 128 + ((c ^ (row & 7)) << 4), b0, b1, b2, b3);
-      mma_bf16_16816(o[2 * n2], hi[0], hi[1], hi[2], hi[3], b0, b1);
-      mma_bf16_16816(o[2 * n2], lo[0], lo[1], lo[2], lo[3], b0, b1);
-      mma_bf16_16816(o[2 * n2 + 1], hi[0], hi[1], hi[2], hi[3], b2, b3);
-      mma_bf16_16816(o[2 * n2 + 1], lo[0], lo[1], lo[2], lo[3], b2, b3);
+      mma_e16_16816(o[2 * n2], hi[0], hi[1], hi[2], hi[3], b0, b1);
+      mma_e16_16816(o[2 * n2], lo[0], lo[1], lo[2], lo[3], b0, b1);
+      mma_e16_16816(o[2 * n2 + 1], hi[0], hi[1], hi[2], hi[3], b2, b3);
+      mma_e16_16816(o[2 * n2 + 1], lo[0], lo[1], lo[2], lo[3], b2, b3);
     }
   }
   // ---- store: row q of the clip, features 8n + 2tq, +1
@@ -164,10 +161,10 @@ __device__ __forceinline__ void attention_mtile(uint32_t sQ_u, uint32_t sK_u, ui
   for (int n = 0; n < 8; ++n) {
     if (q0 < T)
       *reinterpret_cast<uint32_t*>(out_clip + static_cast<size_t>(q0) * ld_out + n * 8 + 2 * tq) =
-          pack_bf16x2(o[n][0], o[n][1]);
+          pack_e16x2(o[n][0], o[n][1]);
     if (q1 < T)
       *reinterpret_cast<uint32_t*>(out_clip + static_cast<size_t>(q1) * ld_out + n * 8 + 2 * tq) =
-          pack_bf16x2(o[n][2], o[n][3]);
+          pack_e16x2(o[n][2], o[n][3]);
   }
 }
 
@@ -195,8 +192,8 @@ attention_kernel(const AttnParams p) {
   const int ld = 3 * p.H * D;
   const int len = (p.lengths != nullptr) ? min(max(__ldg(p.lengths + b), 0), T) : T;
 
-  // stage Q | K | V rows of this head (bf16, 128 B per row, 16-B chunk c stored at c ^ (row & 7)); pad rows are zero
-  const __nv_bfloat16* base = p.qkv + static_cast<size_t>(b) * T * ld + h * D;
+  // stage Q | K | V rows of this head (enc16_t, 128 B per row, 16-B chunk c stored at c ^ (row & 7)); pad rows are zero
+  const enc16_t* base = p.qkv + static_cast<size_t>(b) * T * ld + h * D;
   for (int i = lane; i < 3 * TP * 8; i += 32) {
     const int c = i & 7;
     const int row = (i >> 3) % TP;
@@ -210,7 +207,7 @@ attention_kernel(const AttnParams p) {
 
   const uint32_t sQ_u = smem_u32(sQ), sK_u = smem_u32(sK), sV_u = smem_u32(sV);
   const int mt_count = (T + 15) >> 4;
-  __nv_bfloat16* out_clip = p.out + static_cast<size_t>(b) * T * (p.H * D) + h * D;
+  enc16_t* out_clip = p.out + static_cast<size_t>(b) * T * (p.H * D) + h * D;
   float* probs_clip = p.probs != nullptr ? p.probs + (static_cast<size_t>(h) * p.N + b) * T * T : nullptr;
   for (int mt = 0; mt < mt_count; ++mt)
     attention_mtile<NT>(sQ_u, sK_u, sV_u, mt * 16, 0, mt * 16, T, len, p.scale, lane, out_clip, p.H * D, probs_clip);

@@ -1,6 +1,6 @@
 // sblk_aux.cuh — the memory-bound kernels of the visual encoder (HBM roofline, not tensor):
 //   clip prep (fp32 -> padded bf16), weight packers (BN fold), global average pool,
-//   residual + LayerNorm (+ positional encoding, + pad mask), fp32 -> bf16 cast.
+//   residual + LayerNorm (+ positional encoding, + pad mask), fp32 -> bf16 / fp16 cast.
 #pragma once
 #include "sblk_common.cuh"
 #include "sblk_conv3d.cuh"
@@ -183,15 +183,15 @@ pack_conv3d_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
   }
 }
 
-// fp32 -> bf16 cast (Linear weights, encoder input).  n must be a multiple of 4.
+// fp32 -> bf16 / fp16 cast (Linear weights, encoder input).  n must be a multiple of 4.
 __global__ void __launch_bounds__(256)
-cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
+cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4, int fp16) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
     uint2 o;
-    o.x = pack_bf16x2(v.x, v.y);
-    o.y = pack_bf16x2(v.z, v.w);
+    o.x = fp16 ? pack_f16x2(v.x, v.y) : pack_bf16x2(v.x, v.y);
+    o.y = fp16 ? pack_f16x2(v.z, v.w) : pack_bf16x2(v.z, v.w);
     reinterpret_cast<uint2*>(dst)[i] = o;
   }
 }
@@ -303,7 +303,7 @@ p2p_gather_kernel(const uint4* __restrict__ local, uint4* const* __restrict__ pe
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 avgpool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, float* __restrict__ out_f32,
-               __nv_bfloat16* __restrict__ out_bf16, int F, int HW, int C) {
+               __nv_bfloat16* __restrict__ out_bf16, int F, int HW, int C, int out_fp16) {
   const int C2 = C >> 1;
   const long long total = static_cast<long long>(F) * C2;
   const float inv = 1.0f / static_cast<float>(HW);
@@ -326,7 +326,8 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sc
       b *= m.y;
     }
     if (out_f32 != nullptr) reinterpret_cast<float2*>(out_f32)[i] = make_float2(a, b);
-    if (out_bf16 != nullptr) reinterpret_cast<uint32_t*>(out_bf16)[i] = pack_bf16x2(a, b);
+    if (out_bf16 != nullptr)
+      reinterpret_cast<uint32_t*>(out_bf16)[i] = out_fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
   }
 }
 
@@ -334,7 +335,7 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sc
 // y = LayerNorm(x + residual) * gamma + beta  (+ pe[t])  (* pad_mask[b,t]),  D = 512, eps = 1e-5.
 // Reference: attention.py:58, module.py:51, encoder.py:53-55 (+PE), encoder.py:86,89 (mask).
 // One warp per row; the row lives in registers (16 values per lane); two-pass mean / variance in fp32.
-// Writes the fp32 residual stream and the bf16 copy the next GEMM consumes.
+// Writes the fp32 residual stream and the 16-bit (enc16_t) copy the next GEMM consumes.
 // --------------------------------------------------------------------------------------------
 struct LnParams {
   const float* x;         // [nparts][M, 512] GEMM output (split-K partials are summed here; bias added if given)
@@ -347,7 +348,7 @@ struct LnParams {
   const float* pe;        // [>=T, 512] or nullptr ; row t = m % T
   const int* lengths;     // [M / T] or nullptr ; rows with t >= lengths[b] are zeroed
   float* out_f32;         // [M, 512] or nullptr
-  __nv_bfloat16* out_bf16;  // [M, 512] or nullptr
+  enc16_t* out_bf16;        // [M, 512] or nullptr (encoder operand format, sblk_common.cuh)
   int M;
   int T;
   float eps;
@@ -427,8 +428,8 @@ add_layernorm512_kernel(const LnParams p) {
         reinterpret_cast<float4*>(p.out_f32 + static_cast<size_t>(m) * 512)[col4] = y;
       if (p.out_bf16 != nullptr) {
         uint2 o;
-        o.x = pack_bf16x2(y.x, y.y);
-        o.y = pack_bf16x2(y.z, y.w);
+        o.x = pack_e16x2(y.x, y.y);
+        o.y = pack_e16x2(y.z, y.w);
         reinterpret_cast<uint2*>(p.out_bf16 + static_cast<size_t>(m) * 512)[col4] = o;
       }
     }

@@ -52,9 +52,9 @@ struct EncStackParams {
   const float* be2;
   const int* lengths;        // [N] or nullptr (all T)
   float* out;                // [M, 512] fp32: residual stream while the stack runs, enc_output at the end
-  __nv_bfloat16* x16;        // [M, 512]      workspace: bf16 copy of the residual stream (GEMM operand)
-  __nv_bfloat16* att16;      // [M, 512]      workspace: concatenated attention heads
-  __nv_bfloat16* h16;        // [M, d_inner]  workspace: relu(w_1 x)
+  enc16_t* x16;        // [M, 512]      workspace: bf16 copy of the residual stream (GEMM operand)
+  enc16_t* att16;      // [M, 512]      workspace: concatenated attention heads
+  enc16_t* h16;        // [M, d_inner]  workspace: relu(w_1 x)
   float scale;               // 1 / temperature
   float eps;                 // LayerNorm eps (all three LayerNorms of the reference use the default 1e-5)
   unsigned long long* dbg;   // optional [stages][8] clock64 stamps of cluster 0 / CTA 0 (profiling aid), or nullptr
@@ -351,7 +351,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     for (int s = 0; s < num_stages; ++s) {
       const EncStage d = stage_desc(s);
       const int units = d.num_kb / d.kbps;
-      const uint32_t idesc = make_idesc_bf16(128, d.n);
+      const uint32_t idesc = make_idesc_e16(128, d.n);
       const uint32_t b_bytes = static_cast<uint32_t>(d.n) * 128u;
       tc_fence_after_sync();
       for (int u = 0; u < units; ++u) {
@@ -516,20 +516,20 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               uint4 o[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                o[j].x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                o[j].y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                o[j].z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                o[j].w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                o[j].x = pack_e16x2(v[8 * j + 0], v[8 * j + 1]);
+                o[j].y = pack_e16x2(v[8 * j + 2], v[8 * j + 3]);
+                o[j].z = pack_e16x2(v[8 * j + 4], v[8 * j + 5]);
+                o[j].w = pack_e16x2(v[8 * j + 6], v[8 * j + 7]);
               }
               warp_store_rows64(stg_ln, o, gb, D * 2, warp_valid, lane);
             } else {
               uint4 o[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                o[j].x = pack_bf16x2(v[(8 * j + 0) % NS], v[(8 * j + 1) % NS]);
-                o[j].y = pack_bf16x2(v[(8 * j + 2) % NS], v[(8 * j + 3) % NS]);
-                o[j].z = pack_bf16x2(v[(8 * j + 4) % NS], v[(8 * j + 5) % NS]);
-                o[j].w = pack_bf16x2(v[(8 * j + 6) % NS], v[(8 * j + 7) % NS]);
+                o[j].x = pack_e16x2(v[(8 * j + 0) % NS], v[(8 * j + 1) % NS]);
+                o[j].y = pack_e16x2(v[(8 * j + 2) % NS], v[(8 * j + 3) % NS]);
+                o[j].z = pack_e16x2(v[(8 * j + 4) % NS], v[(8 * j + 5) % NS]);
+                o[j].w = pack_e16x2(v[(8 * j + 6) % NS], v[(8 * j + 7) % NS]);
               }
               warp_store_rows128(stg_ln, o, gb, D * 2, warp_valid, lane);
             }
@@ -573,10 +573,10 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           for (int j = 0; j < 4; ++j) {
             uint4 o = make_uint4(0u, 0u, 0u, 0u);   // rows past the group's clips hold zeros (finite masked keys)
             if (row_ok) {
-              o.x = pack_bf16x2(__uint_as_float(u[8 * j + 0]) + bp[8 * j + 0], __uint_as_float(u[8 * j + 1]) + bp[8 * j + 1]);
-              o.y = pack_bf16x2(__uint_as_float(u[8 * j + 2]) + bp[8 * j + 2], __uint_as_float(u[8 * j + 3]) + bp[8 * j + 3]);
-              o.z = pack_bf16x2(__uint_as_float(u[8 * j + 4]) + bp[8 * j + 4], __uint_as_float(u[8 * j + 5]) + bp[8 * j + 5]);
-              o.w = pack_bf16x2(__uint_as_float(u[8 * j + 6]) + bp[8 * j + 6], __uint_as_float(u[8 * j + 7]) + bp[8 * j + 7]);
+              o.x = pack_e16x2(__uint_as_float(u[8 * j + 0]) + bp[8 * j + 0], __uint_as_float(u[8 * j + 1]) + bp[8 * j + 1]);
+              o.y = pack_e16x2(__uint_as_float(u[8 * j + 2]) + bp[8 * j + 2], __uint_as_float(u[8 * j + 3]) + bp[8 * j + 3]);
+              o.z = pack_e16x2(__uint_as_float(u[8 * j + 4]) + bp[8 * j + 4], __uint_as_float(u[8 * j + 5]) + bp[8 * j + 5]);
+              o.w = pack_e16x2(__uint_as_float(u[8 * j + 6]) + bp[8 * j + 6], __uint_as_float(u[8 * j + 7]) + bp[8 * j + 7]);
             }
             const int chunk = (cc & 1) * 4 + j;
             *reinterpret_cast<uint4*>(dst_row + ((chunk ^ (row & 7)) << 4)) = o;
@@ -592,7 +592,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           const int mt = un - c * mt_count;
           const int b = group * p.G + c;
           const int len = (p.lengths != nullptr) ? min(max(__ldg(p.lengths + b), 0), T) : T;
-          __nv_bfloat16* out_clip = p.att16 + static_cast<size_t>(b) * T * D + head * 64;
+          enc16_t* out_clip = p.att16 + static_cast<size_t>(b) * T * D + head * 64;
           attention_mtile<NT>(sQ_u, sK_u, sV_u, c * T + mt * 16, c * T, mt * 16, T, len, p.scale, lane, out_clip, D,
                               nullptr);
         }
@@ -621,13 +621,13 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             const float* bp = bias + blk * 64 + c2 * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              o[c2 * 4 + j].x = pack_bf16x2(fmaxf(__uint_as_float(u[8 * j + 0]) + bp[8 * j + 0], 0.0f),
+              o[c2 * 4 + j].x = pack_e16x2(fmaxf(__uint_as_float(u[8 * j + 0]) + bp[8 * j + 0], 0.0f),
                                             fmaxf(__uint_as_float(u[8 * j + 1]) + bp[8 * j + 1], 0.0f));
-              o[c2 * 4 + j].y = pack_bf16x2(fmaxf(__uint_as_float(u[8 * j + 2]) + bp[8 * j + 2], 0.0f),
+              o[c2 * 4 + j].y = pack_e16x2(fmaxf(__uint_as_float(u[8 * j + 2]) + bp[8 * j + 2], 0.0f),
                                             fmaxf(__uint_as_float(u[8 * j + 3]) + bp[8 * j + 3], 0.0f));
-              o[c2 * 4 + j].z = pack_bf16x2(fmaxf(__uint_as_float(u[8 * j + 4]) + bp[8 * j + 4], 0.0f),
+              o[c2 * 4 + j].z = pack_e16x2(fmaxf(__uint_as_float(u[8 * j + 4]) + bp[8 * j + 4], 0.0f),
                                             fmaxf(__uint_as_float(u[8 * j + 5]) + bp[8 * j + 5], 0.0f));
-              o[c2 * 4 + j].w = pack_bf16x2(fmaxf(__uint_as_float(u[8 * j + 6]) + bp[8 * j + 6], 0.0f),
+              o[c2 * 4 + j].w = pack_e16x2(fmaxf(__uint_as_float(u[8 * j + 6]) + bp[8 * j + 6], 0.0f),
                                             fmaxf(__uint_as_float(u[8 * j + 7]) + bp[8 * j + 7], 0.0f));
             }
           }

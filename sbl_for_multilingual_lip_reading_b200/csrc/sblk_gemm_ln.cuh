@@ -28,7 +28,7 @@ struct GemmLnParams {
   const float* pe;        // [>= T, 512] or nullptr
   const int* lengths;     // [M / T] or nullptr
   float* out_f32;         // [M, 512] or nullptr
-  __nv_bfloat16* out_bf16;  // [M, 512] or nullptr
+  enc16_t* out_bf16;  // [M, 512] or nullptr
   float eps;
 };
 
@@ -66,7 +66,7 @@ __global__ void __cluster_dims__(gln::CLUSTER, 1, 1) __launch_bounds__(gln::THRE
 gemm_ln512_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const GemmLnParams p) {
   using namespace gln;
-  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc_e16(BLOCK_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
@@ -269,10 +269,10 @@ gemm_ln512_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 o;
-            o.x = pack_bf16x2(y[8 * j + 0], y[8 * j + 1]);
-            o.y = pack_bf16x2(y[8 * j + 2], y[8 * j + 3]);
-            o.z = pack_bf16x2(y[8 * j + 4], y[8 * j + 5]);
-            o.w = pack_bf16x2(y[8 * j + 6], y[8 * j + 7]);
+            o.x = pack_e16x2(y[8 * j + 0], y[8 * j + 1]);
+            o.y = pack_e16x2(y[8 * j + 2], y[8 * j + 3]);
+            o.z = pack_e16x2(y[8 * j + 4], y[8 * j + 5]);
+            o.w = pack_e16x2(y[8 * j + 6], y[8 * j + 7]);
             op[j] = o;
           }
         }

@@ -47,6 +47,9 @@ struct IgemmParams {
   // CTA-pair kernel only: 1 = epilogue stores go through per-warp staging tiles (coalesced rows) that take the place of
   // the last ring stage; 0 = direct per-thread stores and the full ring (L2-latency-bound shapes need every stage)
   int staged;
+  // 16-bit float format of A, B, residual and out_bf16: 0 = bf16 (every conv), 1 = IEEE fp16 (the encoder's linear
+  // layers, sblk_common.cuh "enc16"); both run as tcgen05 kind::f16 at the same rate
+  int fp16;
 };
 
 template <int BLOCK_N, bool DUAL = false>
@@ -70,7 +73,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   using Cfg = IgemmCfg<BLOCK_N, DUAL>;
   static_assert(!DUAL || (IM2COL && BLOCK_N <= 128), "DUAL needs im2col and 4 accumulators of <= 128 columns");
   constexpr int STAGES = Cfg::STAGES;
-  constexpr uint32_t IDESC = make_idesc_bf16(Cfg::BLOCK_M, BLOCK_N);
+  const uint32_t IDESC = (!IM2COL && p.fp16) ? make_idesc_f16(Cfg::BLOCK_M, BLOCK_N)
+                                              : make_idesc_bf16(Cfg::BLOCK_M, BLOCK_N);
+  const bool out_fp16 = !IM2COL && p.fp16;
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -251,10 +256,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 r4 = __ldg(rp + j);
-              f[8 * j + 0] += bf16_lo(r4.x); f[8 * j + 1] += bf16_hi(r4.x);
-              f[8 * j + 2] += bf16_lo(r4.y); f[8 * j + 3] += bf16_hi(r4.y);
-              f[8 * j + 4] += bf16_lo(r4.z); f[8 * j + 5] += bf16_hi(r4.z);
-              f[8 * j + 6] += bf16_lo(r4.w); f[8 * j + 7] += bf16_hi(r4.w);
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[8 * j + 2 * q + 0] += out_fp16 ? f16_lo(rw[q]) : bf16_lo(rw[q]);
+                f[8 * j + 2 * q + 1] += out_fp16 ? f16_hi(rw[q]) : bf16_hi(rw[q]);
+              }
             }
           }
           if (p.relu) {
@@ -266,10 +273,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 o;
-              o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              if (out_fp16) {
+                o.x = pack_f16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_f16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_f16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_f16x2(f[8 * j + 6], f[8 * j + 7]);
+              } else {
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              }
               op[j] = o;
             }
           }

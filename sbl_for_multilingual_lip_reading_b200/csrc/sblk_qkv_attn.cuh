@@ -26,7 +26,7 @@ struct QkvAttnParams {
   int K;                 // d_model (multiple of 64)
   const float* bias;     // [H * 192] head-major (q_h | k_h | v_h)
   const int* lengths;    // [N] valid key counts or nullptr
-  __nv_bfloat16* out;    // [N*T, H*64]
+  enc16_t* out;    // [N*T, H*64]
   float scale;           // 1 / temperature
 };
 
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(qa::THREADS, 1)
 qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const QkvAttnParams p) {
   using namespace qa;
-  constexpr uint32_t IDESC = make_idesc_bf16(BLOCK_M, BLOCK_N);
+  constexpr uint32_t IDESC = make_idesc_e16(BLOCK_M, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
@@ -159,10 +159,10 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int j = 0; j < 4; ++j) {
         const float4 b0 = __ldg(bp + 2 * j), b1 = __ldg(bp + 2 * j + 1);
         uint4 o;
-        o.x = pack_bf16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
-        o.y = pack_bf16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
-        o.z = pack_bf16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
-        o.w = pack_bf16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
+        o.x = pack_e16x2(__uint_as_float(v[8 * j + 0]) + b0.x, __uint_as_float(v[8 * j + 1]) + b0.y);
+        o.y = pack_e16x2(__uint_as_float(v[8 * j + 2]) + b0.z, __uint_as_float(v[8 * j + 3]) + b0.w);
+        o.z = pack_e16x2(__uint_as_float(v[8 * j + 4]) + b1.x, __uint_as_float(v[8 * j + 5]) + b1.y);
+        o.w = pack_e16x2(__uint_as_float(v[8 * j + 6]) + b1.z, __uint_as_float(v[8 * j + 7]) + b1.w);
         const int chunk = (cc & 1) * 4 + j;
         *reinterpret_cast<uint4*>(dst_row + ((chunk ^ (row & 7)) << 4)) = o;
       }
@@ -179,7 +179,7 @@ qkv_attention_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const int b = tile * p.G + c;
       if (b >= p.N) continue;
       const int len = (p.lengths != nullptr) ? min(max(__ldg(p.lengths + b), 0), T) : T;
-      __nv_bfloat16* out_clip = p.out + static_cast<size_t>(b) * T * (p.H * 64) + h * 64;
+      enc16_t* out_clip = p.out + static_cast<size_t>(b) * T * (p.H * 64) + h * 64;
       attention_mtile<NT>(sQ_u, sK_u, sV_u, c * T + mt * 16, c * T, mt * 16, T, len, p.scale, lane, out_clip,
                           p.H * 64, nullptr);
     }

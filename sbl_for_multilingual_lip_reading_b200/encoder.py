@@ -12,7 +12,8 @@ reference's names and initialisation; the forward pass runs libsblk kernels only
     (GEMM -> LayerNorm pairs: split-K partials summed by the LayerNorm kernel at small token counts, one
     cluster-fused launch at large ones; see ops.linear_ln)
 
-The residual stream stays fp32; GEMM operands are bf16 with fp32 accumulation.
+The residual stream stays fp32; GEMM operands are 16-bit (`ops.enc16_dtype()`: fp16 by default — the encoder's
+values are LayerNorm-bounded, so the 3 extra mantissa bits over bf16 cost nothing) with fp32 accumulation.
 Masks are never materialised: `input_lengths` goes to the kernels as an int32 vector
 (reference builds them with a Python loop twice per call, transformer/utils.py:98-113,140-147).
 """
@@ -113,6 +114,11 @@ class Encoder(nn.Module):
         self.parallel_chains = 4   # clip groups run as concurrent kernel chains (1 = single chain)
         self.fused_stack = True    # one-launch cluster kernel for the whole stack when the shape allows it
         self.fused_stack_max_groups = 12
+        # batches with more clip groups than one launch holds are cut into sub-batches of `chunk_groups` groups that go
+        # through the SAME one-launch stack (alternating over two streams), so a clip's output bits never depend on the
+        # batch it arrives in; False = use the per-step kernels for such batches (different rounding points, ~1e-3 apart)
+        self.chunk_large_batches = True
+        self.chunk_groups = 8
         self.split_clusters = True   # 8-11 clip groups: 7 as 16-CTA clusters + the rest as 8-CTA clusters, concurrently
         self.stack_cluster_size = 0  # 0 = automatic; 8 / 16 force the cluster size of the one-launch stack (disables the split)
         self._resident_counter = None   # int32 [2] CUDA tensor while runner.PipelinedVisualEncoderPlan captures (ops.gate_wait)
@@ -134,6 +140,8 @@ class Encoder(nn.Module):
         self.__dict__.setdefault("parallel_chains", 4)
         self.__dict__.setdefault("fused_stack", True)
         self.__dict__.setdefault("fused_stack_max_groups", 12)
+        self.__dict__.setdefault("chunk_large_batches", True)
+        self.__dict__.setdefault("chunk_groups", 8)
         self.__dict__.setdefault("split_clusters", True)
         self.__dict__.setdefault("stack_cluster_size", 0)
         self.__dict__.setdefault("_resident_counter", None)
@@ -150,6 +158,16 @@ class Encoder(nn.Module):
     def _cache_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
+    def invalidate_packed(self):
+        """Drop the packed (bf16 / enc16, BN-folded) weight cache.  The cache key is (data_ptr, tensor._version) of every
+        parameter and buffer, which `load_state_dict`, optimizer steps and `.to()` all change; edits THROUGH `.data`
+        (`p.data.copy_()`, `m.weight.data.normal_()`) do not bump the version counter, so call this after them."""
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _get_packed(self):
         key = self._cache_key()
         pk = self._packed
@@ -157,7 +175,7 @@ class Encoder(nn.Module):
             return pk
         pk = _PackedEncoder()
         pk.key = key
-        pk.w_in = ops.cast_bf16(self.linear_in.weight.detach().contiguous())
+        pk.w_in = ops.cast_enc16(self.linear_in.weight.detach().contiguous())
         pk.layers = []
         nl, hk, dm, di = len(self.layer_stack), self.n_head * self.d_k, self.d_model, self.d_inner
         dev = self.linear_in.weight.device
@@ -168,11 +186,11 @@ class Encoder(nn.Module):
                    g_in=self.layer_norm_in.weight.detach().float().contiguous(),
                    be_in=self.layer_norm_in.bias.detach().float().contiguous(),
                    pe=self.positional_encoding.pe[0],
-                   w_heads=torch.empty((nl * 3 * hk, dm), dtype=torch.bfloat16, device=dev),
+                   w_heads=torch.empty((nl * 3 * hk, dm), dtype=ops.enc16_dtype(), device=dev),
                    b_heads=torch.empty((nl * 3 * hk,), dtype=torch.float32, device=dev),
-                   w_fc=torch.empty((nl * dm, hk), dtype=torch.bfloat16, device=dev),
-                   w_1=torch.empty((nl * di, dm), dtype=torch.bfloat16, device=dev),
-                   w_2=torch.empty((nl * dm, di), dtype=torch.bfloat16, device=dev))
+                   w_fc=torch.empty((nl * dm, hk), dtype=ops.enc16_dtype(), device=dev),
+                   w_1=torch.empty((nl * di, dm), dtype=ops.enc16_dtype(), device=dev),
+                   w_2=torch.empty((nl * dm, di), dtype=ops.enc16_dtype(), device=dev))
 
         def cat(ts):
             return (torch.cat([t_.detach().float().reshape(-1) for t_ in ts]).contiguous() if ts
@@ -187,10 +205,10 @@ class Encoder(nn.Module):
         stk["be2"] = cat([l_.pos_ffn.layer_norm.bias for l_ in self.layer_stack])
         for li, lyr in enumerate(self.layer_stack):
             a, f = lyr.slf_attn, lyr.pos_ffn
-            wqkv = torch.empty((3 * hk, self.d_model), dtype=torch.bfloat16, device=a.w_qs.weight.device)
-            ops.cast_bf16(a.w_qs.weight.detach().contiguous(), out=wqkv[0:hk])
-            ops.cast_bf16(a.w_ks.weight.detach().contiguous(), out=wqkv[hk:2 * hk])
-            ops.cast_bf16(a.w_vs.weight.detach().contiguous(), out=wqkv[2 * hk:3 * hk])
+            wqkv = torch.empty((3 * hk, self.d_model), dtype=ops.enc16_dtype(), device=a.w_qs.weight.device)
+            ops.cast_enc16(a.w_qs.weight.detach().contiguous(), out=wqkv[0:hk])
+            ops.cast_enc16(a.w_ks.weight.detach().contiguous(), out=wqkv[hk:2 * hk])
+            ops.cast_enc16(a.w_vs.weight.detach().contiguous(), out=wqkv[2 * hk:3 * hk])
             bqkv = torch.cat([a.w_qs.bias.detach(), a.w_ks.bias.detach(), a.w_vs.bias.detach()]).contiguous()
             # head-major copy (q_h | k_h | v_h per head) for the fused projection + attention kernel
             wheads, bheads = ops.pack_qkv_heads(wqkv[0:hk], wqkv[hk:2 * hk], wqkv[2 * hk:3 * hk],
@@ -201,9 +219,9 @@ class Encoder(nn.Module):
             pk.layers.append(dict(
                 wqkv=wqkv, bqkv=bqkv,
                 wheads=stk["w_heads"][li * 3 * hk:(li + 1) * 3 * hk], bheads=stk["b_heads"][li * 3 * hk:(li + 1) * 3 * hk],
-                wfc=ops.cast_bf16(a.fc.weight.detach().contiguous(), out=stk["w_fc"][li * dm:(li + 1) * dm]),
-                w1=ops.cast_bf16(f.w_1.weight.detach().contiguous(), out=stk["w_1"][li * di:(li + 1) * di]),
-                w2=ops.cast_bf16(f.w_2.weight.detach().contiguous(), out=stk["w_2"][li * dm:(li + 1) * dm])))
+                wfc=ops.cast_enc16(a.fc.weight.detach().contiguous(), out=stk["w_fc"][li * dm:(li + 1) * dm]),
+                w1=ops.cast_enc16(f.w_1.weight.detach().contiguous(), out=stk["w_1"][li * di:(li + 1) * di]),
+                w2=ops.cast_enc16(f.w_2.weight.detach().contiguous(), out=stk["w_2"][li * dm:(li + 1) * dm])))
         pk.stacked = stk
         self._packed = pk
         return pk
@@ -214,7 +232,7 @@ class Encoder(nn.Module):
         Larger batches fill the machine with the per-step kernels instead."""
         if return_attns or not self.fused_stack or len(self.layer_stack) == 0:
             return False
-        if t > 128 or -(-n // max(1, 128 // t)) > self.fused_stack_max_groups:
+        if t > 128 or (not self.chunk_large_batches and -(-n // max(1, 128 // t)) > self.fused_stack_max_groups):
             return False
         if not ops.encoder_stack_supported(self.n_head, self.d_k, self.d_v, self.d_model, self.d_input, self.d_inner,
                                            t, len(self.layer_stack)):
@@ -238,7 +256,7 @@ class Encoder(nn.Module):
         lens_c = None if lengths is None else lengths[n0:n1]
         pe = self.positional_encoding.pe[0]
         last = len(self.layer_stack) - 1
-        x16 = ops.cast_bf16(xs)
+        x16 = ops.cast_enc16(xs)
         # encoder.py:53-55 — LN(linear_in(x)) + PE in one launch ; no pad mask at this point
         x32, x16 = ops.linear_ln(x16, pk.w_in, self.layer_norm_in.weight.detach(), self.layer_norm_in.bias.detach(),
                                bias=self.linear_in.bias.detach(), pe=pe, T=t, eps=self.layer_norm_in.eps,
@@ -275,6 +293,9 @@ class Encoder(nn.Module):
             raise RuntimeError(f"Encoder: last dim {d_in} != d_input {self.d_input}")
         if t > self.pe_maxlen:
             raise RuntimeError(f"Encoder: T={t} exceeds pe_maxlen={self.pe_maxlen}")
+        if t > 128:
+            raise RuntimeError(f"Encoder (libsblk): T={t} > 128 frames per clip is not implemented (attention tiles hold "
+                               f"one clip; the reference allows up to pe_maxlen={self.pe_maxlen}); no fallback path")
         lens = [int(v) for v in input_lengths]
         if len(lens) != n:
             raise RuntimeError(f"Encoder: {len(lens)} input_lengths for batch {n}")
@@ -304,9 +325,29 @@ class Encoder(nn.Module):
                 # the whole stack as ONE launch: a cluster per clip group, no inter-group synchronisation
                 stk = pk.stacked
                 scale = 1.0 / self.layer_stack[0].slf_attn.temperature
-                x16 = self._x16_override if self._x16_override is not None else ops.cast_bf16(x)
+                x16 = self._x16_override if self._x16_override is not None else ops.cast_enc16(x)
                 g_clips = max(1, 128 // t)
                 groups = -(-n // g_clips)
+                if groups > self.fused_stack_max_groups:
+                    # large batch: sub-batches of whole clip groups through the same kernel, two launches in flight
+                    # (2 x 8 clusters of 8 CTAs = 128 SMs); cluster sizes 8 / 16 are bit-identical, so is any chunking
+                    step = max(1, int(self.chunk_groups)) * g_clips
+                    main = torch.cuda.current_stream()
+                    side = self._side_streams(x.device, 1)[0]
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                    side.wait_event(fork)
+                    for ci, n0 in enumerate(range(0, n, step)):
+                        n1 = min(n, n0 + step)
+                        with torch.cuda.stream(side if ci & 1 else main):
+                            ops.encoder_stack(x16[n0 * t:n1 * t], stk, n1 - n0, t,
+                                              lengths=None if lengths is None else lengths[n0:n1], scale=scale,
+                                              eps=self.layer_norm_in.eps, out=out[n0 * t:n1 * t],
+                                              cluster_size=self.stack_cluster_size or 8)
+                    join = torch.cuda.Event()
+                    join.record(side)
+                    main.wait_event(join)
+                    return (out.view(n, t, self.d_model),)
                 if self.split_clusters and self.stack_cluster_size == 0 and 7 < groups <= 11:
                     # Only 7 clusters of 16 CTAs are co-resident on a B200, and 16-CTA clusters are the faster ones (each
                     # CTA streams half the weights).  The first 7 clip groups run as 16-CTA clusters; the remaining 1-4

@@ -13,6 +13,17 @@ from . import _lib
 
 BF16 = torch.bfloat16
 F32 = torch.float32
+_ENC16 = None
+
+
+def enc16_dtype():
+    """torch dtype of the transformer encoder's 16-bit GEMM / attention operands ("enc16", include/sblk.h): float16 in
+    the default build (LayerNorm-bounded values: 3 more mantissa bits than bf16 at the same tcgen05 kind::f16 rate),
+    bfloat16 when libsblk was built with -DSBLK_ENC_FP16=0.  The convolutional trunk is always bf16."""
+    global _ENC16
+    if _ENC16 is None:
+        _ENC16 = torch.float16 if int(_lib.load().sblk_enc16_format()) == 1 else torch.bfloat16
+    return _ENC16
 
 
 def _stream():
@@ -121,6 +132,17 @@ def cast_bf16(x, out=None):
         out = torch.empty(x.shape, dtype=BF16, device=x.device)
     _req(out, BF16, "out")
     _call("sblk_cast_f32_bf16", f"cast n={x.numel()}", 0, 6 * x.numel(), _p(x), _p(out), x.numel(), _stream())
+    return out
+
+
+def cast_enc16(x, out=None):
+    """fp32 -> the encoder's 16-bit operand format (weights [out,in] are already K-major; fp16 saturates at 65504)."""
+    _req(x, F32, "x")
+    e16 = enc16_dtype()
+    if out is None:
+        out = torch.empty(x.shape, dtype=e16, device=x.device)
+    _req(out, e16, "out")
+    _call("sblk_cast_f32_enc16", f"cast n={x.numel()}", 0, 6 * x.numel(), _p(x), _p(out), x.numel(), _stream())
     return out
 
 
@@ -349,32 +371,35 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     return out
 
 
-def avgpool(x, want_f32=True, want_bf16=False, out_f32=None, out_bf16=None, scale=None):
-    """bf16 NHWC [F, ..., C] -> (fp32 [F, C] | None, bf16 [F, C] | None) mean over the pixels, optionally times the
-    fp32 factor `scale` [F, C] (dropout mask / (1 - p) drawn ahead of time)."""
-    _req(x, BF16, "x"); _req(out_f32, F32, "out_f32"); _req(out_bf16, BF16, "out_bf16"); _req(scale, F32, "scale")
+def avgpool(x, want_f32=True, want_bf16=False, out_f32=None, out_bf16=None, scale=None, enc16=False):
+    """bf16 NHWC [F, ..., C] -> (fp32 [F, C] | None, 16-bit [F, C] | None) mean over the pixels, optionally times the
+    fp32 factor `scale` [F, C] (dropout mask / (1 - p) drawn ahead of time).  enc16=True writes the 16-bit copy in the
+    encoder's operand format (enc16_dtype(): it is the encoder stack's x_in) instead of bf16."""
+    o16_dt = enc16_dtype() if enc16 else BF16
+    _req(x, BF16, "x"); _req(out_f32, F32, "out_f32"); _req(out_bf16, o16_dt, "out_bf16"); _req(scale, F32, "scale")
     f, c = x.shape[0], x.shape[-1]
     hw = x.numel() // (f * c)
     for name, t_ in (("out_f32", out_f32), ("out_bf16", out_bf16), ("scale", scale)):
         if t_ is not None and t_.numel() != f * c:
             raise RuntimeError(f"avgpool: {name} has {t_.numel()} elements, expected {f * c}")
     o32 = out_f32 if out_f32 is not None else (torch.empty((f, c), dtype=F32, device=x.device) if want_f32 else None)
-    o16 = out_bf16 if out_bf16 is not None else (torch.empty((f, c), dtype=BF16, device=x.device) if want_bf16 else None)
+    o16 = out_bf16 if out_bf16 is not None else (torch.empty((f, c), dtype=o16_dt, device=x.device) if want_bf16 else None)
     _call("sblk_avgpool_scale_fwd", f"avgpool HW={hw} C={c}", 0, 2 * x.numel() + (4 if o32 is not None else 0) * f * c +
           (2 if o16 is not None else 0) * f * c + (4 if scale is not None else 0) * f * c,
-          _p(x), _p(scale), _p(o32), _p(o16), f, hw, c, _stream())
+          _p(x), _p(scale), _p(o32), _p(o16), f, hw, c, 1 if enc16 else 0, _stream())
     return o32, o16
 
 
 # ------------------------------------------------------------------------------------ encoder
+# (16-bit operands of everything below are in the encoder operand format, enc16_dtype())
 def gemm(a, w, bias=None, residual=None, relu=False, out_bf16=False, out_f32=False):
     """a bf16 [M,K], w bf16 [N,K] -> (bf16 [M,N] | None, fp32 [M,N] | None)."""
-    _req(a, BF16, "a"); _req(w, BF16, "w"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
+    _req(a, enc16_dtype(), "a"); _req(w, enc16_dtype(), "w"); _req(bias, F32, "bias"); _req(residual, enc16_dtype(), "residual")
     m, k = a.shape
     n, k2 = w.shape
     if k2 != k:
         raise RuntimeError(f"gemm: K mismatch {k} vs {k2}")
-    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if out_bf16 else None
+    o16 = torch.empty((m, n), dtype=enc16_dtype(), device=a.device) if out_bf16 else None
     o32 = torch.empty((m, n), dtype=F32, device=a.device) if out_f32 else None
     _call("sblk_gemm_fwd", f"gemm N={n} K={k}", 2 * m * n * k,
           2 * (m * k + n * k) + m * n * ((2 if out_bf16 else 0) + (4 if out_f32 else 0)),
@@ -390,7 +415,7 @@ def add_layernorm(x, gamma, beta, residual=None, pe=None, lengths=None, T=1, eps
     if out_f32 is not None and tuple(out_f32.shape) != (m, d):
         raise RuntimeError(f"add_layernorm: out_f32 shape {tuple(out_f32.shape)} != {(m, d)}")
     o32 = out_f32 if out_f32 is not None else (torch.empty((m, d), dtype=F32, device=x.device) if want_f32 else None)
-    o16 = torch.empty((m, d), dtype=BF16, device=x.device) if want_bf16 else None
+    o16 = torch.empty((m, d), dtype=enc16_dtype(), device=x.device) if want_bf16 else None
     _call("sblk_add_layernorm_fwd", "add_layernorm", 0,
           m * d * (4 + (4 if residual is not None else 0) + (4 if want_f32 else 0) + (2 if want_bf16 else 0)),
           _p(x), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths), _p(o32), _p(o16), m, T, d, eps, _stream())
@@ -401,7 +426,7 @@ def gemm_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, 
             want_bf16=True, out_f32=None):
     """LayerNorm(a @ w.T + bias + residual) * gamma + beta (+ pe[m % T]) (* pad mask) in one launch.
     a bf16 [M,K], w bf16 [512,K], residual fp32 [M,512] -> (fp32 [M,512] | None, bf16 [M,512] | None)."""
-    _req(a, BF16, "a"); _req(w, BF16, "w"); _req(bias, F32, "bias"); _req(residual, F32, "residual")
+    _req(a, enc16_dtype(), "a"); _req(w, enc16_dtype(), "w"); _req(bias, F32, "bias"); _req(residual, F32, "residual")
     _req(gamma, F32, "gamma"); _req(beta, F32, "beta"); _req(pe, F32, "pe"); _req(lengths, torch.int32, "lengths")
     _req(out_f32, F32, "out_f32")
     m, k = a.shape
@@ -413,7 +438,7 @@ def gemm_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, 
     if out_f32 is not None and tuple(out_f32.shape) != (m, n):
         raise RuntimeError(f"gemm_ln: out_f32 shape {tuple(out_f32.shape)} != {(m, n)}")
     o32 = out_f32 if out_f32 is not None else (torch.empty((m, n), dtype=F32, device=a.device) if want_f32 else None)
-    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if want_bf16 else None
+    o16 = torch.empty((m, n), dtype=enc16_dtype(), device=a.device) if want_bf16 else None
     _call("sblk_gemm_ln_fwd", f"gemm+ln K={k}", 2 * m * n * k,
           2 * (m * k + n * k) + m * n * ((4 if residual is not None else 0) + (4 if o32 is not None else 0) +
                                          (2 if want_bf16 else 0)),
@@ -429,7 +454,7 @@ def linear_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None
     Strategy by token count: when a 128-row tiling already fills the machine the cluster-fused kernel (gemm_ln) does
     it in one launch; at small M (the BASELINE 928 tokens) the GEMM is operand-delivery bound per SM, so it runs
     split-K over all SMs into fp32 partials that the LayerNorm kernel sums (deterministic, no atomics)."""
-    _req(a, BF16, "a"); _req(w, BF16, "w")
+    _req(a, enc16_dtype(), "a"); _req(w, enc16_dtype(), "w")
     m, k = a.shape
     n = w.shape[0]
     splits = int(_lib.load().sblk_gemm_splitk_plan(m, n, k))
@@ -446,7 +471,7 @@ def linear_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None
     _call("sblk_gemm_splitk_fwd", f"gemm splitK={splits} N={n} K={k}", 2 * m * n * k,
           2 * (m * k + n * k) + 4 * splits * m * n, _p(a), _p(w), None, _p(parts), m, n, k, splits, _stream())
     o32 = out_f32 if out_f32 is not None else torch.empty((m, n), dtype=F32, device=a.device)
-    o16 = torch.empty((m, n), dtype=BF16, device=a.device) if want_bf16 else None
+    o16 = torch.empty((m, n), dtype=enc16_dtype(), device=a.device) if want_bf16 else None
     _call("sblk_sum_layernorm_fwd", f"sum{splits}+layernorm", 0,
           m * n * (4 * splits + (4 if residual is not None else 0) + 4 + (2 if want_bf16 else 0)),
           _p(parts), splits, _p(bias), _p(residual), _p(gamma), _p(beta), _p(pe), _p(lengths), _p(o32), _p(o16), m, T, n,
@@ -458,7 +483,7 @@ def pack_qkv_heads(wq, wk, wv, bq, bk, bv, h, d_k=64):
     """bf16 [h*d_k, K] x3 + fp32 [h*d_k] x3 -> head-major (bf16 [h*3*d_k, K], fp32 [h*3*d_k]) for qkv_attention
     (pure re-indexing of already packed weights; no arithmetic)."""
     for t_, n_ in ((wq, "wq"), (wk, "wk"), (wv, "wv")):
-        _req(t_, BF16, n_)
+        _req(t_, enc16_dtype(), n_)
     for t_, n_ in ((bq, "bq"), (bk, "bk"), (bv, "bv")):
         _req(t_, F32, n_)
     k = wq.shape[1]
@@ -469,13 +494,13 @@ def pack_qkv_heads(wq, wk, wv, bq, bk, bv, h, d_k=64):
 
 def qkv_attention(x, w_heads, b_heads, n, t, h, d_k=64, lengths=None, scale=None):
     """x bf16 [n*t, K] -> heads-concatenated self-attention output bf16 [n*t, h*d_k] (projection + attention fused)."""
-    _req(x, BF16, "x"); _req(w_heads, BF16, "w_heads"); _req(b_heads, F32, "b_heads")
+    _req(x, enc16_dtype(), "x"); _req(w_heads, enc16_dtype(), "w_heads"); _req(b_heads, F32, "b_heads")
     _req(lengths, torch.int32, "lengths")
     k = x.shape[1]
     if tuple(x.shape) != (n * t, k) or tuple(w_heads.shape) != (h * 3 * d_k, k) or b_heads.numel() != h * 3 * d_k:
         raise RuntimeError(f"qkv_attention: shapes x{tuple(x.shape)} w{tuple(w_heads.shape)} do not match "
                            f"n={n} t={t} h={h} d_k={d_k}")
-    out = torch.empty((n * t, h * d_k), dtype=BF16, device=x.device)
+    out = torch.empty((n * t, h * d_k), dtype=enc16_dtype(), device=x.device)
     if scale is None:
         scale = 1.0 / (d_k ** 0.5)
     _call("sblk_qkv_attention_fwd", f"qkv+attention T={t}", 2 * n * t * 3 * h * d_k * k + 4 * n * h * t * t * d_k,
@@ -485,10 +510,10 @@ def qkv_attention(x, w_heads, b_heads, n, t, h, d_k=64, lengths=None, scale=None
 
 
 def attention(qkv, n, t, h, d_k=64, lengths=None, want_probs=False, scale=None):
-    _req(qkv, BF16, "qkv"); _req(lengths, torch.int32, "lengths")
+    _req(qkv, enc16_dtype(), "qkv"); _req(lengths, torch.int32, "lengths")
     if tuple(qkv.shape) != (n * t, 3 * h * d_k):
         raise RuntimeError(f"attention: qkv shape {tuple(qkv.shape)} != {(n * t, 3 * h * d_k)}")
-    out = torch.empty((n * t, h * d_k), dtype=BF16, device=qkv.device)
+    out = torch.empty((n * t, h * d_k), dtype=enc16_dtype(), device=qkv.device)
     probs = torch.empty((h * n, t, t), dtype=F32, device=qkv.device) if want_probs else None
     if scale is None:
         scale = 1.0 / (d_k ** 0.5)
@@ -504,13 +529,13 @@ def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layer
 
 
 def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None,
-                  cluster_size=0, resident_counter=None):
+                  cluster_size=0, resident_counter=None, multicast=True):
     """The whole encoder stack in one launch.  x16 bf16 [n*t, d_in]; `stk` = dict of STACKED packed tensors
     (w_in, b_in, g_in, be_in, pe, w_heads, b_heads, w_fc, b_fc, g1, be1, w_1, b_1, w_2, b_2, g2, be2, n_layers, d_inner)
     -> fp32 [n*t, 512]."""
-    _req(x16, BF16, "x16"); _req(lengths, torch.int32, "lengths"); _req(out, F32, "out")
+    _req(x16, enc16_dtype(), "x16"); _req(lengths, torch.int32, "lengths"); _req(out, F32, "out")
     for k_ in ("w_in", "w_heads", "w_fc", "w_1", "w_2"):
-        _req(stk[k_], BF16, k_)
+        _req(stk[k_], enc16_dtype(), k_)
     for k_ in ("b_in", "g_in", "be_in", "pe", "b_heads", "b_fc", "g1", "be1", "b_1", "b_2", "g2", "be2"):
         _req(stk[k_], F32, k_)
     m, d_in = x16.shape
@@ -544,6 +569,7 @@ def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None,
     a.cluster_size = int(cluster_size)   # 0 = automatic
     a.debug_stamps = _p(debug_stamps)   # optional int64 [1 + 4*n_layers, 8] device tensor (profiling aid)
     a.resident_counter = _p(resident_counter)   # optional int32 [2] device tensor (co-scheduling gate, see gate_wait)
+    a.no_multicast = 0 if multicast else 1
     flops = 2 * m * 512 * d_in + nl * (2 * m * 512 * (4 * 512 + 2 * d_inner) + 4 * n * 8 * t * t * 64)
     wbytes = 2 * (512 * d_in + nl * (4 * 512 * 512 + 2 * 512 * d_inner))
     _call("sblk_encoder_stack_fwd", f"encoder stack L={nl} T={t} N={n}", flops, wbytes + m * (2 * d_in + 4 * 512),

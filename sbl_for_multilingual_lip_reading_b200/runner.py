@@ -55,7 +55,32 @@ class VisualEncoderPlan:
             self.ev_out = [torch.cuda.Event() for _ in range(self.slots)]
             self.launches_per_forward = 0
             self._capture()
+            self._pin_captured_state()
         self._i = 0
+
+    # -------------------------------------------------------------------------------------------
+    def _pin_captured_state(self):
+        """A captured graph bakes in raw pointers to tensors the MODULES own as caches: packed weights, the zero-haloed
+        flat workspaces, staged lengths vectors, the uint8 normalisation table.  The plan keeps strong references to all
+        of them (a cache eviction or a re-pack after `load_state_dict` can then never free memory a replay still reads
+        or writes) and records the weight versions it was captured with; `_check_weights` refuses to replay stale ones."""
+        fe, enc = self.frontend, self.encoder
+        self._pinned = (getattr(fe, "_packed", None), getattr(enc, "_packed", None),
+                        dict(getattr(fe, "_flat_ws", {})), dict(getattr(enc, "_len_cache", {})),
+                        dict(getattr(fe, "_lut", {})), getattr(fe, "l2_prefetch_extra", None))
+        self._weights_key = (fe._cache_key(), enc._cache_key())
+
+    def _check_weights(self):
+        if (self.frontend._cache_key(), self.encoder._cache_key()) != self._weights_key:
+            raise RuntimeError("the frontend / encoder weights changed after this plan was captured (load_state_dict or an "
+                               "in-place update): its CUDA graphs still hold the old packed weights — call recapture()")
+
+    def recapture(self):
+        """Re-pack the weights and capture the graphs again (after load_state_dict / an optimizer step)."""
+        self.synchronize()
+        with torch.cuda.device(self.device):
+            self._capture()
+            self._pin_captured_state()
 
     # -------------------------------------------------------------------------------------------
     def _forward_eager(self, x):
@@ -97,6 +122,7 @@ class VisualEncoderPlan:
     # -------------------------------------------------------------------------------------------
     def forward_device(self, slot=0):
         """Replay on the compute stream of the plan; returns the static output tensor [N,T,d_model] fp32."""
+        self._check_weights()
         with torch.cuda.stream(self.compute):
             self.graphs[slot].replay()
         return self.out[slot]
@@ -104,6 +130,7 @@ class VisualEncoderPlan:
     def submit_host(self, x_host, out_host):
         """One pipelined step: x_host pinned fp32 [N,1,T,88,88] -> out_host pinned fp32 [N,T,d_model].
         Asynchronous; returns the event that marks out_host complete."""
+        self._check_weights()
         s = self._i % self.slots
         self._i += 1
         # slot s is reusable once its previous replay finished (input consumed) and its output left the device
@@ -196,7 +223,7 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         # features cross the pipeline stages as the bf16 GEMM operand the encoder stack reads (written by the frontend's
         # last launch — average pool x dropout factor — so the encoder branch of the next replay is the stack kernel
         # alone); `feat` only carries the shape
-        self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=ops.enc16_dtype(), device=dev) for _ in range(2)]
         self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
         self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
         saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail)
@@ -251,6 +278,7 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
     def forward_device(self, slot=0):
         """Replay step `slot`: frontend of x[slot] next to the encoder of the batch replayed before it (the other slot).
         Returns that PREVIOUS batch's static output tensor [N,T,d_model] fp32."""
+        self._check_weights()
         with torch.cuda.stream(self.compute):
             self.graphs[slot].replay()
         return self.out[slot ^ 1]
@@ -258,6 +286,7 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
     def submit_host(self, x_host, out_host):
         """One pipelined step: x_host (pinned) -> device; out_host (pinned) receives the output of the batch submitted
         by the PREVIOUS call (of the warm-up / zero features on the first call).  Returns the completion event."""
+        self._check_weights()
         s = self._i % 2
         self._i += 1
         self.copy_in.wait_event(self.ev_done[s])

@@ -180,6 +180,16 @@ class Lipreading(nn.Module):
     def _cache_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
+    def invalidate_packed(self):
+        """Drop the packed (bf16 / enc16, BN-folded) weight cache.  The cache key is (data_ptr, tensor._version) of every
+        parameter and buffer, which `load_state_dict`, optimizer steps and `.to()` all change; edits THROUGH `.data`
+        (`p.data.copy_()`, `m.weight.data.normal_()`) do not bump the version counter, so call this after them."""
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
     def _get_packed(self):
         key = self._cache_key()
         pk = self._packed
@@ -219,7 +229,7 @@ class Lipreading(nn.Module):
         key = (str(a.data.device if isinstance(a, ops.FlatActs) else a.device), f, p, q, cout, chain)
         ws = self._flat_ws.get(key)
         if ws is None:
-            if len(self._flat_ws) > 16:
+            if len(self._flat_ws) > 16:   # (plans pin the entries their graphs use: runner._pin_captured_state)
                 self._flat_ws.clear()
             dev = a.data.device if isinstance(a, ops.FlatActs) else a.device
             ws = tuple(torch.zeros((ops.flat_rows(f, p, q), cout), dtype=torch.bfloat16, device=dev) for _ in range(2))
@@ -266,7 +276,8 @@ class Lipreading(nn.Module):
                 # head_frac > 0: the first conv of this block is run in two frame ranges — the first one still inside
                 # the head (limited width, next to the other chain), the rest at full width — to use the time by which
                 # the other chain outlasts the head.  Frame ranges of the flat layout are independent (ops.flat_frames).
-                if len(ov) > 3 and ov[3] > 0 and isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
+                if (len(ov) > 3 and ov[3] > 0 and isinstance(a, ops.FlatActs) and stride == 1 and ds is None
+                        and a.f >= 2):
                     split = min(a.f - 1, max(1, int(round(a.f * float(ov[3])))))
                     y = ops.FlatActs(torch.empty_like(a.data), a.f, a.h, a.w)
                     ops.conv3x3_flat(ops.flat_frames(a, 0, split), w1, b1, relu=True,
@@ -314,7 +325,7 @@ class Lipreading(nn.Module):
             end_head()
         tail = self._tail if chain == 0 else None
         if tail is not None:
-            ops.avgpool(a, want_f32=False, out_bf16=tail[1], scale=tail[0])   # feat_out stays unwritten (plan-owned path)
+            ops.avgpool(a, want_f32=False, out_bf16=tail[1], scale=tail[0], enc16=True)   # feat_out stays unwritten (plan-owned path)
         else:
             ops.avgpool(a, out_f32=feat_out)
         if pf_stream is not None:   # join (graph capture needs every forked stream back; no data dependency)

@@ -2,6 +2,7 @@
 loud failure without a GPU."""
 import io
 import json
+import ctypes
 import os
 import pickle
 import re
@@ -38,7 +39,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/sblk.h but not exported by libsblk.so"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == names
-    assert lib.sblk_version() == 100
+    assert lib.sblk_version() == 200
 
 
 def test_library_fails_loudly_without_gpu():
@@ -48,6 +49,33 @@ def test_library_fails_loudly_without_gpu():
     rc = lib.sblk_init()
     assert rc < 0
     assert "cuda" in _lib.last_error().lower()
+
+
+def _integration_snippet():
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        md = f.read()
+    block = md.split("## 3.")[1].split("```python")[1].split("```")[0]
+    return block
+
+
+def test_integration_snippet_matches_the_header():
+    """The ctypes stub INTEGRATION.md shows must bind the function the header declares (argument count and order)."""
+    block = _integration_snippet()
+    m = re.search(r"sblk_conv2d_igemm_fwd\.argtypes = \[(.*?)\]", block)
+    assert m, "no argtypes line in the INTEGRATION.md snippet"
+    shown = [t.strip() for t in m.group(1).split(",")]
+    sig = _lib.SIGNATURES["sblk_conv2d_igemm_fwd"][1]
+    assert len(shown) == len(sig) == 18
+    assert [t == "vp" for t in shown] == [a is ctypes.c_void_p for a in sig]
+    call = re.search(r"lib\.sblk_conv2d_igemm_fwd\((.*?)\)\n", block, re.S).group(1)
+    call = re.sub(r"#.*", "", call)
+    # x.data_ptr() style arguments contain parentheses: count top-level commas
+    depth, nargs = 0, 1
+    for ch in call:
+        depth += ch == "("
+        depth -= ch == ")"
+        nargs += (ch == "," and depth == 0)
+    assert nargs == 18, f"the example call passes {nargs} arguments"
 
 
 def test_sass_is_blackwell_native():
@@ -70,7 +98,8 @@ def test_sass_is_blackwell_native():
             # (the one-launch encoder stack embeds the same per-head attention routine next to its tcgen05 GEMMs)
             assert func is not None and ("attention_kernel" in func or "encoder_stack_kernel" in func), \
                 f"legacy mma.sync in {func}"
-    for name in ("igemm_kernel", "conv3d_bn_relu_pool_kernel", "flatconv3x3_c64_kernel", "encoder_stack_kernel"):
+    for name in ("igemm_kernel", "igemm2_kernel", "conv3d_bn_relu_pool_kernel", "flatconv2_kernel", "gemm_ln512_kernel",
+                 "qkv_attention_kernel", "encoder_stack_kernel"):
         body = [seg for seg in sass.split("Function :") if name in seg.splitlines()[0]]
         assert body and all("UTCHMMA" in seg for seg in body), f"{name} does not use tcgen05.mma"
 

@@ -211,12 +211,12 @@ def test_state_dict_reload_invalidates_packed_weights(dev):
 def test_c_abi_rejects_bad_arguments(dev):
     from sbl_for_multilingual_lip_reading_b200 import ops
     with pytest.raises(RuntimeError, match="multiples of 64"):
-        ops.gemm(torch.zeros(8, 48, dtype=torch.bfloat16, device=dev),
-                 torch.zeros(64, 48, dtype=torch.bfloat16, device=dev), out_f32=True)
+        ops.gemm(torch.zeros(8, 48, dtype=ops.enc16_dtype(), device=dev),
+                 torch.zeros(64, 48, dtype=ops.enc16_dtype(), device=dev), out_f32=True)
     with pytest.raises(RuntimeError, match="only 512"):
         ops.add_layernorm(torch.zeros(4, 256, device=dev), torch.ones(256, device=dev), torch.zeros(256, device=dev))
     with pytest.raises(RuntimeError, match="T=200"):
-        ops.attention(torch.zeros(200, 1536, dtype=torch.bfloat16, device=dev), 1, 200, 8)
+        ops.attention(torch.zeros(200, 1536, dtype=ops.enc16_dtype(), device=dev), 1, 200, 8)
     with pytest.raises(RuntimeError, match="expected dtype"):
         ops.conv2d(torch.zeros(1, 22, 22, 64, device=dev), torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device=dev),
                    torch.zeros(64, device=dev))
@@ -250,18 +250,21 @@ def test_encoder_stack_matches_oracle_and_per_step_kernels(encoder6, dev, n, t, 
             assert float(fused[b, l_:].abs().max() if l_ < t else 0.0) == 0.0
 
 
-def test_encoder_stack_cluster_sizes_agree(encoder6, dev, monkeypatch):
+def test_encoder_stack_cluster_sizes_agree(encoder6, dev):
     """Clusters of 8 and of 16 CTAs, with and without TMA multicast of the activation tiles, are bit-identical
     (LayerNorm statistics are merged from the same sixteen 32-column partials in the same order), so a clip's
     output does not depend on how many clips share its batch."""
     g = torch.Generator().manual_seed(77)
     x = torch.randn(6, 29, 512, generator=g).to(dev)
+    from sbl_for_multilingual_lip_reading_b200 import ops
     outs = []
+    lens = torch.tensor([29, 29, 5, 29, 12, 29], dtype=torch.int32, device=dev)
     with torch.no_grad():
-        for cl, mc in (("16", "1"), ("16", "0"), ("8", "1"), ("8", "0")):
-            monkeypatch.setenv("SBLK_ENC_STACK_CL", cl)
-            monkeypatch.setenv("SBLK_ENC_STACK_MC", mc)
-            outs.append(encoder6(x, [29, 29, 5, 29, 12, 29])[0].clone())
+        stk = encoder6._get_packed().stacked
+        x16 = ops.cast_enc16(x.view(-1, 512).contiguous())
+        for cl, mc in ((16, True), (16, False), (8, True), (8, False)):
+            outs.append(ops.encoder_stack(x16, stk, 6, 29, lengths=lens, cluster_size=cl, multicast=mc).clone())
+        outs.append(encoder6(x, [29, 29, 5, 29, 12, 29])[0].reshape(-1, 512).clone())
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
@@ -272,7 +275,7 @@ def test_encoder_stack_rejects_unsupported_shapes(dev):
     enc.load_state_dict(synth.encoder_state_dict(4, 1))
     enc = enc.to(dev).eval()
     stk = enc._get_packed().stacked
-    x16 = torch.zeros(4 * 130, 512, dtype=torch.bfloat16, device=dev)
+    x16 = torch.zeros(4 * 130, 512, dtype=ops.enc16_dtype(), device=dev)
     with pytest.raises(RuntimeError, match="T <= 128"):
         ops.encoder_stack(x16, stk, 4, 130)
     with pytest.raises(RuntimeError, match="workspace"):
@@ -445,10 +448,12 @@ def test_avgpool_with_dropout_factor_matches_pool_then_dropout(dev):
     torch.manual_seed(5)
     scale = F.dropout(torch.ones_like(pooled), p=0.5)
     got32, got16 = ops.avgpool(x, want_f32=True, want_bf16=True, scale=scale)
+    _, gote16 = ops.avgpool(x, want_f32=False, want_bf16=True, scale=scale, enc16=True)
     torch.cuda.synchronize(dev)
     assert 0.4 < (want == 0).float().mean().item() < 0.6
     assert torch.equal(got32, want)
     assert torch.equal(got16, ops.cast_bf16(want))
+    assert gote16.dtype == ops.enc16_dtype() and torch.equal(gote16, ops.cast_enc16(want))
     with pytest.raises(RuntimeError):
         ops.avgpool(x, scale=scale[:10])
 
@@ -646,3 +651,26 @@ def test_p2p_gather_two_gpus():
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("p2p gather OK") == 2
+
+
+def test_integration_md_ctypes_snippet_runs(dev):
+    """INTEGRATION.md §3 shows the ctypes stub a maintainer would write against include/sblk.h: execute exactly that
+    snippet and check what it computed against torch's conv2d on the same bf16 operands."""
+    import os
+    import torch.nn.functional as F
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "INTEGRATION.md")) as f:
+        md = f.read()
+    block = md.split("## 3.")[1].split("```python")[1].split("```")[0]
+    ns = {}
+    cwd = os.getcwd()
+    os.chdir(root)          # the snippet loads the library by its repo-relative path
+    try:
+        torch.manual_seed(0)
+        exec(compile(block, "INTEGRATION.md#3", "exec"), ns)
+    finally:
+        os.chdir(cwd)
+    torch.cuda.synchronize(dev)
+    x, wp, out = ns["x"], ns["wp"], ns["out"]
+    want = F.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wp.float().permute(0, 3, 1, 2), padding=1)).permute(0, 2, 3, 1)
+    assert rel_fro(out, want) < REL_TOL
