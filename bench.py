@@ -710,6 +710,112 @@ def run_b200_arm(args):
     return 0
 
 
+def run_config4_sweep(args):
+    """BASELINE configs[4]: the full SBL multilingual model, teacher-forced forward (`Transformer.forward`,
+    transformer/transformer.py:22-43) — the B200 visual frontend + encoder with the UNMODIFIED reference bidirectional
+    decoder (oracle/_ref) on top — over a batch sweep, next to the all-reference fp32 CUDA model (cuDNN / cuBLAS, TF32
+    off) on the same inputs.  One rank per GPU, the batch sharded across ranks (no collective: every rank decodes its own
+    clips).  Prints ONE JSON line; wall-clock timing with synchronize on both sides, max over ranks."""
+    import random
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sblk_bench_nccl_%h_%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    from oracle import ref_runtime
+    from sbl_for_multilingual_lip_reading_b200 import dropin, ops, sharding, synth
+    ops.init()
+    ref_runtime.fp32_exact()
+    R = ref_runtime.load_reference("sbl")
+    sd = dict(synth.frontend_state_dict(1, prefix="visual_frontend."))
+    sd.update(synth.encoder_state_dict(2, 6, prefix="encoder."))
+    ref = ref_runtime.build_sbl_reference(R, sd).to(dev).eval()
+    with dropin.patched_reference(R.dir):
+        import transformer.encoder as tenc
+        import transformer.transformer as ttr
+        torch.manual_seed(7)
+        enc = tenc.Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+        dec = R.Decoder(0, 1, 58, 512, 6, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1,
+                        pe_maxlen=5000)
+        ours = ttr.Transformer(enc, dec, None)
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev).eval()
+    T = 30
+    rows = []
+    for gb in [int(v) for v in args.config4_batches.split(",")]:
+        n = max(1, gb // world)
+        g = torch.Generator().manual_seed(11 + rank)
+        x = synth.synthetic_clips(n, T, seed=900 + rank)[:, 0].to(dev)            # [n,T,88,88] as train.py feeds it
+        tgt = torch.full((n, 14), -1, dtype=torch.long)
+        for i in range(n):   # data_gen.py:297-302
+            ln = int(torch.randint(3, 12, (1,), generator=g))
+            tgt[i, :ln] = torch.randint(2, 58, (ln,), generator=g)
+        tgt_r = tgt.clone()
+        for i in range(n):
+            ln = int((tgt[i] >= 0).sum())
+            tgt_r[i, :ln] = tgt[i, :ln].flip(0)
+        tgt, tgt_r = tgt.to(dev), tgt_r.to(dev)
+
+        def timed(model, reps):
+            with torch.no_grad():
+                random.seed(7); torch.manual_seed(5)
+                out = model(x, tgt, tgt_r)
+                torch.cuda.synchronize(dev)
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    out = model(x, tgt, tgt_r)
+                torch.cuda.synchronize(dev)
+                return sharding.max_over_ranks((time.perf_counter() - t0) / reps, dev), out
+
+        def timed_encoder(model, reps):
+            with torch.no_grad():
+                xi = x.unsqueeze(4).permute(0, 4, 1, 2, 3)
+                f = model.visual_frontend(xi); model.encoder(f, [T] * n)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    f = model.visual_frontend(xi)
+                    model.encoder(f, [T] * n)
+                torch.cuda.synchronize(dev)
+                return sharding.max_over_ranks((time.perf_counter() - t0) / reps, dev)
+
+        reps = max(2, min(args.steps, 10))
+        t_ours, o1 = timed(ours, reps)
+        t_ref, o2 = timed(ref, reps)
+        e_ours, e_ref = timed_encoder(ours, reps), timed_encoder(ref, reps)
+        rows.append({"global_batch": n * world, "clips_per_gpu": n,
+                     "b200_dropins_clips_per_s": n * world / t_ours, "reference_cuda_fp32_clips_per_s": n * world / t_ref,
+                     "ms_per_forward": {"b200_dropins": 1e3 * t_ours, "reference_cuda_fp32": 1e3 * t_ref},
+                     "visual_encoder_ms": {"b200_dropins": 1e3 * e_ours, "reference_cuda_fp32": 1e3 * e_ref},
+                     "decoder_share_of_forward_b200": 1.0 - e_ours / t_ours})
+    if rank == 0:
+        line = {"metric": "sbl_full_model_teacher_forced_forward_clips_per_sec", "unit": UNIT, "n_gpus": world,
+                "config": {"workload": "BASELINE configs[4]: full SBL multilingual model teacher-forced forward (B200 visual "
+                                       "frontend + encoder, reference bidirectional decoder from oracle/_ref on top), "
+                                       f"{T}-frame clips, batch sweep, batch sharded over {world} GPU(s)",
+                           "decoder": "unmodified reference Decoder.forward (decoder.py:79-191): 16 steps x 2 directions x "
+                                      "6 layers, full-prefix recompute, torch CUDA fp32",
+                           "always_on_dropout": True},
+                "sweep": rows, "data": "synthetic", "timing": "wall clock, synchronize both sides, max over ranks"}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -727,6 +833,9 @@ def main():
     ap.add_argument("--inline-gather", action="store_true",
                     help="multi-GPU, pipelined plan: gather each step's output in stream after the replay instead of on a "
                          "side stream next to the following step's replay")
+    ap.add_argument("--workload", default="visual_encoder", choices=["visual_encoder", "config4"],
+                    help="config4 = BASELINE configs[4] sweep: full SBL model (reference decoder on the drop-ins)")
+    ap.add_argument("--config4-batches", default="16,32,64,128,256,512")
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the BASELINE configs[2] (8 clips x 40 frames per GPU) leg")
@@ -744,6 +853,8 @@ def main():
                              f"--nproc-per-node {args.gpus} (one rank per GPU)")
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "config4":
+        return run_config4_sweep(args)
     return run_b200_arm(args)
 
 

@@ -68,10 +68,16 @@ class VisualEncoderPlan:
         self._pinned = (getattr(fe, "_packed", None), getattr(enc, "_packed", None),
                         dict(getattr(fe, "_flat_ws", {})), dict(getattr(enc, "_len_cache", {})),
                         dict(getattr(fe, "_lut", {})), getattr(fe, "l2_prefetch_extra", None))
-        self._weights_key = (fe._cache_key(), enc._cache_key())
+        # the parameter / buffer OBJECTS are fixed for a module's life (load_state_dict, .to() and optimizers update them
+        # in place), so the per-replay check walks a cached flat list instead of the module tree (~20 us)
+        self._wtensors = [t for m in (fe, enc) for t in list(m.parameters()) + list(m.buffers())]
+        self._weights_key = self._weights_now()
+
+    def _weights_now(self):
+        return tuple([(t.data_ptr(), t._version) for t in self._wtensors])
 
     def _check_weights(self):
-        if (self.frontend._cache_key(), self.encoder._cache_key()) != self._weights_key:
+        if self._weights_now() != self._weights_key:
             raise RuntimeError("the frontend / encoder weights changed after this plan was captured (load_state_dict or an "
                                "in-place update): its CUDA graphs still hold the old packed weights — call recapture()")
 
