@@ -237,6 +237,72 @@ typedef struct sblk_encoder_stack_args {
 long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
 int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);
 
+
+/* ---- training path: forward with batch statistics + backward (BASELINE configs[3]) ---------------------------------
+ * replaces: `model.train()` + `loss.backward()` through the hot path,
+ * VSR_visual_frontend_pretraining_on_LRW_LRW1000_classify/train.py:107-146 and SBL/train.py:177-210 (autograd of the stock
+ * nn.Conv3d / Conv2d / BatchNorm / ReLU / MaxPool3d / AdaptiveAvgPool2d / Linear / LayerNorm / softmax call sites cited
+ * above).  Every contraction of the backward pass runs on the forward tcgen05 kernels: dgrad of a stride-1 3x3 conv is
+ * sblk_conv2d_igemm_fwd with the flipped, transposed filter (stride 2: over the zero-stuffed gradient), wgrad and the
+ * Linear backward are sblk_gemm_fmt_fwd over K-major operands produced by sblk_transpose16 / sblk_im2col_t.  Gradients
+ * are bf16 (fp32 for parameters and the encoder's residual stream); saved encoder activations are enc16. */
+/* sblk_gemm_fwd with an explicit 16-bit operand format (fp16 = 0: bf16, 1: IEEE fp16) and optional split-K:
+ * splits == 1 -> out_16 and/or out_f32 [M,N]; splits > 1 -> out_f32 is [splits][M,N] raw partials ((K/64) % splits == 0). */
+int sblk_gemm_fmt_fwd(const void* a, const void* w, const float* bias, const void* residual_16, void* out_16,
+                      float* out_f32, int M, int N, int K, int relu, int splits, int fp16, void* stream);
+/* out[c][r] = in[r][c] for 16-bit elements: in [R, C] (row pitch ld_in), out [C, ld_out], columns R..ld_out-1 zero
+ * (K padding of the wgrad GEMMs).  convert = 1 re-rounds IEEE fp16 input to bf16. */
+int sblk_transpose16(const void* in, void* out, long long R, int C, long long ld_in, long long ld_out, int convert,
+                     void* stream);
+/* Transposed im2col of NHWC bf16 [F,H,W,C] for an R x S / stride / pad conv: out[(r*S + s)*C + c][m] (row pitch ld_out,
+ * zero outside the image and for m >= F*P*Q): the K-major B operand of the wgrad GEMM dW = dY^T col.  C % 64 == 0. */
+int sblk_im2col_t(const void* x, void* out, int F, int H, int W, int C, int R, int S, int stride, int pad,
+                  long long ld_out, void* stream);
+/* im2col of the Conv3d stem (x fp32 [N,T,88,88]; k = (dt*7 + r)*7 + s, 245 taps zero-padded to 256):
+ * transposed = 0 -> bf16 [N*T*44*44, 256] (A operand of the training-forward GEMM); 1 -> bf16 [256, ld_out] (wgrad). */
+int sblk_stem_im2col(const float* x, void* out, int N, int T, int transposed, long long ld_out, void* stream);
+/* Deterministic per-channel reductions over the rows of [M, C] -> out_2C = (first[C], second[C]):
+ *   mode 0: a 16-bit -> (sum, sum of squares)        mode 2: a fp32 -> (sum, -)        mode 4: a 16-bit -> (sum, -)
+ *   mode 1: BatchNorm backward sums (sum dz, sum dz * xhat): a = dy bf16, b = BN output bf16 (ReLU mask) or NULL,
+ *           c = raw conv output bf16, mean / rstd [C].
+ * workspace: sblk_colreduce_workspace_floats(C) floats.  fp16: 16-bit inputs of modes 0 / 4 are IEEE fp16. */
+long long sblk_colreduce_workspace_floats(int C);
+int sblk_colreduce(int mode, const void* a, const void* b, const void* c, const float* mean, const float* rstd,
+                   long long M, int C, int fp16, float* workspace, float* out_2C, void* stream);
+/* (sum, sumsq)[2C] over `count` rows -> mean, rstd = 1/sqrt(biased var + eps); running stats (may be NULL) updated with
+ * `momentum` and the unbiased variance (torch.nn.BatchNorm training semantics). */
+int sblk_bn_finalize(const float* sums_2C, float* mean, float* rstd, float* running_mean, float* running_var, int C,
+                     float count, float eps, float momentum, void* stream);
+/* out = act((x - mean) * rstd * gamma + beta (+ residual)), bf16 [M, C], C % 8 == 0. */
+int sblk_bn_apply_fwd(const void* x, const void* residual, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, void* out, long long M, int C, int relu, void* stream);
+/* dz = dy * (out_act > 0) (out_act NULL: no ReLU); dx = gamma * rstd * (dz - sum_dz/M - xhat * sum_dzx/M) with sums_2C from
+ * sblk_colreduce mode 1; dres (optional) receives dz (gradient of the residual branch). */
+int sblk_bn_bwd(const void* dy, const void* out_act, const void* x, const float* mean, const float* rstd,
+                const float* gamma, const float* sums_2C, void* dx, void* dres, long long M, int C, void* stream);
+/* MaxPool 3x3 / stride 2 / pad 1 over NHWC bf16 (the spatial part of MaxPool3d((1,3,3),(1,2,2),(0,1,1))), and its backward
+ * (gradient to the first maximum of every window, PyTorch's tie rule). */
+int sblk_maxpool3x3s2_fwd(const void* x, void* out, int F, int H, int W, int C, void* stream);
+int sblk_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int F, int H, int W, int C, void* stream);
+/* AdaptiveAvgPool2d(1) backward: dx bf16 [F, HW, C] = dfeat fp32 [F, C] / HW. */
+int sblk_avgpool_bwd(const float* dfeat, void* dx, long long F, int HW, int C, void* stream);
+/* out [F,H,W,C] = 0 except out[f,2p,2q,:] = dy[f,p,q,:] (dgrad of a stride-2 conv = stride-1 conv over this). */
+int sblk_zero_stuff2(const void* dy, void* out, int F, int H, int W, int C, int P, int Q, void* stream);
+/* dh (bf16, in place) *= (h > 0), h enc16: ReLU backward of the FFN hidden layer. */
+int sblk_relu_bwd(void* dh_bf16, const void* h_enc16, long long n, void* stream);
+/* LayerNorm(512) backward from the saved pre-normalisation sum z fp32 [M,512]: dz (fp32 and/or bf16) and
+ * dgamma_dbeta_1024 = (dgamma[512], dbeta[512]); rows with t >= lengths[m / T] carry no gradient (`*= non_pad_mask`). */
+long long sblk_ln_bwd_workspace_floats(void);
+int sblk_ln_bwd(const float* dy, const float* z, const float* gamma, const int* lengths, float* dz_f32, void* dz_bf16,
+                float* dgamma_dbeta_1024, float* workspace, int M, int T, float eps, void* stream);
+/* Training-mode scaled-dot-product self-attention (T <= 64, d_k = 64): qkv enc16 [N*T, 3*H*64], drop = dropout factor
+ * mask/(1-p) fp32 [H*N,T,T] or NULL, probs fp32 [H*N,T,T] (written by fwd, read by bwd), out enc16 / dout bf16
+ * [N*T, H*64], dqkv bf16 [N*T, 3*H*64].  replaces: ScaledDotProductAttention.forward + autograd, attention.py:72-83 */
+int sblk_attention_train_fwd(const void* qkv, const float* drop, float* probs, void* out, const int* lengths, int N,
+                             int T, int H, float scale, void* stream);
+int sblk_attention_train_bwd(const void* qkv, const float* drop, const float* probs, const void* dout, void* dqkv,
+                             const int* lengths, int N, int T, int H, float scale, void* stream);
+
 /* ---- one-shot all-gather of the per-GPU outputs over NVLink / NVSwitch peer memory (one process per GPU) ----------
  * replaces: nn.DataParallel's gather of the replicas' outputs, SBL/train.py:114-115.
  * sblk_p2p_alloc: cudaMalloc + zero a buffer of its own and return its 64-byte CUDA IPC handle (exchange it with the

@@ -72,6 +72,24 @@ SIGNATURES = {
     "sblk_p2p_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "sblk_p2p_close": (_i, [_vp, _i]),
     "sblk_p2p_gather_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, ctypes.c_uint, _vp]),
+    "sblk_gemm_fmt_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sblk_transpose16": (_i, [_vp, _vp, _ll, _i, _ll, _ll, _i, _vp]),
+    "sblk_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _vp]),
+    "sblk_stem_im2col": (_i, [_vp, _vp, _i, _i, _i, _ll, _vp]),
+    "sblk_colreduce_workspace_floats": (_ll, [_i]),
+    "sblk_colreduce": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp]),
+    "sblk_bn_finalize": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _f, _f, _vp]),
+    "sblk_bn_apply_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
+    "sblk_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
+    "sblk_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "sblk_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sblk_avgpool_bwd": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
+    "sblk_zero_stuff2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sblk_relu_bwd": (_i, [_vp, _vp, _ll, _vp]),
+    "sblk_ln_bwd_workspace_floats": (_ll, []),
+    "sblk_ln_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "sblk_attention_train_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "sblk_attention_train_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
     "sblk_encoder_stack_workspace_bytes": (_ll, [_i, _i, _i]),
     "sblk_encoder_stack_fwd": (_i, [ctypes.POINTER(EncoderStackArgs), _vp]),
 }

@@ -24,6 +24,7 @@
 #include "sblk_gemm_ln.cuh"
 #include "sblk_qkv_attn.cuh"
 #include "sblk_encoder_stack.cuh"
+#include "sblk_train.cuh"
 
 namespace {
 
@@ -146,6 +147,8 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::attention_kernel<4>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<8>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attention_kernel<16>, 100 * 1024))) return rc;
+    if ((rc = set_smem(sblk::attn_train_kernel<false>, 104 * 1024))) return rc;
+    if ((rc = set_smem(sblk::attn_train_kernel<true>, 104 * 1024))) return rc;
     st.ready = true;
   }
   if (num_sms_out != nullptr)
@@ -791,7 +794,8 @@ static int pick_block_n_linear(int m_tiles, int N, int splits, int num_sms) {
 }
 
 static int gemm_impl(const void* a, const void* w, const float* bias, const void* residual, void* out_bf16,
-                     float* out_f32, int M, int N, int K, int relu, int splits, void* stream, const char* who) {
+                     float* out_f32, int M, int N, int K, int relu, int splits, void* stream, const char* who,
+                     int fp16 = SBLK_ENC_FP16 ? 1 : 0) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!a || !w || (!out_bf16 && !out_f32)) return fail(-1, "%s: null pointer", who);
@@ -831,7 +835,7 @@ static int gemm_impl(const void* a, const void* w, const float* bias, const void
   p.residual = static_cast<const __nv_bfloat16*>(residual);
   p.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16);
   p.out_f32 = out_f32;
-  p.splits = splits; p.flat_out = 0; p.dbg = nullptr; p.staged = 0; p.fp16 = SBLK_ENC_FP16 ? 1 : 0;
+  p.splits = splits; p.flat_out = 0; p.dbg = nullptr; p.staged = 0; p.fp16 = fp16;
   p.split_stride = static_cast<long long>(M) * N;
   return launch_igemm<false>(bn, tmA, tmB, p, sms, static_cast<cudaStream_t>(stream));
 }
@@ -1146,6 +1150,233 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   }
   return mc ? launch_encoder_stack_nt<8, true>(T, tm, p, groups, s)
             : launch_encoder_stack_nt<8, false>(T, tm, p, groups, s);
+}
+
+
+// =====================================================================================================================
+// Training path (forward with batch statistics + backward): see include/sblk.h "training" section, sblk_train.cuh
+// =====================================================================================================================
+int sblk_gemm_fmt_fwd(const void* a, const void* w, const float* bias, const void* residual, void* out_16,
+                      float* out_f32, int M, int N, int K, int relu, int splits, int fp16, void* stream) {
+  return gemm_impl(a, w, bias, residual, out_16, out_f32, M, N, K, relu, splits, stream, "sblk_gemm_fmt_fwd",
+                   fp16 ? 1 : 0);
+}
+
+int sblk_transpose16(const void* in, void* out, long long R, int C, long long ld_in, long long ld_out, int convert,
+                     void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!in || !out) return fail(-1, "sblk_transpose16: null pointer");
+  if (R <= 0 || C <= 0 || ld_in < C || ld_out < R) return fail(-1, "sblk_transpose16: bad shape R=%lld C=%d ld_in=%lld ld_out=%lld", R, C, ld_in, ld_out);
+  const long long tiles = ((ld_out + 63) / 64) * ((C + 63) / 64);
+  const long long cap = static_cast<long long>(sms) * 8;
+  return launch(sblk::transpose16_kernel, dim3(static_cast<unsigned>(tiles < cap ? tiles : cap)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "transpose16_kernel", static_cast<const uint16_t*>(in),
+                static_cast<uint16_t*>(out), R, C, ld_in, ld_out, convert);
+}
+
+int sblk_im2col_t(const void* x, void* out, int F, int H, int W, int C, int R, int S, int stride, int pad,
+                  long long ld_out, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !out) return fail(-1, "sblk_im2col_t: null pointer");
+  if (F <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 64 != 0 || R <= 0 || S <= 0 || stride <= 0 || pad < 0)
+    return fail(-1, "sblk_im2col_t: bad shape (C %% 64 == 0)");
+  const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+  const long long M = static_cast<long long>(F) * P * Q;
+  if (ld_out < M) return fail(-1, "sblk_im2col_t: ld_out=%lld < M=%lld", ld_out, M);
+  const long long tiles = ((ld_out + 63) / 64) * (C / 64) * R * S;
+  const long long cap = static_cast<long long>(sms) * 8;
+  return launch(sblk::im2col_t_kernel, dim3(static_cast<unsigned>(tiles < cap ? tiles : cap)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "im2col_t_kernel", static_cast<const uint16_t*>(x),
+                static_cast<uint16_t*>(out), F, H, W, C, P, Q, R, S, stride, pad, ld_out);
+}
+
+int sblk_stem_im2col(const float* x, void* out, int N, int T, int transposed, long long ld_out, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !out) return fail(-1, "sblk_stem_im2col: null pointer");
+  const long long M = static_cast<long long>(N) * T * 44 * 44;
+  if (N <= 0 || T <= 0) return fail(-1, "sblk_stem_im2col: bad shape");
+  if (transposed && (ld_out < M || (ld_out & 1))) return fail(-1, "sblk_stem_im2col: ld_out must be even and >= M");
+  if (!aligned16(out)) return fail(-1, "sblk_stem_im2col: output must be 16-byte aligned");
+  const long long items = transposed ? 128 * ld_out : M * 32;
+  return launch(sblk::stem_im2col_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "stem_im2col_kernel", x, static_cast<uint16_t*>(out), N, T,
+                transposed, ld_out);
+}
+
+static const int kColReduceBlocks = 592;
+long long sblk_colreduce_workspace_floats(int C) { return C > 0 ? static_cast<long long>(kColReduceBlocks) * 2 * C : -1; }
+
+int sblk_colreduce(int mode, const void* a, const void* b, const void* c, const float* mean, const float* rstd,
+                   long long M, int C, int fp16, float* workspace, float* out_2C, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!a || !workspace || !out_2C) return fail(-1, "sblk_colreduce: null pointer");
+  if (mode != 0 && mode != 1 && mode != 2 && mode != 4) return fail(-1, "sblk_colreduce: unknown mode %d", mode);
+  if (mode == 1 && (!c || !mean || !rstd)) return fail(-1, "sblk_colreduce: mode 1 needs x, mean, rstd");
+  if (M <= 0 || C <= 0 || C % 2 != 0) return fail(-1, "sblk_colreduce: bad shape M=%lld C=%d", M, C);
+  const int cols2 = C / 2;
+  const int cpb = cols2 < 128 ? cols2 : 128;
+  if (256 % cpb != 0 || cols2 % cpb != 0) return fail(-1, "sblk_colreduce: C=%d not supported (C/2 must divide 256 or be a multiple of 128)", C);
+  const int rif = 256 / cpb;
+  long long grid = (M + rif - 1) / rif;
+  const long long cap = sms * 4 < kColReduceBlocks ? sms * 4 : kColReduceBlocks;
+  if (grid > cap) grid = cap;
+  sblk::ColReduceParams p;
+  p.a = a; p.b = b; p.c = c; p.mean = mean; p.rstd = rstd; p.lengths = nullptr; p.part = workspace; p.M = M; p.C = C;
+  p.mode = mode; p.fp16 = fp16; p.T = 1; p.eps = 0.0f;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((rc = launch(sblk::colreduce_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 256 * 4 * sizeof(float), s, false,
+                   "colreduce_kernel", p)))
+    return rc;
+  return launch(sblk::colreduce_finish_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, s, false,
+                "colreduce_finish_kernel", static_cast<const float*>(workspace), out_2C, static_cast<int>(grid), 2 * C);
+}
+
+int sblk_bn_finalize(const float* sums_2C, float* mean, float* rstd, float* running_mean, float* running_var, int C,
+                     float count, float eps, float momentum, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!sums_2C || !mean || !rstd || C <= 0 || count <= 0.0f) return fail(-1, "sblk_bn_finalize: bad arguments");
+  if ((running_mean == nullptr) != (running_var == nullptr)) return fail(-1, "sblk_bn_finalize: running_mean / running_var must come together");
+  return launch(sblk::bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream), false,
+                "bn_finalize_kernel", sums_2C, mean, rstd, running_mean, running_var, C, count, eps, momentum);
+}
+
+int sblk_bn_apply_fwd(const void* x, const void* residual, const float* mean, const float* rstd, const float* gamma,
+                      const float* beta, void* out, long long M, int C, int relu, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !mean || !rstd || !gamma || !beta || !out) return fail(-1, "sblk_bn_apply_fwd: null pointer");
+  if (M <= 0 || C <= 0 || C % 8 != 0) return fail(-1, "sblk_bn_apply_fwd: bad shape M=%lld C=%d (C %% 8 == 0)", M, C);
+  if (!aligned16(x) || !aligned16(out) || (residual && !aligned16(residual))) return fail(-1, "sblk_bn_apply_fwd: pointers must be 16-byte aligned");
+  const long long total8 = M * (C / 8);
+  return launch(sblk::bn_apply_kernel, dim3(elementwise_grid(total8, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "bn_apply_kernel", static_cast<const uint4*>(x),
+                static_cast<const uint4*>(residual), mean, rstd, gamma, beta, static_cast<uint4*>(out), total8, C, relu);
+}
+
+int sblk_bn_bwd(const void* dy, const void* out_act, const void* x, const float* mean, const float* rstd,
+                const float* gamma, const float* sums_2C, void* dx, void* dres, long long M, int C, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!dy || !x || !mean || !rstd || !gamma || !sums_2C || !dx) return fail(-1, "sblk_bn_bwd: null pointer");
+  if (M <= 0 || C <= 0 || C % 8 != 0) return fail(-1, "sblk_bn_bwd: bad shape M=%lld C=%d (C %% 8 == 0)", M, C);
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || (out_act && !aligned16(out_act)) || (dres && !aligned16(dres)))
+    return fail(-1, "sblk_bn_bwd: pointers must be 16-byte aligned");
+  const long long total8 = M * (C / 8);
+  return launch(sblk::bn_bwd_apply_kernel, dim3(elementwise_grid(total8, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "bn_bwd_apply_kernel", static_cast<const uint4*>(dy),
+                static_cast<const uint4*>(out_act), static_cast<const uint4*>(x), mean, rstd, gamma, sums_2C,
+                static_cast<uint4*>(dx), static_cast<uint4*>(dres), total8, C, 1.0f / static_cast<float>(M));
+}
+
+int sblk_maxpool3x3s2_fwd(const void* x, void* out, int F, int H, int W, int C, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !out || F <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 1)) return fail(-1, "sblk_maxpool3x3s2_fwd: bad arguments");
+  const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(F) * P * Q * (C / 2);
+  return launch(sblk::maxpool3x3s2_fwd_kernel, dim3(elementwise_grid(total, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "maxpool3x3s2_fwd_kernel", static_cast<const uint32_t*>(x),
+                static_cast<uint32_t*>(out), F, H, W, C / 2, P, Q);
+}
+
+int sblk_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int F, int H, int W, int C, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !dy || !dx || F <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 1)) return fail(-1, "sblk_maxpool3x3s2_bwd: bad arguments");
+  const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
+  const long long total = static_cast<long long>(F) * H * W * (C / 2);
+  return launch(sblk::maxpool3x3s2_bwd_kernel, dim3(elementwise_grid(total, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "maxpool3x3s2_bwd_kernel", static_cast<const uint32_t*>(x),
+                static_cast<const uint32_t*>(dy), static_cast<uint32_t*>(dx), F, H, W, C / 2, P, Q);
+}
+
+int sblk_avgpool_bwd(const float* dfeat, void* dx, long long F, int HW, int C, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!dfeat || !dx || F <= 0 || HW <= 0 || C <= 0 || (C & 1)) return fail(-1, "sblk_avgpool_bwd: bad arguments");
+  const long long total = F * HW * (C / 2);
+  return launch(sblk::avgpool_bwd_kernel, dim3(elementwise_grid(total, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "avgpool_bwd_kernel", reinterpret_cast<const float2*>(dfeat),
+                static_cast<uint32_t*>(dx), F, HW, C / 2);
+}
+
+int sblk_zero_stuff2(const void* dy, void* out, int F, int H, int W, int C, int P, int Q, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!dy || !out || F <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0 || P <= 0 || Q <= 0)
+    return fail(-1, "sblk_zero_stuff2: bad arguments (C %% 8 == 0)");
+  if (2 * (P - 1) >= H || 2 * (Q - 1) >= W) return fail(-1, "sblk_zero_stuff2: P x Q does not fit H x W at stride 2");
+  if (!aligned16(dy) || !aligned16(out)) return fail(-1, "sblk_zero_stuff2: pointers must be 16-byte aligned");
+  const long long total = static_cast<long long>(F) * H * W * (C / 8);
+  return launch(sblk::zero_stuff2_kernel, dim3(elementwise_grid(total, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "zero_stuff2_kernel", static_cast<const uint4*>(dy),
+                static_cast<uint4*>(out), F, H, W, C / 8, P, Q);
+}
+
+int sblk_relu_bwd(void* dh_bf16, const void* h_enc16, long long n, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!dh_bf16 || !h_enc16 || n <= 0 || (n & 1)) return fail(-1, "sblk_relu_bwd: bad arguments");
+  return launch(sblk::relu_bwd_kernel, dim3(elementwise_grid(n / 2, 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "relu_bwd_kernel", static_cast<uint32_t*>(dh_bf16),
+                static_cast<const uint32_t*>(h_enc16), n / 2, SBLK_ENC_FP16 ? 1 : 0);
+}
+
+long long sblk_ln_bwd_workspace_floats(void) { return static_cast<long long>(kColReduceBlocks) * 1024; }
+
+int sblk_ln_bwd(const float* dy, const float* z, const float* gamma, const int* lengths, float* dz_f32, void* dz_bf16,
+                float* dgamma_dbeta_1024, float* workspace, int M, int T, float eps, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!dy || !z || !gamma || !dgamma_dbeta_1024 || !workspace || (!dz_f32 && !dz_bf16)) return fail(-1, "sblk_ln_bwd: null pointer");
+  if (M <= 0 || T <= 0 || M % T != 0) return fail(-1, "sblk_ln_bwd: bad shape M=%d T=%d", M, T);
+  if (!aligned16(dy) || !aligned16(z) || !aligned16(gamma) || (dz_f32 && !aligned16(dz_f32)) || (dz_bf16 && !aligned16(dz_bf16)))
+    return fail(-1, "sblk_ln_bwd: pointers must be 16-byte aligned");
+  sblk::LnBwdParams p;
+  p.dy = dy; p.z = z; p.gamma = gamma; p.lengths = lengths; p.dz_f32 = dz_f32; p.dz_bf16 = static_cast<uint16_t*>(dz_bf16);
+  p.part = workspace; p.M = M; p.T = T; p.eps = eps;
+  int grid = (M + 7) / 8;
+  const int cap = sms * 2 < kColReduceBlocks ? sms * 2 : kColReduceBlocks;
+  if (grid > cap) grid = cap;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if ((rc = launch(sblk::ln_bwd_kernel, dim3(grid), dim3(256), 0, s, false, "ln_bwd_kernel", p))) return rc;
+  return launch(sblk::colreduce_finish_kernel, dim3(4), dim3(256), 0, s, false, "colreduce_finish_kernel",
+                static_cast<const float*>(workspace), dgamma_dbeta_1024, grid, 1024);
+}
+
+static int attn_train_impl(bool bwd, const void* qkv, const float* drop, float* probs, void* out, const void* dout,
+                           void* dqkv, const int* lengths, int N, int T, int H, float scale, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!qkv || !probs || (!bwd && !out) || (bwd && (!dout || !dqkv))) return fail(-1, "sblk_attention_train: null pointer");
+  if (N <= 0 || T <= 0 || T > 64 || H <= 0) return fail(-1, "sblk_attention_train: bad shape N=%d T=%d H=%d (training attention: T <= 64)", N, T, H);
+  sblk::AttnTrainParams p;
+  p.qkv = static_cast<const uint16_t*>(qkv); p.drop = drop; p.probs = probs; p.out = static_cast<uint16_t*>(out);
+  p.dout = static_cast<const uint16_t*>(dout); p.dqkv = static_cast<uint16_t*>(dqkv); p.lengths = lengths;
+  p.N = N; p.T = T; p.H = H; p.scale = scale; p.fp16 = SBLK_ENC_FP16 ? 1 : 0;
+  const size_t fl = static_cast<size_t>(3) * T * 65 + static_cast<size_t>(T) * (T + 1) +
+                    (bwd ? static_cast<size_t>(T) * 65 + static_cast<size_t>(T) * (T + 1) : 0);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (bwd)
+    return launch(sblk::attn_train_kernel<true>, dim3(N * H), dim3(256), fl * sizeof(float), s, false,
+                  "attn_train_kernel<bwd>", p);
+  return launch(sblk::attn_train_kernel<false>, dim3(N * H), dim3(256), fl * sizeof(float), s, false,
+                "attn_train_kernel<fwd>", p);
+}
+
+int sblk_attention_train_fwd(const void* qkv, const float* drop, float* probs, void* out, const int* lengths, int N,
+                             int T, int H, float scale, void* stream) {
+  return attn_train_impl(false, qkv, drop, probs, out, nullptr, nullptr, lengths, N, T, H, scale, stream);
+}
+
+int sblk_attention_train_bwd(const void* qkv, const float* drop, const float* probs, const void* dout, void* dqkv,
+                             const int* lengths, int N, int T, int H, float scale, void* stream) {
+  return attn_train_impl(true, qkv, drop, const_cast<float*>(probs), nullptr, dout, dqkv, lengths, N, T, H, scale, stream);
 }
 
 }  // extern "C"

@@ -158,6 +158,14 @@ class Encoder(nn.Module):
     def _cache_key(self):
         return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
 
+    def _check_train_config(self, t, return_attns):
+        if return_attns:
+            raise RuntimeError("Encoder (libsblk): return_attns is an evaluation feature (training path returns no maps)")
+        if t > 64:
+            raise RuntimeError(f"Encoder (libsblk): training attention is implemented for T <= 64 frames (got {t})")
+        if self.n_head * self.d_k != 512 or self.d_input % 64 or self.d_inner % 64:
+            raise RuntimeError("Encoder (libsblk): training path needs n_head*d_k == 512 and 64-aligned widths")
+
     def invalidate_packed(self):
         """Drop the packed (bf16 / enc16, BN-folded) weight cache.  The cache key is (data_ptr, tensor._version) of every
         parameter and buffer, which `load_state_dict`, optimizer steps and `.to()` all change; edits THROUGH `.data`
@@ -283,9 +291,6 @@ class Encoder(nn.Module):
     def forward(self, padded_input, input_lengths, return_attns=False):
         """padded_input: N x T x d_input (fp32, CUDA); input_lengths: N ints -> (enc_output N x T x d_model,)"""
         self._check_config()
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("Encoder (libsblk): training-mode forward/backward is not implemented yet; "
-                               "call .eval() / torch.no_grad()")
         if not padded_input.is_cuda:
             raise RuntimeError("Encoder (libsblk) runs on a B200 CUDA device only; no CPU fallback exists")
         n, t, d_in = padded_input.shape
@@ -299,6 +304,11 @@ class Encoder(nn.Module):
         lens = [int(v) for v in input_lengths]
         if len(lens) != n:
             raise RuntimeError(f"Encoder: {len(lens)} input_lengths for batch {n}")
+        if self.training:
+            # model.train(): dropout active, every block a torch.autograd.Function backed by libsblk (training.py)
+            self._check_train_config(t, return_attns)
+            from . import training
+            return training.encoder_forward_train(self, padded_input.float(), lens)
         m = n * t
         x = padded_input.detach()
         if x.dtype != torch.float32:

@@ -237,9 +237,6 @@ class Lipreading(nn.Module):
         return ws
 
     def _check_input(self, x):
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("Lipreading (libsblk): training-mode forward/backward is not implemented yet "
-                               "(eval-mode BatchNorm is folded into the kernels); call .eval() / torch.no_grad()")
         if x.dim() != 5 or x.size(1) != 1 or x.size(3) != 88 or x.size(4) != 88:
             raise RuntimeError(f"Lipreading expects [N,1,T,88,88], got {tuple(x.shape)}")
         if not x.is_cuda:
@@ -389,8 +386,9 @@ class Lipreading(nn.Module):
         data_gen.py:122-125,276-296; cvtransforms.py:7-48).  `crop`: (y1, x1) or an int32 CUDA tensor [N*T_in, 2] of
         per-frame offsets (RandomCrop).  Bit-identical to forward(reference-normalised fp32 clip); 4x fewer host->device
         bytes."""
-        if self.training and torch.is_grad_enabled():
-            raise RuntimeError("Lipreading (libsblk): training-mode forward/backward is not implemented yet")
+        if self.training:
+            raise RuntimeError("Lipreading.forward_u8 (libsblk) is the evaluation / serving input path; training runs "
+                               "through forward() on the loader's augmented fp32 clips")
         if not torch.is_tensor(x_u8) or x_u8.dtype != torch.uint8 or x_u8.dim() != 4:
             raise RuntimeError("forward_u8 expects a uint8 tensor [N, T, H0, W0]")
         if not x_u8.is_cuda:
@@ -417,9 +415,21 @@ class Lipreading(nn.Module):
             feat = F.dropout(feat, p=0.5)  # functional default training=True, exactly as reference :122
         return feat.view(-1, t_out, self.inputDim)
 
+    def train(self, mode=True):
+        # training updates the BatchNorm running statistics in place from a kernel (no torch version bump): the
+        # BN-folded evaluation weights are re-packed whenever the mode changes
+        self._packed = None
+        return super().train(mode)
+
     def forward(self, x):
-        """reference :119-125."""
+        """reference :119-125.  model.train(): BatchNorm on batch statistics + autograd through libsblk
+        (training.py); model.eval(): running statistics folded into the kernels, output detached from autograd."""
         frameLen = x.size(2)
+        if self.training:
+            from . import training
+            feat = training.frontend_forward_train(self, self._check_input(x))
+            feat = F.dropout(feat, p=0.5)  # reference :122 (functional default training=True); torch autograd
+            return feat.view(-1, frameLen, self.inputDim)
         feat = self._frontend_forward(x)
         if self.always_on_dropout and self._tail is None:
             feat = F.dropout(feat, p=0.5)  # functional default training=True, exactly as reference :122

@@ -216,10 +216,18 @@ def test_unsupported_encoder_config_is_rejected():
         enc(torch.zeros(1, 4, 512), [4])
 
 
-def test_training_mode_is_rejected():
+def test_training_mode_has_no_cpu_fallback_either():
+    """model.train() runs the libsblk training path (training.py): on a CPU tensor it must fail loudly, never fall back."""
     fe = Lipreading().train()
-    with pytest.raises(RuntimeError, match="training-mode"):
+    with pytest.raises(RuntimeError, match="CUDA"):
         fe(torch.zeros(1, 1, 2, 88, 88))
+    enc = Encoder(512, 1, 8, 64, 64, 512, 2048).train()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        enc(torch.zeros(1, 2, 512), [2, 2][:1])
+    # switching modes re-packs the BN-folded evaluation weights (training updates running stats from a kernel)
+    fe._packed = object()
+    fe.eval()
+    assert fe._packed is None
 
 
 def test_flat_frames_is_a_valid_flat_sub_buffer():
