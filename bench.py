@@ -816,6 +816,120 @@ def run_config4_sweep(args):
     return 0
 
 
+def run_config3(args):
+    """BASELINE configs[3]: 1500-class frontend pre-training (stage-1 classify model), forward + backward + Adam step,
+    global batch 256 (strong scaling: 256 / world clips per GPU), 31-frame clips, 3-layer encoder; gradients all-reduced
+    by DistributedDataParallel (bucketed NCCL, overlapped with the libsblk backward).  Device-timed with CUDA events around
+    each step, max over ranks.  The all-reference fp32 CUDA model (cuDNN / cuBLAS, TF32 off) runs the same step beside it
+    for context.  Prints ONE JSON line."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sblk_bench_nccl_%h_%p.log")
+        dist.init_process_group("nccl", device_id=dev)
+    from sbl_for_multilingual_lip_reading_b200 import ops, sharding, stage1, synth
+    ops.init()
+    gb, T, L = args.config3_batch, 31, 3
+    n = max(1, gb // world)
+    torch.manual_seed(7)
+    model = stage1.Stage1Classifier(n_layers_enc=L, dropout=0.1).load_synthetic(1, 3).to(dev).train()
+    net = (torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], broadcast_buffers=False)
+           if world > 1 else model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+    x = synth.synthetic_clips(n, T, seed=40 + rank, pad_frames=2).to(dev)
+    y = torch.randint(0, 1500, (n,), generator=torch.Generator().manual_seed(rank)).to(dev)
+    lang = torch.randint(0, 2, (n,), generator=torch.Generator().manual_seed(100 + rank)).to(dev)
+
+    def step(m, o):
+        v_t, v_l = m(x)
+        loss = F.cross_entropy(v_t, y) + 0.1 * F.cross_entropy(v_l, lang)     # train.py:129-132
+        o.zero_grad()
+        loss.backward()
+        o.step()
+        return loss
+
+    def timed(m, o, steps, warmup):
+        for _ in range(warmup):
+            step(m, o)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        evs = []
+        before = ops.launch_count()
+        for _ in range(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            loss = step(m, o)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize(dev)
+        launches = ops.launch_count() - before
+        ms = sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), dev) / steps
+        return ms, float(loss.detach()), launches
+
+    steps, warmup = max(3, min(args.steps, 10)), max(2, min(args.warmup, 3))
+    ms, loss, launches = timed(net, opt, steps, warmup)
+    ref_ms = None
+    if not args.no_cpu_baseline:
+        # context arm: the unmodified reference modules under the same step on the same GPU(s) (fp32, cuDNN / cuBLAS)
+        from oracle import ref_runtime
+        ref_runtime.fp32_exact()
+        R = ref_runtime.load_reference("cls")
+        sd = dict(synth.frontend_state_dict(1, prefix="visual_frontend."))
+        sd.update(synth.encoder_state_dict(3, L, prefix="encoder_v."))
+        rmodel = ref_runtime.build_cls_reference(R, sd, n_layers_enc=L).to(dev).train()
+
+        class RefStage1(torch.nn.Module):
+            def __init__(self, m):
+                super().__init__()
+                self.m = m
+
+            def forward(self, xx):
+                feat = self.m.visual_frontend(xx)
+                out, *_ = self.m.encoder_v(feat, [feat.size(1)] * feat.size(0))
+                return self.m.fc_1500(out.mean(dim=1)), self.m.fc_2(out[:, 30, :])
+        rnet = RefStage1(rmodel)
+        if world > 1:
+            rnet = torch.nn.parallel.DistributedDataParallel(rnet, device_ids=[local_rank], broadcast_buffers=False)
+        ropt = torch.optim.Adam(rmodel.parameters(), lr=1e-4, betas=(0.9, 0.98), eps=1e-9)
+        ref_ms, _, _ = timed(rnet, ropt, max(2, steps // 2), 1)
+    if rank == 0:
+        # 2*MACs of the forward x3 (dgrad + wgrad) is the usual training estimate; the stem has no dgrad
+        fpc = flops_per_clip(T, L)
+        peaks = load_peaks()
+        tf = 3.0 * n * fpc / (ms * 1e-3) / 1e12
+        line = {"metric": "stage1_pretraining_clips_per_sec_fwd_bwd", "value": n * world / (ms * 1e-3), "unit": UNIT,
+                "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[3]: 1500-class frontend pre-training (stage-1 classify model: Conv3d "
+                                       "frontend + ResNet-18 + 3-layer encoder + fc_1500 / fc_2), forward + backward + Adam "
+                                       f"step, global batch {n * world} = {n} clips x {T} frames per GPU, "
+                                       "batch-statistics BatchNorm, dropout 0.1, DistributedDataParallel NCCL gradient "
+                                       "all-reduce" + ("" if world > 1 else " (single GPU: no collective)"),
+                           "global_batch": n * world, "clips_per_gpu": n, "frames": T, "encoder_layers": L,
+                           "parallelism": f"ddp{world}"},
+                "loss": loss, "gpu_launches_per_step": launches // steps,
+                "approx_tflops_per_gpu": tf, "approx_frac_of_bf16_peak": tf / float(peaks["bf16_tflops"]),
+                "reference_cuda_fp32": None if ref_ms is None else
+                {"ms_per_step": ref_ms, "clips_per_s": n * world / (ref_ms * 1e-3),
+                 "what": "unmodified reference modules (oracle/_ref), same step, fp32 cuDNN / cuBLAS with TF32 off"}}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -833,9 +947,10 @@ def main():
     ap.add_argument("--inline-gather", action="store_true",
                     help="multi-GPU, pipelined plan: gather each step's output in stream after the replay instead of on a "
                          "side stream next to the following step's replay")
-    ap.add_argument("--workload", default="visual_encoder", choices=["visual_encoder", "config4"],
+    ap.add_argument("--workload", default="visual_encoder", choices=["visual_encoder", "config3", "config4"],
                     help="config4 = BASELINE configs[4] sweep: full SBL model (reference decoder on the drop-ins)")
     ap.add_argument("--config4-batches", default="16,32,64,128,256,512")
+    ap.add_argument("--config3-batch", type=int, default=256, help="global batch of the configs[3] training step")
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the BASELINE configs[2] (8 clips x 40 frames per GPU) leg")
@@ -855,6 +970,8 @@ def main():
         return run_reference_arm(args)
     if args.workload == "config4":
         return run_config4_sweep(args)
+    if args.workload == "config3":
+        return run_config3(args)
     return run_b200_arm(args)
 
 

@@ -251,7 +251,7 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);
 int sblk_gemm_fmt_fwd(const void* a, const void* w, const float* bias, const void* residual_16, void* out_16,
                       float* out_f32, int M, int N, int K, int relu, int splits, int fp16, void* stream);
 /* out[c][r] = in[r][c] for 16-bit elements: in [R, C] (row pitch ld_in), out [C, ld_out], columns R..ld_out-1 zero
- * (K padding of the wgrad GEMMs).  convert = 1 re-rounds IEEE fp16 input to bf16. */
+ * (K padding of the wgrad GEMMs).  convert = 1 re-rounds IEEE fp16 input to bf16.  C, ld_in, ld_out % 8 == 0. */
 int sblk_transpose16(const void* in, void* out, long long R, int C, long long ld_in, long long ld_out, int convert,
                      void* stream);
 /* Transposed im2col of NHWC bf16 [F,H,W,C] for an R x S / stride / pad conv: out[(r*S + s)*C + c][m] (row pitch ld_out,
@@ -281,9 +281,11 @@ int sblk_bn_apply_fwd(const void* x, const void* residual, const float* mean, co
 int sblk_bn_bwd(const void* dy, const void* out_act, const void* x, const float* mean, const float* rstd,
                 const float* gamma, const float* sums_2C, void* dx, void* dres, long long M, int C, void* stream);
 /* MaxPool 3x3 / stride 2 / pad 1 over NHWC bf16 (the spatial part of MaxPool3d((1,3,3),(1,2,2),(0,1,1))), and its backward
- * (gradient to the first maximum of every window, PyTorch's tie rule). */
+ * (gradient to the first maximum of every window, PyTorch's tie rule; `pooled` = the forward output; x is a ReLU output:
+ * non-positive pixels take no gradient, which the ReLU backward would mask anyway). */
 int sblk_maxpool3x3s2_fwd(const void* x, void* out, int F, int H, int W, int C, void* stream);
-int sblk_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int F, int H, int W, int C, void* stream);
+int sblk_maxpool3x3s2_bwd(const void* x, const void* pooled, const void* dy, void* dx, int F, int H, int W, int C,
+                          void* stream);
 /* AdaptiveAvgPool2d(1) backward: dx bf16 [F, HW, C] = dfeat fp32 [F, C] / HW. */
 int sblk_avgpool_bwd(const float* dfeat, void* dx, long long F, int HW, int C, void* stream);
 /* out [F,H,W,C] = 0 except out[f,2p,2q,:] = dy[f,p,q,:] (dgrad of a stride-2 conv = stride-1 conv over this). */

@@ -82,7 +82,7 @@ SIGNATURES = {
     "sblk_bn_apply_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp]),
     "sblk_bn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "sblk_maxpool3x3s2_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "sblk_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "sblk_maxpool3x3s2_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sblk_avgpool_bwd": (_i, [_vp, _vp, _ll, _i, _i, _vp]),
     "sblk_zero_stuff2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_relu_bwd": (_i, [_vp, _vp, _ll, _vp]),

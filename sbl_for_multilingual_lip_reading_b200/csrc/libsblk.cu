@@ -1168,6 +1168,8 @@ int sblk_transpose16(const void* in, void* out, long long R, int C, long long ld
   if ((rc = ensure_init(&sms))) return rc;
   if (!in || !out) return fail(-1, "sblk_transpose16: null pointer");
   if (R <= 0 || C <= 0 || ld_in < C || ld_out < R) return fail(-1, "sblk_transpose16: bad shape R=%lld C=%d ld_in=%lld ld_out=%lld", R, C, ld_in, ld_out);
+  if ((C & 7) || (ld_in & 7) || (ld_out & 7) || !aligned16(in) || !aligned16(out))
+    return fail(-1, "sblk_transpose16: C, ld_in, ld_out must be multiples of 8 and the bases 16-byte aligned");
   const long long tiles = ((ld_out + 63) / 64) * ((C + 63) / 64);
   const long long cap = static_cast<long long>(sms) * 8;
   return launch(sblk::transpose16_kernel, dim3(static_cast<unsigned>(tiles < cap ? tiles : cap)), dim3(256), 0,
@@ -1185,6 +1187,7 @@ int sblk_im2col_t(const void* x, void* out, int F, int H, int W, int C, int R, i
   const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
   const long long M = static_cast<long long>(F) * P * Q;
   if (ld_out < M) return fail(-1, "sblk_im2col_t: ld_out=%lld < M=%lld", ld_out, M);
+  if ((ld_out & 7) || !aligned16(x) || !aligned16(out)) return fail(-1, "sblk_im2col_t: ld_out must be a multiple of 8 and the bases 16-byte aligned");
   const long long tiles = ((ld_out + 63) / 64) * (C / 64) * R * S;
   const long long cap = static_cast<long long>(sms) * 8;
   return launch(sblk::im2col_t_kernel, dim3(static_cast<unsigned>(tiles < cap ? tiles : cap)), dim3(256), 0,
@@ -1200,10 +1203,11 @@ int sblk_stem_im2col(const float* x, void* out, int N, int T, int transposed, lo
   if (N <= 0 || T <= 0) return fail(-1, "sblk_stem_im2col: bad shape");
   if (transposed && (ld_out < M || (ld_out & 1))) return fail(-1, "sblk_stem_im2col: ld_out must be even and >= M");
   if (!aligned16(out)) return fail(-1, "sblk_stem_im2col: output must be 16-byte aligned");
-  const long long items = transposed ? 128 * ld_out : M * 32;
-  return launch(sblk::stem_im2col_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "stem_im2col_kernel", x, static_cast<uint16_t*>(out), N, T,
-                transposed, ld_out);
+  const dim3 grid = transposed ? dim3(256, static_cast<unsigned>((ld_out + 1935) / 1936))
+                               : dim3(static_cast<unsigned>(static_cast<long long>(N) * T * 44));
+  if (transposed && grid.y > 65535u) return fail(-1, "sblk_stem_im2col: too many frames for one launch (%u)", grid.y);
+  return launch(sblk::stem_im2col_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), false,
+                "stem_im2col_kernel", x, static_cast<uint16_t*>(out), N, T, transposed, ld_out);
 }
 
 static const int kColReduceBlocks = 592;
@@ -1216,10 +1220,11 @@ int sblk_colreduce(int mode, const void* a, const void* b, const void* c, const 
   if (!a || !workspace || !out_2C) return fail(-1, "sblk_colreduce: null pointer");
   if (mode != 0 && mode != 1 && mode != 2 && mode != 4) return fail(-1, "sblk_colreduce: unknown mode %d", mode);
   if (mode == 1 && (!c || !mean || !rstd)) return fail(-1, "sblk_colreduce: mode 1 needs x, mean, rstd");
-  if (M <= 0 || C <= 0 || C % 2 != 0) return fail(-1, "sblk_colreduce: bad shape M=%lld C=%d", M, C);
-  const int cols2 = C / 2;
-  const int cpb = cols2 < 128 ? cols2 : 128;
-  if (256 % cpb != 0 || cols2 % cpb != 0) return fail(-1, "sblk_colreduce: C=%d not supported (C/2 must divide 256 or be a multiple of 128)", C);
+  if (M <= 0 || C <= 0 || C % 8 != 0) return fail(-1, "sblk_colreduce: bad shape M=%lld C=%d (C %% 8 == 0)", M, C);
+  const int cols8 = C / 8;
+  const int cpb = cols8 < 64 ? cols8 : 64;
+  if (256 % cpb != 0 || cols8 % cpb != 0) return fail(-1, "sblk_colreduce: C=%d not supported (C/8 must divide 256 or be a multiple of 64)", C);
+  if (!aligned16(a) || (b && !aligned16(b)) || (c && !aligned16(c))) return fail(-1, "sblk_colreduce: pointers must be 16-byte aligned");
   const int rif = 256 / cpb;
   long long grid = (M + rif - 1) / rif;
   const long long cap = sms * 4 < kColReduceBlocks ? sms * 4 : kColReduceBlocks;
@@ -1228,7 +1233,7 @@ int sblk_colreduce(int mode, const void* a, const void* b, const void* c, const 
   p.a = a; p.b = b; p.c = c; p.mean = mean; p.rstd = rstd; p.lengths = nullptr; p.part = workspace; p.M = M; p.C = C;
   p.mode = mode; p.fp16 = fp16; p.T = 1; p.eps = 0.0f;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if ((rc = launch(sblk::colreduce_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 256 * 4 * sizeof(float), s, false,
+  if ((rc = launch(sblk::colreduce_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 256 * 16 * sizeof(float), s, false,
                    "colreduce_kernel", p)))
     return rc;
   return launch(sblk::colreduce_finish_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, s, false,
@@ -1284,15 +1289,17 @@ int sblk_maxpool3x3s2_fwd(const void* x, void* out, int F, int H, int W, int C, 
                 static_cast<uint32_t*>(out), F, H, W, C / 2, P, Q);
 }
 
-int sblk_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int F, int H, int W, int C, void* stream) {
+int sblk_maxpool3x3s2_bwd(const void* x, const void* pooled, const void* dy, void* dx, int F, int H, int W, int C,
+                          void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
-  if (!x || !dy || !dx || F <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 1)) return fail(-1, "sblk_maxpool3x3s2_bwd: bad arguments");
+  if (!x || !pooled || !dy || !dx || F <= 0 || H <= 0 || W <= 0 || C <= 0 || (C & 7)) return fail(-1, "sblk_maxpool3x3s2_bwd: bad arguments (C %% 8 == 0)");
+  if (!aligned16(x) || !aligned16(pooled) || !aligned16(dy) || !aligned16(dx)) return fail(-1, "sblk_maxpool3x3s2_bwd: pointers must be 16-byte aligned");
   const int P = (H - 1) / 2 + 1, Q = (W - 1) / 2 + 1;
-  const long long total = static_cast<long long>(F) * H * W * (C / 2);
+  const long long total = static_cast<long long>(F) * H * W * (C / 8);
   return launch(sblk::maxpool3x3s2_bwd_kernel, dim3(elementwise_grid(total, 256, sms)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "maxpool3x3s2_bwd_kernel", static_cast<const uint32_t*>(x),
-                static_cast<const uint32_t*>(dy), static_cast<uint32_t*>(dx), F, H, W, C / 2, P, Q);
+                static_cast<cudaStream_t>(stream), false, "maxpool3x3s2_bwd_kernel", static_cast<const uint4*>(x),
+                static_cast<const uint4*>(pooled), static_cast<const uint4*>(dy), static_cast<uint4*>(dx), F, H, W, C / 8, P, Q);
 }
 
 int sblk_avgpool_bwd(const float* dfeat, void* dx, long long F, int HW, int C, void* stream) {

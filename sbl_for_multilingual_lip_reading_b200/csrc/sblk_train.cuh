@@ -28,41 +28,67 @@ __device__ __forceinline__ float hi16(uint32_t u, int fp16) { return fp16 ? f16_
 // R <= r < ld_out (K padding of the wgrad GEMMs).  convert = 1 re-rounds IEEE fp16 input to bf16 (saved enc16
 // activations feeding a bf16 gradient GEMM).  64 x 64 tiles through shared memory, coalesced both ways.
 // ----------------------------------------------------------------------------------------------------------------
+// Shared 64 x 64 tile of 16-bit values, 128-byte rows, 16-byte chunk c of row r stored at chunk c ^ ((r >> 3) & 7):
+// load: thread -> (row, 8-column chunk) as one 16-byte store (a quarter-warp covers one row: conflict-free);
+// store: thread -> (column, 8-row chunk) gathered with 8 halfword reads (lanes of a warp differ in the row group, i.e. in
+// the swizzled chunk position: conflict-free) and written to global memory as one 16-byte access.
+struct Tile64 {
+  uint16_t v[64 * 64];
+};
+__device__ __forceinline__ uint4* tile_chunk(Tile64& t, int row, int chunk) {
+  return reinterpret_cast<uint4*>(&t.v[row * 64 + ((chunk ^ ((row >> 3) & 7)) << 3)]);
+}
+__device__ __forceinline__ uint4 tile_gather_col8(const Tile64& t, int col, int row0) {   // row0 % 8 == 0
+  const int off = (((col >> 3) ^ ((row0 >> 3) & 7)) << 3) + (col & 7);
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    w[j] = static_cast<uint32_t>(t.v[(row0 + 2 * j) * 64 + off]) |
+           (static_cast<uint32_t>(t.v[(row0 + 2 * j + 1) * 64 + off]) << 16);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 cvt8_f16_to_bf16(uint4 u) {
+  uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) w[j] = pack_bf16x2(f16_lo(w[j]), f16_hi(w[j]));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// Requires C % 8 == 0, ld_in % 8 == 0, ld_out % 8 == 0 and 16-byte aligned bases (checked by the C ABI).
 __global__ void __launch_bounds__(256)
 transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, long long R, int C, long long ld_in,
                    long long ld_out, int convert) {
-  __shared__ uint16_t tile[64][66];
+  __shared__ __align__(16) Tile64 tile;
   const long long tiles_r = (ld_out + 63) / 64;
   const int tiles_c = (C + 63) / 64;
   const long long total = tiles_r * tiles_c;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
   for (long long tI = blockIdx.x; tI < total; tI += gridDim.x) {
     const long long tr = tI / tiles_c;
     const int tc = static_cast<int>(tI - tr * tiles_c);
     const long long r0 = tr * 64;
     const int c0 = tc * 64;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int rr = ty + 4 * i;
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + 256 * i;      // 512 chunks: 64 rows x 8 chunks
+      const int rr = idx >> 3, ch = idx & 7;
       const long long r = r0 + rr;
-      const int c = c0 + tx;
-      uint16_t v = 0;
+      const int c = c0 + ch * 8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (r < R && c < C) {
-        v = in[r * ld_in + c];
-        if (convert) {
-          const float f = __half2float(__ushort_as_half(v));
-          v = static_cast<uint16_t>(pack_bf16x2(f, 0.0f) & 0xFFFFu);
-        }
+        v = __ldg(reinterpret_cast<const uint4*>(in + r * ld_in + c));
+        if (convert) v = cvt8_f16_to_bf16(v);
       }
-      tile[rr][tx] = v;
+      *tile_chunk(tile, rr, ch) = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int cc = ty + 4 * i;
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + 256 * i;      // 512 chunks: 64 columns x 8 row-chunks
+      const int cc = idx >> 3, rc = idx & 7;
       const int c = c0 + cc;
-      const long long r = r0 + tx;
-      if (c < C && r < ld_out) out[static_cast<long long>(c) * ld_out + r] = tile[tx][cc];
+      const long long r = r0 + rc * 8;
+      if (c < C && r < ld_out)
+        *reinterpret_cast<uint4*>(out + static_cast<long long>(c) * ld_out + r) = tile_gather_col8(tile, cc, rc * 8);
     }
     __syncthreads();
   }
@@ -77,13 +103,12 @@ transpose16_kernel(const uint16_t* __restrict__ in, uint16_t* __restrict__ out, 
 __global__ void __launch_bounds__(256)
 im2col_t_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int F, int H, int W, int C, int P, int Q,
                 int R, int S, int stride, int pad, long long ld_out) {
-  __shared__ uint16_t tile[64][66];
+  __shared__ __align__(16) Tile64 tile;
   const long long M = static_cast<long long>(F) * P * Q;
   const long long tiles_m = (ld_out + 63) / 64;
   const int tiles_c = C / 64;
   const int taps = R * S;
   const long long total = tiles_m * tiles_c * taps;
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   for (long long tI = blockIdx.x; tI < total; tI += gridDim.x) {
     const long long tm = tI / (tiles_c * taps);
     const int rest = static_cast<int>(tI - tm * (tiles_c * taps));
@@ -91,10 +116,11 @@ im2col_t_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int 
     const int tc = rest - tap * tiles_c;
     const int r = tap / S, s = tap - r * S;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int mm = ty + 4 * i;
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + 256 * i;      // 64 pixels x 8 channel chunks
+      const int mm = idx >> 3, ch = idx & 7;
       const long long m = tm * 64 + mm;
-      uint16_t v = 0;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
       if (m < M) {
         const int q = static_cast<int>(m % Q);
         const long long t2 = m / Q;
@@ -102,16 +128,19 @@ im2col_t_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ out, int 
         const long long f = t2 / P;
         const int y = pp * stride + r - pad, xx = q * stride + s - pad;
         if (y >= 0 && y < H && xx >= 0 && xx < W)
-          v = x[((f * H + y) * W + xx) * static_cast<long long>(C) + tc * 64 + tx];
+          v = __ldg(reinterpret_cast<const uint4*>(x + ((f * H + y) * W + xx) * static_cast<long long>(C) + tc * 64 + ch * 8));
       }
-      tile[mm][tx] = v;
+      *tile_chunk(tile, mm, ch) = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int cc = ty + 4 * i;
-      const long long m = tm * 64 + tx;
-      if (m < ld_out) out[(static_cast<long long>(tap) * C + tc * 64 + cc) * ld_out + m] = tile[tx][cc];
+    for (int i = 0; i < 2; ++i) {
+      const int idx = threadIdx.x + 256 * i;      // 64 channels x 8 pixel chunks
+      const int cc = idx >> 3, mc = idx & 7;
+      const long long m = tm * 64 + mc * 8;
+      if (m < ld_out)
+        *reinterpret_cast<uint4*>(out + (static_cast<long long>(tap) * C + tc * 64 + cc) * ld_out + m) =
+            tile_gather_col8(tile, cc, mc * 8);
     }
     __syncthreads();
   }
@@ -130,52 +159,50 @@ __device__ __forceinline__ float stem_tap(const float* __restrict__ x, int T, lo
   return __ldg(x + ((n * T + tt) * 88 + yy) * 88 + xx);
 }
 
+// transposed == 0: blockIdx.x = output row (f, y); threads = 44 pixels x 32 chunks of 8 taps, 16-byte stores
+// transposed == 1: blockIdx.x = tap k (256), blockIdx.y = frame slot (1936 consecutive m); 2-pixel 4-byte stores
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int N, int T, int transposed,
                    long long ld_out) {
   const long long M = static_cast<long long>(N) * T * 44 * 44;
   if (!transposed) {
-    // one thread = 8 consecutive k of one output pixel (16-byte store); 32 threads per pixel row of 256
-    const long long total = M * 32;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const long long m = i >> 5;
-      const int k0 = static_cast<int>(i & 31) * 8;
-      const int xo = static_cast<int>(m % 44);
-      const long long t2 = m / 44;
-      const int y = static_cast<int>(t2 % 44);
-      const long long f = t2 / 44;
-      const int t = static_cast<int>(f % T);
-      const long long n = f / T;
+    const int fy = blockIdx.x;                  // f * 44 + y
+    const int y = fy % 44;
+    const int f = fy / 44;
+    const int t = f % T;
+    const long long n = f / T;
+    uint4* dst = reinterpret_cast<uint4*>(out) + static_cast<long long>(fy) * 44 * 32;
+    for (int i = threadIdx.x; i < 44 * 32; i += blockDim.x) {
+      const int xo = i >> 5;
+      const int k0 = (i & 31) * 8;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = stem_tap(x, T, n, t, y, xo, k0 + j);
       uint4 o;
       o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
       o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      reinterpret_cast<uint4*>(out)[i] = o;
+      dst[i] = o;
     }
   } else {
-    // one thread = 2 consecutive m of one k (coalesced along m)
-    const long long half = ld_out / 2;
-    const long long total = 256 * half;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-      const int k = static_cast<int>(i / half);
-      const long long m0 = (i - k * half) * 2;
-      float v[2] = {0.0f, 0.0f};
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const long long m = m0 + j;
-        if (m < M) {
-          const int xo = static_cast<int>(m % 44);
-          const long long t2 = m / 44;
-          const int y = static_cast<int>(t2 % 44);
-          const long long f = t2 / 44;
-          v[j] = stem_tap(x, T, f / T, static_cast<int>(f % T), y, xo, k);
-        }
+    const int k = blockIdx.x;
+    const long long m0 = static_cast<long long>(blockIdx.y) * 1936;
+    const int f = blockIdx.y;
+    const bool real = k < 245 && f < N * T;
+    const int t = real ? f % T : 0;
+    const long long n = real ? f / T : 0;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + static_cast<long long>(k) * ld_out + m0);
+    for (int i = threadIdx.x; i < 968; i += blockDim.x) {      // 968 pixel pairs of one frame
+      const long long m = m0 + 2 * i;
+      if (m >= ld_out) break;
+      float a = 0.0f, b = 0.0f;
+      if (real) {
+        const int px = 2 * i;
+        const int y = px / 44, xo = px - y * 44;              // 44 is even: both pixels in the same row
+        a = stem_tap(x, T, n, t, y, xo, k);
+        b = stem_tap(x, T, n, t, y, xo + 1, k);
       }
-      reinterpret_cast<uint32_t*>(out)[i] = pack_bf16x2(v[0], v[1]);
+      if (m + 1 < ld_out) dst[i] = pack_bf16x2(a, b);
+      else *reinterpret_cast<uint16_t*>(dst + i) = static_cast<uint16_t>(pack_bf16x2(a, 0.0f) & 0xFFFFu);
     }
   }
 }
@@ -186,9 +213,7 @@ stem_im2col_kernel(const float* __restrict__ x, uint16_t* __restrict__ out, int 
 //   0  x 16-bit                    -> (sum x, sum x^2)                          BatchNorm batch statistics
 //   1  dy 16-bit, out 16-bit, x 16-bit, mean/rstd -> (sum dz, sum dz * xhat), dz = dy * (out > 0 or no mask)   BN backward
 //   2  x fp32                      -> (sum x, -)                                bias gradients of fp32 rows
-//   3  dy fp32, z fp32 [M,512] rows -> (sum dy*xhat_row, sum dy) with per-ROW LayerNorm statistics recomputed from z
 //   4  x 16-bit                    -> (sum x, -)                                bias gradients of 16-bit rows
-// A thread owns 2 adjacent channels; blockDim = (C/2 capped at 128) x rows-in-flight.
 // ----------------------------------------------------------------------------------------------------------------
 struct ColReduceParams {
   const void* a;        // x / dy
@@ -206,58 +231,69 @@ struct ColReduceParams {
   float eps;            // mode 3
 };
 
+// A thread owns 8 adjacent channels (one 16-byte load per operand and row); blockDim = (C/8 capped at 64) x rows in
+// flight.  C % 8 == 0 and (C/8 <= 64 with 256 % (C/8) == 0, or C/8 % 64 == 0).
 __global__ void __launch_bounds__(256)
 colreduce_kernel(const ColReduceParams p) {
-  extern __shared__ float red[];   // [rows_in_flight][2][cols*2]
-  const int cols2 = p.C / 2;                        // channel pairs
-  const int cpb = cols2 < 128 ? cols2 : 128;        // channel pairs per block pass
+  extern __shared__ float red[];   // [256 threads][16]
+  const int cols8 = p.C / 8;
+  const int cpb = cols8 < 64 ? cols8 : 64;          // 8-channel chunks per block pass
   const int rif = blockDim.x / cpb;                 // rows in flight
   const int cx = threadIdx.x % cpb, ry = threadIdx.x / cpb;
-  for (int cbase = 0; cbase < cols2; cbase += cpb) {
-    const int c2 = cbase + cx;
-    float s0a = 0.0f, s0b = 0.0f, s1a = 0.0f, s1b = 0.0f;
-    float mean0 = 0.0f, mean1 = 0.0f, rstd0 = 0.0f, rstd1 = 0.0f;
+  for (int cbase = 0; cbase < cols8; cbase += cpb) {
+    const int c8 = cbase + cx;
+    float s0[8], s1[8], mean[8], rstd[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s0[e] = 0.0f; s1[e] = 0.0f; mean[e] = 0.0f; rstd[e] = 0.0f; }
     if (p.mode == 1) {
-      mean0 = __ldg(p.mean + 2 * c2); mean1 = __ldg(p.mean + 2 * c2 + 1);
-      rstd0 = __ldg(p.rstd + 2 * c2); rstd1 = __ldg(p.rstd + 2 * c2 + 1);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { mean[e] = __ldg(p.mean + 8 * c8 + e); rstd[e] = __ldg(p.rstd + 8 * c8 + e); }
     }
     for (long long m = static_cast<long long>(blockIdx.x) * rif + ry; m < p.M; m += static_cast<long long>(gridDim.x) * rif) {
-      const long long idx = m * cols2 + c2;
-      if (p.mode == 0 || p.mode == 4) {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p.a) + idx);
-        const float a0 = lo16(u, p.fp16), a1 = hi16(u, p.fp16);
-        s0a += a0; s0b += a1;
-        if (p.mode == 0) { s1a += a0 * a0; s1b += a1 * a1; }
-      } else if (p.mode == 1) {
-        const uint32_t ud = __ldg(reinterpret_cast<const uint32_t*>(p.a) + idx);
-        float d0 = bf16_lo(ud), d1 = bf16_hi(ud);
-        if (p.b != nullptr) {
-          const uint32_t uo = __ldg(reinterpret_cast<const uint32_t*>(p.b) + idx);
-          if (!(bf16_lo(uo) > 0.0f)) d0 = 0.0f;
-          if (!(bf16_hi(uo) > 0.0f)) d1 = 0.0f;
+      const long long idx = m * cols8 + c8;
+      if (p.mode == 2) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.a) + 2 * idx);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.a) + 2 * idx + 1);
+        s0[0] += a.x; s0[1] += a.y; s0[2] += a.z; s0[3] += a.w; s0[4] += b.x; s0[5] += b.y; s0[6] += b.z; s0[7] += b.w;
+      } else {
+        const uint4 ua = __ldg(reinterpret_cast<const uint4*>(p.a) + idx);
+        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w};
+        if (p.mode == 0 || p.mode == 4) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a0 = lo16(wa[j], p.fp16), a1 = hi16(wa[j], p.fp16);
+            s0[2 * j] += a0; s0[2 * j + 1] += a1;
+            if (p.mode == 0) { s1[2 * j] += a0 * a0; s1[2 * j + 1] += a1 * a1; }
+          }
+        } else {   // mode 1
+          uint4 uo = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);   // "positive": no mask
+          if (p.b != nullptr) uo = __ldg(reinterpret_cast<const uint4*>(p.b) + idx);
+          const uint4 ux = __ldg(reinterpret_cast<const uint4*>(p.c) + idx);
+          const uint32_t wo[4] = {uo.x, uo.y, uo.z, uo.w}, wx[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d0 = bf16_lo(wo[j]) > 0.0f ? bf16_lo(wa[j]) : 0.0f;
+            const float d1 = bf16_hi(wo[j]) > 0.0f ? bf16_hi(wa[j]) : 0.0f;
+            s0[2 * j] += d0; s0[2 * j + 1] += d1;
+            s1[2 * j] += d0 * ((bf16_lo(wx[j]) - mean[2 * j]) * rstd[2 * j]);
+            s1[2 * j + 1] += d1 * ((bf16_hi(wx[j]) - mean[2 * j + 1]) * rstd[2 * j + 1]);
+          }
         }
-        const uint32_t ux = __ldg(reinterpret_cast<const uint32_t*>(p.c) + idx);
-        s0a += d0; s0b += d1;
-        s1a += d0 * ((bf16_lo(ux) - mean0) * rstd0);
-        s1b += d1 * ((bf16_hi(ux) - mean1) * rstd1);
-      } else if (p.mode == 2) {
-        const float2 v = __ldg(reinterpret_cast<const float2*>(p.a) + idx);
-        s0a += v.x; s0b += v.y;
       }
     }
-    float* my = red + (ry * 2) * (2 * cpb);
-    my[2 * cx] = s0a; my[2 * cx + 1] = s0b;
-    my[2 * cpb + 2 * cx] = s1a; my[2 * cpb + 2 * cx + 1] = s1b;
+    float* my = red + threadIdx.x * 16;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { my[e] = s0[e]; my[8 + e] = s1[e]; }
     __syncthreads();
     if (ry == 0) {
       for (int r = 1; r < rif; ++r) {
-        const float* o = red + (r * 2) * (2 * cpb);
-        s0a += o[2 * cx]; s0b += o[2 * cx + 1];
-        s1a += o[2 * cpb + 2 * cx]; s1b += o[2 * cpb + 2 * cx + 1];
+        const float* o = red + (r * cpb + cx) * 16;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s0[e] += o[e]; s1[e] += o[8 + e]; }
       }
       float* dst = p.part + static_cast<long long>(blockIdx.x) * 2 * p.C;
-      dst[2 * c2] = s0a; dst[2 * c2 + 1] = s0b;
-      dst[p.C + 2 * c2] = s1a; dst[p.C + 2 * c2 + 1] = s1b;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { dst[8 * c8 + e] = s0[e]; dst[p.C + 8 * c8 + e] = s1[e]; }
     }
     __syncthreads();
   }
@@ -395,46 +431,75 @@ maxpool3x3s2_fwd_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ o
   }
 }
 
+// `pooled` is the forward output.  A pixel receives a window's gradient iff it equals the window maximum and no EARLIER
+// pixel of the window (row-major scan order, PyTorch's tie rule) does; only candidates (x == max) scan their window.
+// Non-positive pixels take no gradient: the pooled tensor is a ReLU output, so its gradient is masked there anyway.
 __global__ void __launch_bounds__(256)
-maxpool3x3s2_bwd_kernel(const uint32_t* __restrict__ x, const uint32_t* __restrict__ dy, uint32_t* __restrict__ dx, int F,
-                        int H, int W, int C2, int P, int Q) {
-  const long long total = static_cast<long long>(F) * H * W * C2;
+maxpool3x3s2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ pooled, const uint4* __restrict__ dy,
+                        uint4* __restrict__ dx, int F, int H, int W, int C8, int P, int Q) {
+  const long long total = static_cast<long long>(F) * H * W * C8;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % C2);
-    long long t = i / C2;
+    const int c = static_cast<int>(i % C8);
+    long long t = i / C8;
     const int xx = static_cast<int>(t % W); t /= W;
     const int y = static_cast<int>(t % H);
     const long long f = t / H;
-    const uint32_t self = __ldg(x + i);
-    const float va = bf16_lo(self), vb = bf16_hi(self);
-    float ga = 0.0f, gb = 0.0f;
-    // windows (pp, q) with 2pp-1 <= y <= 2pp+1
-    for (int pp = (y >> 1); pp <= ((y + 1) >> 1); ++pp) {
-      if (pp >= P) continue;
-      for (int q = (xx >> 1); q <= ((xx + 1) >> 1); ++q) {
-        if (q >= Q) continue;
-        bool first_a = true, first_b = true;   // is (y, xx) the first maximum of this window?
-        for (int r = 0; r < 3; ++r) {
-          const int y2 = 2 * pp + r - 1;
-          if (y2 < 0 || y2 >= H) continue;
-          for (int s = 0; s < 3; ++s) {
-            const int x2 = 2 * q + s - 1;
-            if (x2 < 0 || x2 >= W) continue;
-            if (y2 == y && x2 == xx) continue;
-            const uint32_t u = __ldg(x + ((f * H + y2) * W + x2) * C2 + c);
-            const bool before = (y2 < y) || (y2 == y && x2 < xx);
-            const float oa = bf16_lo(u), ob = bf16_hi(u);
-            if (oa > va || (before && oa == va)) first_a = false;
-            if (ob > vb || (before && ob == vb)) first_b = false;
+    const uint4 self = __ldg(x + i);
+    const uint32_t sw[4] = {self.x, self.y, self.z, self.w};
+    float v[8], g[8];
+    bool any_pos = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = bf16_lo(sw[j]); v[2 * j + 1] = bf16_hi(sw[j]);
+      g[2 * j] = 0.0f; g[2 * j + 1] = 0.0f;
+      any_pos = any_pos || v[2 * j] > 0.0f || v[2 * j + 1] > 0.0f;
+    }
+    if (any_pos) {
+      for (int pp = (y >> 1); pp <= ((y + 1) >> 1); ++pp) {
+        if (pp >= P) continue;
+        for (int q = (xx >> 1); q <= ((xx + 1) >> 1); ++q) {
+          if (q >= Q) continue;
+          const long long widx = ((f * P + pp) * Q + q) * C8 + c;
+          const uint4 mx = __ldg(pooled + widx);
+          const uint32_t mw[4] = {mx.x, mx.y, mx.z, mx.w};
+          bool cand[8];
+          bool any = false;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cand[2 * j] = v[2 * j] > 0.0f && v[2 * j] == bf16_lo(mw[j]);
+            cand[2 * j + 1] = v[2 * j + 1] > 0.0f && v[2 * j + 1] == bf16_hi(mw[j]);
+            any = any || cand[2 * j] || cand[2 * j + 1];
+          }
+          if (!any) continue;
+          // tie check: an equal value EARLIER in the window's row-major scan order wins
+          for (int r = 0; r < 3; ++r) {
+            const int y2 = 2 * pp + r - 1;
+            if (y2 < 0 || y2 > y) continue;
+            for (int s2 = 0; s2 < 3; ++s2) {
+              const int x2 = 2 * q + s2 - 1;
+              if (x2 < 0 || x2 >= W) continue;
+              if (!(y2 < y || x2 < xx)) continue;
+              const uint4 u = __ldg(x + ((f * H + y2) * W + x2) * C8 + c);
+              const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (bf16_lo(uw[j]) == v[2 * j]) cand[2 * j] = false;
+                if (bf16_hi(uw[j]) == v[2 * j + 1]) cand[2 * j + 1] = false;
+              }
+            }
+          }
+          const uint4 gy = __ldg(dy + widx);
+          const uint32_t gw[4] = {gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (cand[2 * j]) g[2 * j] += bf16_lo(gw[j]);
+            if (cand[2 * j + 1]) g[2 * j + 1] += bf16_hi(gw[j]);
           }
         }
-        const uint32_t g = __ldg(dy + ((f * P + pp) * Q + q) * C2 + c);
-        if (first_a) ga += bf16_lo(g);
-        if (first_b) gb += bf16_hi(g);
       }
     }
-    dx[i] = pack_bf16x2(ga, gb);
+    dx[i] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], g[3]), pack_bf16x2(g[4], g[5]), pack_bf16x2(g[6], g[7]));
   }
 }
 

@@ -149,12 +149,15 @@ def maxpool_fwd(x):
     return out
 
 
-def maxpool_bwd(x, dy):
-    _req(x, BF16, "x"); _req(dy, BF16, "dy")
+def maxpool_bwd(x, pooled, dy):
+    """x: the pooled layer's input (a ReLU output), pooled: maxpool_fwd(x), dy: gradient of pooled."""
+    _req(x, BF16, "x"); _req(pooled, BF16, "pooled"); _req(dy, BF16, "dy")
     f, h, w, c = x.shape
+    if pooled.shape != dy.shape:
+        raise RuntimeError("maxpool_bwd: pooled / dy shape mismatch")
     dx = torch.empty_like(x)
-    _call("sblk_maxpool3x3s2_bwd", "maxpool bwd", 0, 2 * (2 * x.numel() + dy.numel()), _p(x), _p(dy), _p(dx), f, h, w, c,
-          _stream())
+    _call("sblk_maxpool3x3s2_bwd", "maxpool bwd", 0, 2 * (2 * x.numel() + 2 * dy.numel()), _p(x), _p(pooled), _p(dy),
+          _p(dx), f, h, w, c, _stream())
     return dx
 
 

@@ -85,7 +85,8 @@ def conv_wgrad(x, dy, r, stride):
     co = dy.shape[-1]
     pad = r // 2
     dw = _wgrad_gemm(dy.reshape(-1, co), lambda ld: ot.im2col_t(x, r, r, stride, pad, ld), r * r * ci)
-    return dw.view(co, r, r, ci).permute(0, 3, 1, 2).contiguous()
+    # ([Co,Ci*r*r] round trip: canonical strides even for 1x1 filters, as DDP's gradient buckets expect)
+    return dw.view(co, r, r, ci).permute(0, 3, 1, 2).reshape(co, ci * r * r).contiguous().view(co, ci, r, r)
 
 
 class _BNState:
@@ -141,14 +142,14 @@ class StemFn(torch.autograd.Function):
         act, st = bn_forward_train(raw, bn, relu=True)                    # [M, 64] = [F,44,44,64]
         act4 = act.view(n * t, 44, 44, 64)
         out = ot.maxpool_fwd(act4)
-        ctx.save_for_backward(xs, raw, act4, gamma)
+        ctx.save_for_backward(xs, raw, act4, gamma, out)
         ctx.st = st
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        xs, raw, act4, gamma = ctx.saved_tensors
-        dact = ot.maxpool_bwd(act4, dout.contiguous())
+        xs, raw, act4, gamma, pooled = ctx.saved_tensors
+        dact = ot.maxpool_bwd(act4, pooled, dout.contiguous())
         draw, dgamma, dbeta, _ = bn_backward_train(dact.view(-1, 64), act4.view(-1, 64), raw, ctx.st, gamma)
         n, t = xs.shape[0], xs.shape[1]
         dw = _wgrad_gemm(draw, lambda ld: ot.stem_im2col(xs, transposed=True, ld_out=ld), 256)

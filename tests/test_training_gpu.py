@@ -135,7 +135,7 @@ def test_maxpool_forward_backward(dev):
     want.backward(dy.float().permute(0, 3, 1, 2))
     out = ot.maxpool_fwd(x)
     assert torch.equal(out.float(), want.detach().permute(0, 2, 3, 1))
-    dx = ot.maxpool_bwd(x, dy)
+    dx = ot.maxpool_bwd(x, out, dy)
     wg = x32.grad.permute(0, 2, 3, 1)
     # ties (exact zeros after ReLU, equal bf16 values) go to the first maximum in both implementations
     mism = ((dx.float() - wg).abs() > 1e-2 * wg.abs().max()).float().mean().item()
@@ -518,3 +518,31 @@ def test_stage1_training_step_with_reference_heads(dev):
     lb2, _ = step(ours, 4)
     la2, _ = step(ref, 4)
     assert abs(la2 - lb2) < 5e-3 * abs(la2)
+
+
+def test_ddp_gradient_allreduce_two_gpus():
+    """BASELINE configs[3]: the stage-1 model under DistributedDataParallel on 2 GPUs — every rank ends the backward with
+    the NCCL-averaged gradient of the libsblk backward (tests/ddp_train_worker.py under torchrun)."""
+    import subprocess
+    import sys
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(here, "ddp_train_worker.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ddp gradient all-reduce OK") == 2
+
+
+def test_stage1_module_has_the_reference_state_dict(dev):
+    """stage1.Stage1Classifier mirrors ...classify/transformer/transformer.py key for key."""
+    from oracle import ref_runtime
+    from sbl_for_multilingual_lip_reading_b200 import stage1
+    R = ref_runtime.load_reference("cls")
+    ref = ref_runtime.build_cls_reference(R)
+    ours = stage1.Stage1Classifier(n_layers_enc=3)
+    a, b = ref.state_dict(), ours.state_dict()
+    assert sorted(a) == sorted(b)
+    assert all(a[k].shape == b[k].shape and a[k].dtype == b[k].dtype for k in a)
+    ours.load_state_dict(a)
