@@ -750,6 +750,16 @@ def run_config4_sweep(args):
         ours = ttr.Transformer(enc, dec, None)
     ours.load_state_dict(ref.state_dict())
     ours = ours.to(dev).eval()
+    # row f.1: the SBL decoder on libsblk as well (decoder.py) — the whole model behind the reference's Transformer class
+    with dropin.patched_reference(R.dir, decoder=True):
+        import transformer.decoder as tdec
+        torch.manual_seed(7)
+        enc2 = tenc.Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+        dec2 = tdec.Decoder(0, 1, 58, 512, 6, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1,
+                            pe_maxlen=5000)
+        full = ttr.Transformer(enc2, dec2, None)
+    full.load_state_dict(ref.state_dict())
+    full = full.to(dev).eval()
     T = 30
     rows = []
     for gb in [int(v) for v in args.config4_batches.split(",")]:
@@ -792,21 +802,30 @@ def run_config4_sweep(args):
                 return sharding.max_over_ranks((time.perf_counter() - t0) / reps, dev)
 
         reps = max(2, min(args.steps, 10))
+        t_full, o0 = timed(full, reps)
         t_ours, o1 = timed(ours, reps)
         t_ref, o2 = timed(ref, reps)
         e_ours, e_ref = timed_encoder(ours, reps), timed_encoder(ref, reps)
         rows.append({"global_batch": n * world, "clips_per_gpu": n,
+                     "b200_full_model_clips_per_s": n * world / t_full,
                      "b200_dropins_clips_per_s": n * world / t_ours, "reference_cuda_fp32_clips_per_s": n * world / t_ref,
-                     "ms_per_forward": {"b200_dropins": 1e3 * t_ours, "reference_cuda_fp32": 1e3 * t_ref},
+                     "ms_per_forward": {"b200_full_model": 1e3 * t_full, "b200_dropins": 1e3 * t_ours,
+                                        "reference_cuda_fp32": 1e3 * t_ref},
                      "visual_encoder_ms": {"b200_dropins": 1e3 * e_ours, "reference_cuda_fp32": 1e3 * e_ref},
-                     "decoder_share_of_forward_b200": 1.0 - e_ours / t_ours})
+                     "decoder_share_of_forward_b200": 1.0 - e_ours / t_ours,
+                     "logits_rel_err_full_vs_reference": {
+                         "l2r": float(((o0[0] - o2[0]).norm() / o2[0].norm())),
+                         "r2l": float(((o0[2] - o2[2]).norm() / o2[2].norm()))}})
     if rank == 0:
         line = {"metric": "sbl_full_model_teacher_forced_forward_clips_per_sec", "unit": UNIT, "n_gpus": world,
                 "config": {"workload": "BASELINE configs[4]: full SBL multilingual model teacher-forced forward (B200 visual "
                                        "frontend + encoder, reference bidirectional decoder from oracle/_ref on top), "
                                        f"{T}-frame clips, batch sweep, batch sharded over {world} GPU(s)",
-                           "decoder": "unmodified reference Decoder.forward (decoder.py:79-191): 16 steps x 2 directions x "
-                                      "6 layers, full-prefix recompute, torch CUDA fp32",
+                           "arms": "b200_full_model = frontend + encoder + SBL decoder on libsblk (decoder.py); b200_dropins = "
+                                   "libsblk frontend + encoder under the UNMODIFIED reference decoder; reference_cuda_fp32 = "
+                                   "all-reference model (cuDNN / cuBLAS fp32, TF32 off)",
+                           "decoder": "Decoder.forward (decoder.py:79-191): 16 steps x 2 directions x 6 layers, full-prefix "
+                                      "recompute each step",
                            "always_on_dropout": True},
                 "sweep": rows, "data": "synthetic", "timing": "wall clock, synchronize both sides, max over ranks"}
         os.write(json_fd, (json.dumps(line) + "\n").encode())

@@ -305,6 +305,26 @@ int sblk_attention_train_fwd(const void* qkv, const float* drop, float* probs, v
 int sblk_attention_train_bwd(const void* qkv, const float* drop, const float* probs, const void* dout, void* dqkv,
                              const int* lengths, int N, int T, int H, float scale, void* stream);
 
+/* ---- SBL bidirectional decoder glue ----------------------------------------------------------------
+ * The decoder's projections, FFNs and residual + LayerNorms run on the encoder entry points above (sblk_gemm_fwd,
+ * sblk_gemm_splitk_fwd + sblk_sum_layernorm_fwd, sblk_gemm_ln_fwd); these three add what the encoder does not have. */
+/* Multi-head attention with separate query and key / value sources (enc16, d_k = 64, head h at columns h*64):
+ * Q rows (b*Lq + i)*ldq, K / V rows (b*Lk + j)*ldk|ldv, out rows (b*Lq + i)*ldo; mask = causal (key j > query i) and / or
+ * key lengths klens[b] (NULL = all Lk).  Lq <= 32, Lk <= 128.
+ * replaces: MultiHeadAttention / ScaledDotProductAttention inside DecoderLayer (decoder.py:388-408, attention.py:32-83)
+ * with get_subsequent_mask (utils.py:116-124) — self-attention over the decoded prefix and decoder-encoder attention */
+int sblk_xattention_fwd(const void* q, const void* k, const void* v, void* out, const int* klens, int ldq, int ldk,
+                        int ldv, int ldo, int N, int Lq, int Lk, int H, int causal, float scale, void* stream);
+/* x[r, :] = emb[tokens[r], :] * scale + pe[r % L, :] for r < rows (tokens int64): fp32 [rows, D] and (optional) enc16.
+ * replaces: tgt_word_emb(ys) * x_logit_scale + positional_encoding(ys), decoder.py:323-327 */
+int sblk_embed_pe_fwd(const void* tokens_i64, const float* emb, const float* pe, float* out_f32, void* out_16, int rows,
+                      int L, int D, int vocab, float scale, void* stream);
+/* Synchronous bidirectional mixing of the two directions' hidden states [N, L, D] fp32 (the reference's aliased in-place
+ * loops): l2r' = l2r + flip_L(r2l); r2l' = r2l + flip_L(l2r') = 2 r2l + flip_L(l2r).  Writes fp32 + enc16 copies.
+ * replaces: decoder.py:336-346,358-362 */
+int sblk_bidir_mix_fwd(const float* l2r, const float* r2l, float* l2r_out, float* r2l_out, void* l2r_16, void* r2l_16,
+                       int N, int L, int D, void* stream);
+
 /* ---- one-shot all-gather of the per-GPU outputs over NVLink / NVSwitch peer memory (one process per GPU) ----------
  * replaces: nn.DataParallel's gather of the replicas' outputs, SBL/train.py:114-115.
  * sblk_p2p_alloc: cudaMalloc + zero a buffer of its own and return its 64-byte CUDA IPC handle (exchange it with the

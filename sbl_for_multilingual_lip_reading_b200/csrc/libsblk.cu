@@ -25,6 +25,7 @@
 #include "sblk_qkv_attn.cuh"
 #include "sblk_encoder_stack.cuh"
 #include "sblk_train.cuh"
+#include "sblk_decoder.cuh"
 
 namespace {
 
@@ -149,6 +150,7 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::attention_kernel<16>, 100 * 1024))) return rc;
     if ((rc = set_smem(sblk::attn_train_kernel<false>, 104 * 1024))) return rc;
     if ((rc = set_smem(sblk::attn_train_kernel<true>, 104 * 1024))) return rc;
+    if ((rc = set_smem(sblk::xattention_kernel, 100 * 1024))) return rc;
     st.ready = true;
   }
   if (num_sms_out != nullptr)
@@ -1384,6 +1386,53 @@ int sblk_attention_train_fwd(const void* qkv, const float* drop, float* probs, v
 int sblk_attention_train_bwd(const void* qkv, const float* drop, const float* probs, const void* dout, void* dqkv,
                              const int* lengths, int N, int T, int H, float scale, void* stream) {
   return attn_train_impl(true, qkv, drop, const_cast<float*>(probs), nullptr, dout, dqkv, lengths, N, T, H, scale, stream);
+}
+
+
+// =====================================================================================================================
+// SBL bidirectional decoder glue (row f.1): see include/sblk.h "decoder" section, sblk_decoder.cuh
+// =====================================================================================================================
+int sblk_xattention_fwd(const void* q, const void* k, const void* v, void* out, const int* klens, int ldq, int ldk,
+                        int ldv, int ldo, int N, int Lq, int Lk, int H, int causal, float scale, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!q || !k || !v || !out) return fail(-1, "sblk_xattention_fwd: null pointer");
+  if (N <= 0 || H <= 0 || Lq <= 0 || Lq > 32 || Lk <= 0 || Lk > 128)
+    return fail(-1, "sblk_xattention_fwd: bad shape N=%d H=%d Lq=%d Lk=%d (Lq <= 32, Lk <= 128)", N, H, Lq, Lk);
+  if (ldq < H * 64 || ldk < H * 64 || ldv < H * 64 || ldo < H * 64) return fail(-1, "sblk_xattention_fwd: row pitches must cover H*64 features");
+  sblk::XAttnParams p;
+  p.q = static_cast<const uint16_t*>(q); p.k = static_cast<const uint16_t*>(k); p.v = static_cast<const uint16_t*>(v);
+  p.out = static_cast<uint16_t*>(out); p.klens = klens; p.ldq = ldq; p.ldk = ldk; p.ldv = ldv; p.ldo = ldo;
+  p.N = N; p.Lq = Lq; p.Lk = Lk; p.H = H; p.causal = causal ? 1 : 0; p.scale = scale; p.fp16 = SBLK_ENC_FP16 ? 1 : 0;
+  const size_t fl = static_cast<size_t>(Lq + 2 * Lk) * 65 + static_cast<size_t>(Lq) * (Lk + 1);
+  return launch(sblk::xattention_kernel, dim3(N * H), dim3(128), fl * sizeof(float), static_cast<cudaStream_t>(stream),
+                true, "xattention_kernel", p);
+}
+
+int sblk_embed_pe_fwd(const void* tokens_i64, const float* emb, const float* pe, float* out_f32, void* out_16, int rows,
+                      int L, int D, int vocab, float scale, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!tokens_i64 || !emb || !pe || !out_f32) return fail(-1, "sblk_embed_pe_fwd: null pointer");
+  if (rows <= 0 || L <= 0 || rows % L != 0 || D <= 0 || D % 4 != 0 || vocab <= 0) return fail(-1, "sblk_embed_pe_fwd: bad shape");
+  if (!aligned16(emb) || !aligned16(pe) || !aligned16(out_f32) || (out_16 && (reinterpret_cast<uintptr_t>(out_16) & 7u)))
+    return fail(-1, "sblk_embed_pe_fwd: misaligned pointer");
+  return launch(sblk::embed_pe_kernel, dim3(elementwise_grid(static_cast<long long>(rows) * (D / 4), 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "embed_pe_kernel", static_cast<const long long*>(tokens_i64), emb,
+                pe, out_f32, static_cast<uint16_t*>(out_16), rows, L, D, vocab, scale, SBLK_ENC_FP16 ? 1 : 0);
+}
+
+int sblk_bidir_mix_fwd(const float* l2r, const float* r2l, float* l2r_out, float* r2l_out, void* l2r_16, void* r2l_16,
+                       int N, int L, int D, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!l2r || !r2l || !l2r_out || !r2l_out || !l2r_16 || !r2l_16) return fail(-1, "sblk_bidir_mix_fwd: null pointer");
+  if (N <= 0 || L <= 0 || D <= 0 || D % 4 != 0) return fail(-1, "sblk_bidir_mix_fwd: bad shape");
+  if (l2r == l2r_out || r2l == r2l_out || l2r == r2l_out || r2l == l2r_out) return fail(-1, "sblk_bidir_mix_fwd: outputs must not alias inputs");
+  if (!aligned16(l2r) || !aligned16(r2l) || !aligned16(l2r_out) || !aligned16(r2l_out)) return fail(-1, "sblk_bidir_mix_fwd: pointers must be 16-byte aligned");
+  return launch(sblk::bidir_mix_kernel, dim3(elementwise_grid(static_cast<long long>(N) * L * (D / 4), 256, sms)), dim3(256), 0,
+                static_cast<cudaStream_t>(stream), false, "bidir_mix_kernel", l2r, r2l, l2r_out, r2l_out,
+                static_cast<uint16_t*>(l2r_16), static_cast<uint16_t*>(r2l_16), N, L, D, SBLK_ENC_FP16 ? 1 : 0);
 }
 
 }  // extern "C"

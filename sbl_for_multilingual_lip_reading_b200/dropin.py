@@ -16,6 +16,7 @@ import importlib
 import runpy
 import sys
 
+from . import decoder as _dec
 from . import encoder as _enc
 from . import video_frontend as _vf
 
@@ -30,13 +31,21 @@ _PATCHED = {
 }
 
 
-def patch_reference(ref_dir):
-    """Rebind the hot-path names inside the reference package found at `ref_dir`.  Returns
-    ({module name: module}, {(<module>, <attr>): original}) so the patch can be undone."""
+# opt-in (evaluation only): the SBL bidirectional decoder, greedy decode + teacher-forced forward on libsblk (decoder.py);
+# training keeps the reference decoder
+_PATCHED_DECODER = {"transformer.decoder": {"Decoder": _dec.Decoder, "DecoderLayer": _dec.DecoderLayer}}
+
+
+def patch_reference(ref_dir, decoder=False):
+    """Rebind the hot-path names inside the reference package found at `ref_dir` (decoder=True: the SBL decoder too).
+    Returns ({module name: module}, {(<module>, <attr>): original}) so the patch can be undone."""
     if ref_dir not in sys.path:
         sys.path.insert(0, ref_dir)
     mods, saved = {}, {}
-    for mod_name, names in _PATCHED.items():
+    table = dict(_PATCHED)
+    if decoder:
+        table.update(_PATCHED_DECODER)
+    for mod_name, names in table.items():
         mod = importlib.import_module(mod_name)
         mods[mod_name] = mod
         for attr, repl in names.items():
@@ -55,8 +64,8 @@ def unpatch_reference(ref_dir, saved):
 
 
 @contextlib.contextmanager
-def patched_reference(ref_dir):
-    mods, saved = patch_reference(ref_dir)
+def patched_reference(ref_dir, decoder=False):
+    mods, saved = patch_reference(ref_dir, decoder=decoder)
     try:
         yield mods
     finally:

@@ -305,3 +305,126 @@ def test_stage_error_budget(models, dev):
     assert table["features"] < 4e-3, table
     assert table["enc_layer5"] < 4e-3, table
     assert max(table.values()) < 1e-2, table
+
+
+# ------------------------------------------------------------------ row f.1: the SBL decoder on libsblk
+@pytest.fixture(scope="module")
+def native_decoder(models, dev):
+    """The libsblk Decoder loaded from the reference decoder's state dict (same keys)."""
+    from sbl_for_multilingual_lip_reading_b200.decoder import Decoder
+    R, ref, ours = models
+    dec = Decoder(0, 1, 58, 512, 6, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1, pe_maxlen=5000)
+    sd = ref.decoder.state_dict()
+    assert sorted(sd) == sorted(dec.state_dict())
+    dec.load_state_dict(sd)
+    return dec.to(dev).eval()
+
+
+def test_native_decoder_init_matches_reference_under_same_seed(models):
+    from sbl_for_multilingual_lip_reading_b200.decoder import Decoder
+    R, ref, ours = models
+    torch.manual_seed(123)
+    a = R.Decoder(0, 1, 58, 512, 2, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1, pe_maxlen=100)
+    torch.manual_seed(123)
+    b = Decoder(0, 1, 58, 512, 2, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1, pe_maxlen=100)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+def test_native_decoder_teacher_forced_logits(models, native_decoder, dev):
+    """Decoder.forward (decoder.py:79-191) on the SAME encoder outputs and the same coin flips: logits of all 16 steps
+    within 5e-3 of the reference decoder (fp16 operands, fp32 accumulation / LayerNorm / softmax / mixing)."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    R, ref, ours = models
+    n, t = 16, 30
+    g = torch.Generator().manual_seed(5)
+    x = synth.structured_clips(n, t, seed=321)[:, 0].to(dev)
+    tgt = torch.full((n, 14), -1, dtype=torch.long)
+    for i in range(n):
+        ln = int(torch.randint(3, 12, (1,), generator=g))
+        tgt[i, :ln] = torch.randint(2, 58, (ln,), generator=g)
+    tgt_r = tgt.clone()
+    for i in range(n):
+        ln = int((tgt[i] >= 0).sum())
+        tgt_r[i, :ln] = tgt[i, :ln].flip(0)
+    tgt, tgt_r = tgt.to(dev), tgt_r.to(dev)
+    from oracle import ref_runtime
+    with torch.no_grad(), ref_runtime.dropout_neutralised(R):
+        feat = ref.visual_frontend(x.unsqueeze(4).permute(0, 4, 1, 2, 3))
+        enc, *_ = ref.encoder(feat, [t] * n)
+        random.seed(11)
+        pa = ref.decoder(tgt, tgt_r, enc, [t] * n)
+        random.seed(11)
+        pb = native_decoder(tgt, tgt_r, enc, [t] * n)
+    assert torch.equal(pa[1], pb[1]) and torch.equal(pa[3], pb[3])
+    e1, e2 = rel_fro(pb[0], pa[0]), rel_fro(pb[2], pa[2])
+    _dump("r02_native_decoder_teacher_forced.json", {"pred_l2r_rel_err": e1, "pred_r2l_rel_err": e2})
+    assert e1 < 5e-3 and e2 < 5e-3, (e1, e2)
+
+
+def test_native_decoder_greedy_tokens_1000_clips(models, native_decoder, dev):
+    """recognize_beam (decoder.py:301-385) of the libsblk decoder vs the reference decoder on the reference's own fp32
+    encoder outputs for the 1,000 structured clips, margin-aware like the encoder test: every sequence whose smallest
+    top-1/top-2 margin is clear of 2 x the largest logit difference between the two decoders (measured on the steps whose
+    prefixes are still identical) must be identical; near-ties are counted."""
+    from oracle import ref_runtime
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    R, ref, ours = models
+    chunk, chunks = 40, 25
+    res = {d: dict(same=0, clear=0, clear_same=0) for d in ("l2r", "r2l")}
+    thr = {"l2r": 0.0, "r2l": 0.0}
+    recs = []
+    with torch.no_grad(), ref_runtime.dropout_neutralised(R):
+        for c in range(chunks):
+            x = synth.structured_clips(chunk, T, seed=5000 + c)[:, 0].to(dev)
+            a = _recognize(ref, x)
+            b = native_decoder._greedy(a[2], want_logits=True)
+            for di, d in enumerate(("l2r", "r2l")):
+                la, lb = a[3 + di], b[2 + di]
+                top2 = la.topk(2, dim=-1).values
+                margin = (top2[..., 0] - top2[..., 1]).min(dim=1).values
+                # BOTH directions feed every step (bidirectional mixing): a prefix is "still identical" while both are
+                fd = torch.minimum(_first_divergence(a[0], b[0]), _first_divergence(a[1], b[1]))
+                valid = torch.arange(la.shape[1], device=dev)[None, :] <= fd[:, None]
+                thr[d] = max(thr[d], 2.0 * float(((lb - la).abs().max(dim=-1).values * valid).max()))
+                same = (a[di] == b[di]).all(1)
+                recs.append((d, margin.tolist(), same.tolist()))
+                res[d]["same"] += int(same.sum())
+    for d, margins, sames in recs:
+        for mg, s_ in zip(margins, sames):
+            if mg > thr[d]:
+                res[d]["clear"] += 1
+                res[d]["clear_same"] += int(s_)
+    out = {"clips": chunk * chunks, "margin_threshold_logits": thr, **res}
+    _dump("r02_native_decoder_greedy_parity.json", out)
+    print(json.dumps(out))
+    for d in ("l2r", "r2l"):
+        assert res[d]["clear_same"] == res[d]["clear"], (d, res[d])
+        assert res[d]["same"] >= 970, (d, res[d])
+
+
+def test_reference_transformer_on_all_dropins_recognize(models, dev):
+    """`Transformer.recognize` with frontend, encoder AND decoder replaced (dropin.patch_reference(..., decoder=True)):
+    the whole SBL model on libsblk, assembled by the reference's own Transformer class."""
+    from oracle import ref_runtime
+    from sbl_for_multilingual_lip_reading_b200 import dropin, synth
+    from sbl_for_multilingual_lip_reading_b200.decoder import Decoder as B200Decoder
+    R, ref, ours = models
+    with dropin.patched_reference(R.dir, decoder=True):
+        import transformer.decoder as tdec
+        import transformer.encoder as tenc
+        import transformer.transformer as ttr
+        enc = tenc.Encoder(512, 6, 8, 64, 64, 512, 2048, dropout=0.1, pe_maxlen=5000)
+        dec = tdec.Decoder(0, 1, 58, 512, 6, 8, 64, 64, 512, 2048, dropout=0.1, tgt_emb_prj_weight_sharing=1,
+                           pe_maxlen=5000)
+        full = ttr.Transformer(enc, dec, None)
+    assert isinstance(full.decoder, B200Decoder)
+    full.load_state_dict(ref.state_dict())
+    full = full.to(dev).eval()
+    full.visual_frontend.always_on_dropout = False
+    x = synth.structured_clips(40, T, seed=5003)[:, 0].to(dev)
+    with torch.no_grad(), ref_runtime.dropout_neutralised(R):
+        a_l2r, a_r2l = ref.recognize(x)
+        b_l2r, b_r2l = full.recognize(x)
+    assert b_l2r.shape == a_l2r.shape == (40, 17) and b_l2r.dtype == torch.long
+    assert int((a_l2r == b_l2r).all(1).sum()) >= 38 and int((a_r2l == b_r2l).all(1).sum()) >= 36
