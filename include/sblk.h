@@ -315,10 +315,10 @@ int sblk_attention_train_bwd(const void* qkv, const float* drop, const float* pr
  * with get_subsequent_mask (utils.py:116-124) — self-attention over the decoded prefix and decoder-encoder attention */
 int sblk_xattention_fwd(const void* q, const void* k, const void* v, void* out, const int* klens, int ldq, int ldk,
                         int ldv, int ldo, int N, int Lq, int Lk, int H, int causal, float scale, void* stream);
-/* x[r, :] = emb[tokens[r], :] * scale + pe[r % L, :] for r < rows (tokens int64): fp32 [rows, D] and (optional) enc16.
- * replaces: tgt_word_emb(ys) * x_logit_scale + positional_encoding(ys), decoder.py:323-327 */
-int sblk_embed_pe_fwd(const void* tokens_i64, const float* emb, const float* pe, float* out_f32, void* out_16, int rows,
-                      int L, int D, int vocab, float scale, void* stream);
+/* x[n*L + l, :] = emb[tokens[n*ld_tokens + l], :] * scale + pe[l, :] (tokens int64, rows = N*L): fp32 [rows, D] and
+ * (optional) enc16.  replaces: tgt_word_emb(ys) * x_logit_scale + positional_encoding(ys), decoder.py:323-327 */
+int sblk_embed_pe_fwd(const void* tokens_i64, int ld_tokens, const float* emb, const float* pe, float* out_f32,
+                      void* out_16, int rows, int L, int D, int vocab, float scale, void* stream);
 /* Synchronous bidirectional mixing of the two directions' hidden states [N, L, D] fp32 (the reference's aliased in-place
  * loops): l2r' = l2r + flip_L(r2l); r2l' = r2l + flip_L(l2r') = 2 r2l + flip_L(l2r).  Writes fp32 + enc16 copies.
  * replaces: decoder.py:336-346,358-362 */

@@ -1409,16 +1409,16 @@ int sblk_xattention_fwd(const void* q, const void* k, const void* v, void* out, 
                 true, "xattention_kernel", p);
 }
 
-int sblk_embed_pe_fwd(const void* tokens_i64, const float* emb, const float* pe, float* out_f32, void* out_16, int rows,
-                      int L, int D, int vocab, float scale, void* stream) {
+int sblk_embed_pe_fwd(const void* tokens_i64, int ld_tokens, const float* emb, const float* pe, float* out_f32,
+                      void* out_16, int rows, int L, int D, int vocab, float scale, void* stream) {
   int sms, rc;
   if ((rc = ensure_init(&sms))) return rc;
   if (!tokens_i64 || !emb || !pe || !out_f32) return fail(-1, "sblk_embed_pe_fwd: null pointer");
-  if (rows <= 0 || L <= 0 || rows % L != 0 || D <= 0 || D % 4 != 0 || vocab <= 0) return fail(-1, "sblk_embed_pe_fwd: bad shape");
+  if (rows <= 0 || L <= 0 || rows % L != 0 || D <= 0 || D % 4 != 0 || vocab <= 0 || ld_tokens < L) return fail(-1, "sblk_embed_pe_fwd: bad shape");
   if (!aligned16(emb) || !aligned16(pe) || !aligned16(out_f32) || (out_16 && (reinterpret_cast<uintptr_t>(out_16) & 7u)))
     return fail(-1, "sblk_embed_pe_fwd: misaligned pointer");
   return launch(sblk::embed_pe_kernel, dim3(elementwise_grid(static_cast<long long>(rows) * (D / 4), 256, sms)), dim3(256), 0,
-                static_cast<cudaStream_t>(stream), false, "embed_pe_kernel", static_cast<const long long*>(tokens_i64), emb,
+                static_cast<cudaStream_t>(stream), false, "embed_pe_kernel", static_cast<const long long*>(tokens_i64), ld_tokens, emb,
                 pe, out_f32, static_cast<uint16_t*>(out_16), rows, L, D, vocab, scale, SBLK_ENC_FP16 ? 1 : 0);
 }
 

@@ -93,19 +93,19 @@ xattention_kernel(const XAttnParams p) {
   }
 }
 
-// x[n, l, :] = emb[tok[n, l], :] * scale + pe[l, :]   -> fp32 and enc16 copies ([N*L, D], D % 4 == 0)
+// x[n, l, :] = emb[tok[n * ld_tok + l], :] * scale + pe[l, :]   -> fp32 and enc16 copies ([N*L, D], D % 4 == 0)
 // decoder.py:323-327: self.tgt_word_emb(ys) * self.x_logit_scale + self.positional_encoding(ys)
 __global__ void __launch_bounds__(256)
-embed_pe_kernel(const long long* __restrict__ tok, const float* __restrict__ emb, const float* __restrict__ pe,
-                float* __restrict__ out_f32, uint16_t* __restrict__ out_16, int rows, int L, int D, int vocab, float scale,
-                int fp16) {
+embed_pe_kernel(const long long* __restrict__ tok, int ld_tok, const float* __restrict__ emb,
+                const float* __restrict__ pe, float* __restrict__ out_f32, uint16_t* __restrict__ out_16, int rows, int L,
+                int D, int vocab, float scale, int fp16) {
   const int d4 = D / 4;
   const long long total = static_cast<long long>(rows) * d4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % d4);
     const int r = static_cast<int>(i / d4);
-    long long t = tok[r];
+    long long t = tok[static_cast<long long>(r / L) * ld_tok + (r % L)];
     t = t < 0 ? 0 : (t >= vocab ? vocab - 1 : t);
     const float4 e = __ldg(reinterpret_cast<const float4*>(emb + t * D) + c);
     const float4 q = __ldg(reinterpret_cast<const float4*>(pe + static_cast<long long>(r % L) * D) + c);

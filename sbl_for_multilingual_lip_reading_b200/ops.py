@@ -448,7 +448,7 @@ def gemm_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, 
 
 
 def linear_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None, T=1, eps=1e-5, want_bf16=True,
-              out_f32=None):
+              out_f32=None, fused=None):
     """LayerNorm(a @ w.T + bias + residual) * gamma + beta (+ pe) (* pad mask) -> (fp32 [M,512], bf16 [M,512] | None).
 
     Strategy by token count: when a 128-row tiling already fills the machine the cluster-fused kernel (gemm_ln) does
@@ -460,7 +460,8 @@ def linear_ln(a, w, gamma, beta, bias=None, residual=None, pe=None, lengths=None
     splits = int(_lib.load().sblk_gemm_splitk_plan(m, n, k))
     if splits < 1:
         raise RuntimeError(f"linear_ln: {_lib.last_error()}")
-    if splits == 1 and (m + 127) // 128 * 4 >= 64:
+    # fused: None = by token count (below); True / False force the one-launch cluster kernel / the split-K pair
+    if fused is True or (fused is None and splits == 1 and (m + 127) // 128 * 4 >= 64):
         return gemm_ln(a, w, gamma, beta, bias=bias, residual=residual, pe=pe, lengths=lengths, T=T, eps=eps,
                        want_bf16=want_bf16, out_f32=out_f32)
     _req(bias, F32, "bias"); _req(residual, F32, "residual"); _req(gamma, F32, "gamma"); _req(beta, F32, "beta")

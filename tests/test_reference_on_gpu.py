@@ -428,3 +428,32 @@ def test_reference_transformer_on_all_dropins_recognize(models, dev):
         b_l2r, b_r2l = full.recognize(x)
     assert b_l2r.shape == a_l2r.shape == (40, 17) and b_l2r.dtype == torch.long
     assert int((a_l2r == b_l2r).all(1).sum()) >= 38 and int((a_r2l == b_r2l).all(1).sum()) >= 36
+
+
+def test_native_decoder_cuda_graph_steps_equal_eager(models, native_decoder, dev):
+    """The captured decode steps (one CUDA graph per prefix length, PDL on) return the bits of the eager launches, for
+    two different batch shapes in a row (plans are cached per shape) and after a weight change."""
+    from oracle import ref_runtime
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    R, ref, ours = models
+    with torch.no_grad(), ref_runtime.dropout_neutralised(R):
+        for n, t, seed in ((5, 29, 1), (12, 40, 2), (5, 29, 3)):
+            x = synth.structured_clips(n, t, seed=600 + seed)[:, 0].to(dev)
+            feat = ref.visual_frontend(x.unsqueeze(4).permute(0, 4, 1, 2, 3))
+            enc, *_ = ref.encoder(feat, [t] * n)
+            native_decoder.use_cuda_graphs = True
+            a = native_decoder._greedy(enc, want_logits=True)
+            native_decoder.use_cuda_graphs = False
+            b = native_decoder._greedy(enc, want_logits=True)
+            native_decoder.use_cuda_graphs = True
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+            assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+        # in-place weight update -> packed weights and plans are rebuilt
+        w = native_decoder.tgt_word_prj_l2r.weight
+        before = native_decoder._greedy(enc, want_logits=True)[2]
+        with torch.no_grad():
+            w.mul_(0.5)
+        after = native_decoder._greedy(enc, want_logits=True)[2]
+        with torch.no_grad():
+            w.mul_(2.0)
+        assert torch.allclose(after, before * 0.5, rtol=2e-2, atol=1e-3) and not torch.equal(after, before)
