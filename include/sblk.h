@@ -38,6 +38,10 @@ int sblk_set_pdl(int enable);
  * even count; 0 = all SMs).  Used to run independent kernel chains (halves of a clip batch) concurrently on disjoint
  * SM sets.  Returns the previous limit. */
 int sblk_set_sm_limit(int max_sms);
+/* Which kernel sblk_conv3d_bn_relu_pool_fwd launches for the CALLING THREAD: 0 (default) = the transposed stem with
+ * the filter resident in tensor memory (csrc/sblk_stem_t.cuh), 1 = the pixel-major stem of round 1
+ * (csrc/sblk_conv3d.cuh, kept for A/B measurements).  Same inputs, same outputs.  Returns the previous value. */
+int sblk_set_stem_variant(int variant);
 /* Number of kernels launched by this library since load (all threads). */
 long long sblk_launch_count(void);
 

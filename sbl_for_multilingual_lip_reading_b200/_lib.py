@@ -40,6 +40,7 @@ SIGNATURES = {
     "sblk_watchdog_code": (ctypes.c_uint, []),
     "sblk_set_pdl": (_i, [_i]),
     "sblk_set_sm_limit": (_i, [_i]),
+    "sblk_set_stem_variant": (_i, [_i]),
     "sblk_launch_count": (_ll, []),
     "sblk_pack_conv3d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]),
     "sblk_pack_conv2d": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -15,6 +15,7 @@
 #include "sblk_igemm.cuh"
 #include "sblk_igemm2.cuh"
 #include "sblk_conv3d.cuh"
+#include "sblk_stem_t.cuh"
 #ifdef SBLK_DEBUG
 #include "sblk_flatconv.cuh"   // v1 single-CTA flat conv: A/B timing baseline only (SBLK_FLATCONV2=0)
 #endif
@@ -35,6 +36,7 @@ std::atomic<long long> g_launches{0};
 // captures with PDL on, or sizes grids for a co-running chain, never changes what another thread's launches do.
 thread_local int g_pdl = 0;        // != 0: launches carry the programmatic-dependent-launch attribute
 thread_local int g_sm_limit = 0;   // > 0: size persistent grids for at most this many SMs (concurrent kernel chains)
+thread_local int g_stem_variant = 0;   // 0: transposed stem with the filter in tensor memory; 1: pixel-major stem
 
 // Tuning / profiling switches read from the environment exist only in -DSBLK_DEBUG builds (tools/, experiments): the
 // release library never calls getenv and cannot be steered into its timing-experiment modes.
@@ -136,6 +138,7 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::stem_t_kernel, sblk::stt::SMEM_BYTES))) return rc;
 #ifdef SBLK_DEBUG
     if ((rc = set_smem(sblk::flatconv3x3_c64_kernel, sblk::fc::SMEM_BYTES))) return rc;
 #endif
@@ -275,6 +278,11 @@ int sblk_set_pdl(int enable) {
 int sblk_set_sm_limit(int max_sms) {
   const int prev = g_sm_limit;
   g_sm_limit = max_sms > 0 ? (max_sms & ~1) : 0;   // even: CTA-pair kernels take whole TPCs
+  return prev;
+}
+int sblk_set_stem_variant(int variant) {
+  const int prev = g_stem_variant;
+  g_stem_variant = variant == 1 ? 1 : 0;
   return prev;
 }
 long long sblk_launch_count(void) { return g_launches.load(); }
@@ -475,6 +483,29 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   if (N <= 0 || T <= 0) return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: bad shape N=%d T=%d", N, T);
   if (!aligned16(xp) || !aligned16(wp) || !aligned16(out))
     return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: pointers must be 16-byte aligned");
+  if (g_stem_variant == 0) {
+    const long long steps = static_cast<long long>(N) * ((T + 1) / 2) * sblk::stt::TILES_PER_UNIT;
+    if (steps > 0x7fffffffLL / 2) return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: batch too large (N=%d T=%d)", N, T);
+    sblk::StemTParams q;
+    q.N = N;
+    q.T = T;
+    q.x8 = static_cast<const uint4*>(xp);
+    q.wp = static_cast<const __nv_bfloat16*>(wp);
+    q.bias = bias;
+    q.out = static_cast<__nv_bfloat16*>(out);
+    q.flat_out = flat_out ? 1 : 0;
+    {
+      const char* dm = dbg_env("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+      q.debug_mode = dm ? atoi(dm) : 0;
+      const char* st = dbg_env("SBLK_C3D_STAMPS");      // device pointer (hex) of a [grid][8] uint64 stamp buffer
+      q.dbg = st ? reinterpret_cast<unsigned long long*>(strtoull(st, nullptr, 16)) : nullptr;
+    }
+    // every CTA gets an equal contiguous share of the (frame pair, row pair) steps; at least two tiles per CTA
+    long long g = steps / 2 < 1 ? 1 : steps / 2;
+    if (g > sms) g = sms;
+    return launch(sblk::stem_t_kernel, dim3(static_cast<unsigned>(g)), dim3(sblk::stt::THREADS), sblk::stt::SMEM_BYTES,
+                  static_cast<cudaStream_t>(stream), true, "stem_t_kernel", q);
+  }
   CUtensorMap tmW;
   {
     cuuint64_t dims[2] = {KPAD, COUT};

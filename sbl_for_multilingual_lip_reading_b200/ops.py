@@ -97,6 +97,12 @@ def set_sm_limit(max_sms: int) -> int:
     return int(_lib.load().sblk_set_sm_limit(int(max_sms)))
 
 
+def set_stem_variant(variant: int) -> int:
+    """Stem kernel of this thread's next launches: 0 = transposed, filter in tensor memory (default); 1 = the
+    pixel-major round-1 kernel (A/B measurements).  Returns the previous value."""
+    return int(_lib.load().sblk_set_stem_variant(int(variant)))
+
+
 def launch_count() -> int:
     return int(_lib.load().sblk_launch_count())
 

@@ -212,14 +212,16 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         if self.head_sm_limit is None:
             self.head_sm_limit = (sms - enc_ctas) & ~1
         if self.head_blocks is None:
-            # BASELINE-sized batches: only prep + stem fit next to the ~0.2 ms encoder (measured, tools/exp/
-            # pipeline_probe.py); small latency-bound batches: the whole frontend co-runs with it
-            self.head_blocks = 0 if self.n * self.t > 512 else 8
+            # BASELINE-sized batches: prep + the (tensor-memory-filter) stem + the first residual block fit next to the
+            # ~0.2 ms encoder (measured, tools/exp/head_frac_probe.py: 712.7 us with half a conv in the head, 700.4 with
+            # a whole conv, 675.8 with the whole block, 706.6 with two blocks); small latency-bound batches: the whole
+            # frontend co-runs with it
+            self.head_blocks = 1 if self.n * self.t > 512 else 8
         self.head_blocks = int(self.head_blocks)
         if self.head_frac is None:
-            # measured at the BASELINE batch (tools/exp/pipeline_probe.py): 708.6 us (0) / 704.5 (0.3) / 700.4 (0.4) /
-            # 698.4 (0.5) / 698.4 (0.6) per step; the encoder outlasts prep + stem on 84 SMs by ~35 us
-            self.head_frac = 0.5 if self.head_blocks == 0 else 0.0
+            # share of the frames of the first conv AFTER the head that still runs inside it: 675.8 us (0) / 679.9 (0.1) /
+            # 677.9 (0.2) / 682.0 (0.4) per step at the BASELINE batch with one block in the head
+            self.head_frac = 0.0
         self.head_frac = float(self.head_frac)
         torch.cuda.synchronize(dev)
         self.enc_stream = torch.cuda.Stream(device=dev, priority=-1)

@@ -14,7 +14,7 @@ N, T, L = int(os.environ.get("N", 32)), int(os.environ.get("T", 29)), int(os.env
 enc = Encoder(512, L, 8, 64, 64, 512, 2048)
 enc.load_state_dict(synth.encoder_state_dict(2, L))
 enc = enc.to(dev).eval()
-x16 = torch.randn(N * T, 512, device=dev).to(torch.bfloat16)
+x16 = torch.randn(N * T, 512, device=dev).to(ops.enc16_dtype())
 with torch.no_grad():
     pk = enc._get_packed()
     groups = (N + (128 // T) - 1) // (128 // T)
