@@ -570,6 +570,10 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
   p.bias = bias;
   const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
   p.dbg = nullptr;
+  {
+    const char* dm = dbg_env("SBLK_FLAT_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    p.debug_mode = dm ? atoi(dm) : 0;
+  }
   if (dbg_env("SBLK_FLAT_STAMPS")) {   // profiling aid: per-tile clock stamps of CTA 0, printed after a synchronise
     static unsigned long long* d_dbg = nullptr;
     const int tiles0 = (p.num_tiles + pairs - 1) / pairs;

@@ -82,6 +82,7 @@ struct FlatConv2Params {
   int has_res;
   const float* bias;           // [C] folded BN shift
   unsigned long long* dbg;     // profiling aid (SBLK_FLAT_STAMPS=1): per-tile clock64 stamps of CTA 0, or nullptr
+  int debug_mode;              // SBLK_DEBUG builds, timing experiments (wrong results): 16 = issue the MMAs with N = 32
 };
 
 template <int CB>
@@ -274,6 +275,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       uint32_t acc_phase = 0;
       const uint64_t db0 = make_desc_sw128(smem_base + Cfg::OFF_B);
       const uint32_t db0_lo = static_cast<uint32_t>(db0);
+      const uint32_t idesc = (p.debug_mode & 16) ? make_idesc_bf16(256, 32) : IDESC;
       uint32_t tap_off[9];   // (r*Wp + s) rows of 128 B, in descriptor units of 16 B
 #pragma unroll
       for (int t = 0; t < 9; ++t) tap_off[t] = static_cast<uint32_t>(((t / 3) * Wp + (t % 3)) * 8);
@@ -306,7 +308,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma2_bf16(d_tmem, desc_with_lo(da0, a_lo + static_cast<uint32_t>(2 * k)),
-                           desc_with_lo(db0, b_lo + static_cast<uint32_t>(2 * k)), IDESC,
+                           desc_with_lo(db0, b_lo + static_cast<uint32_t>(2 * k)), idesc,
                            (cb > 0 || t > 0 || k > 0) ? 1u : 0u);
               if (!Cfg::B_RESIDENT) umma2_commit_mc(&b_empty[slot]);
             }
