@@ -230,13 +230,16 @@ typedef struct sblk_encoder_stack_args {
   int N, T, n_layers, n_head, d_k, d_model, d_in, d_inner;
   float scale; /* 1 / temperature */
   float eps;   /* LayerNorm eps (shared by all LayerNorms of the stack) */
-  int cluster_size;   /* 0 = automatic (16 CTAs per clip group when <= 7 groups, else 8), or 8 / 16 */
+  int cluster_size;   /* 0 = automatic (16 CTAs per cluster when <= 7 clusters, else 8), or 8 / 16 */
   void* debug_stamps; /* NULL, or device uint64 [(1 + 4*n_layers)*8 + 2*groups]: per-stage clock64 stamps of CTA 0, then
                        * (start, end) globaltimer ns of every cluster (profiling aid) */
   void* resident_counter; /* NULL, or device uint32[2] (zero-initialised once): every CTA adds 1 to word 0 when it starts
                            * running, i.e. when its cluster owns its SMs (see sblk_gate_wait) */
   int no_multicast;   /* 0 = activation tiles are loaded once per cluster and TMA-multicast (default); 1 = every CTA loads
                        * its own copy (bit-identical; A/B timing and tests) */
+  int groups_per_cluster; /* 0 / 1 = one clip group per cluster; 2 = every cluster runs two clip groups through the stack
+                           * alternately, the loads / MMAs of one hidden behind the epilogues / cluster barriers of the
+                           * other (half the SMs for little more than the time of one group; bit-identical) */
 } sblk_encoder_stack_args;
 long long sblk_encoder_stack_workspace_bytes(int N, int T, int d_inner);
 int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* args, void* stream);

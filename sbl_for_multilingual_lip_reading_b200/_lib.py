@@ -29,7 +29,7 @@ class EncoderStackArgs(ctypes.Structure):
         "ln1_beta", "w_1", "b_1", "w_2", "b_2", "ln2_gamma", "ln2_beta", "lengths", "out", "workspace")] +
         [(n, _i) for n in ("N", "T", "n_layers", "n_head", "d_k", "d_model", "d_in", "d_inner")] +
         [("scale", _f), ("eps", _f), ("cluster_size", _i), ("debug_stamps", _vp), ("resident_counter", _vp),
-         ("no_multicast", _i)])
+         ("no_multicast", _i), ("groups_per_cluster", _i)])
 
 
 # name -> (restype, argtypes); must list EVERY symbol include/sblk.h declares (tests check this).

@@ -1143,7 +1143,9 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   // of the BASELINE batch in one wave).  args.cluster_size / args.no_multicast select the variants explicitly.
   const int G = sblk_qkv_group_clips(T);
   const int groups = (N + G - 1) / G;
-  int cl = a->cluster_size != 0 ? a->cluster_size : (groups <= 7 ? 16 : 8);
+  const int gpc = a->groups_per_cluster == 2 ? 2 : 1;   // clip groups interleaved per cluster
+  const int clusters = (groups + gpc - 1) / gpc;
+  int cl = a->cluster_size != 0 ? a->cluster_size : (clusters <= 7 ? 16 : 8);
   const bool mc = a->no_multicast == 0;
   if (cl != 8 && cl != 16) return fail(-1, "sblk_encoder_stack_fwd: cluster_size must be 0 (automatic), 8 or 16");
   if (d_inner % (64 * cl) != 0 || d_inner / cl > (cl == 16 ? 192 : 256))
@@ -1161,6 +1163,7 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   p.scale = a->scale; p.eps = a->eps;
   p.dbg = static_cast<unsigned long long*>(a->debug_stamps);
   p.resident = static_cast<unsigned int*>(a->resident_counter);
+  p.gpc = gpc;
 
   CUtensorMap tm[9];
   const cuuint32_t a_rows = mc ? static_cast<cuuint32_t>(128 / cl) : 128u;
@@ -1182,11 +1185,11 @@ int sblk_encoder_stack_fwd(const sblk_encoder_stack_args* a, void* stream) {
   if ((rc = enc(&tm[8], a->w_2, static_cast<long long>(L) * 512, d_inner, ns))) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (cl == 16) {
-    return mc ? launch_encoder_stack_nt<16, true>(T, tm, p, groups, s)
-              : launch_encoder_stack_nt<16, false>(T, tm, p, groups, s);
+    return mc ? launch_encoder_stack_nt<16, true>(T, tm, p, clusters, s)
+              : launch_encoder_stack_nt<16, false>(T, tm, p, clusters, s);
   }
-  return mc ? launch_encoder_stack_nt<8, true>(T, tm, p, groups, s)
-            : launch_encoder_stack_nt<8, false>(T, tm, p, groups, s);
+  return mc ? launch_encoder_stack_nt<8, true>(T, tm, p, clusters, s)
+            : launch_encoder_stack_nt<8, false>(T, tm, p, clusters, s);
 }
 
 

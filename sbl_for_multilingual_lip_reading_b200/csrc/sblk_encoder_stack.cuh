@@ -23,6 +23,16 @@
 // With MC the A tiles are loaded ONCE per cluster: CTA r fetches rows [r*128/CL, ...) of every k-block and multicasts
 // them into all CL CTAs' rings (ring slots are then released cluster-wide by a multicast tcgen05.commit).
 //
+// Two clip groups per cluster (EncStackParams::gpc == 2).  The chain of one group is latency-bound: per layer ~10 us of
+// operand delivery + MMAs, ~7 us of epilogues and ~6 us of cluster barriers, each waiting for the previous one.  With
+// gpc == 2 a cluster runs groups A and B through the same stages alternately — virtual stage v = 2 * stage + group —
+// and the producer and MMA warps work ONE virtual stage ahead of the barrier sequence: while the epilogue warps
+// finish (stage, A) and wait in its barriers, the operands of (stage, B) stream in and its MMAs run (second TMEM
+// accumulator), and vice versa.  Every (stage, group) keeps its own cluster barriers in the same global order, the
+// LayerNorm epilogues of A / B live in the two halves of the epilogue warps (each keeps ITS group's residual-stream
+// slice in registers), and all arithmetic is per group exactly as with gpc == 1: results are bit-identical, the
+// cluster just serves two groups in little more than the time of one.
+//
 // Roles (192 threads): warp 0 TMA producer (prefetches the next stage's weight tiles BEFORE the barrier that publishes
 // its activations), warp 1 MMA issuer / TMEM owner, warps 2-5 epilogue (one token row per thread) + attention.
 #pragma once
@@ -59,6 +69,7 @@ struct EncStackParams {
   float eps;                 // LayerNorm eps (all three LayerNorms of the reference use the default 1e-5)
   unsigned long long* dbg;   // optional [stages][8] clock64 stamps of cluster 0 / CTA 0 (profiling aid), or nullptr
   unsigned int* resident;    // optional: every CTA adds 1 when it starts running (sblk_gate_wait: co-scheduling hint)
+  int gpc;                   // clip groups per cluster: 1, or 2 (interleaved, see above)
 };
 
 template <int CL>
@@ -80,7 +91,7 @@ struct EncCfg {
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr int VEC_FLOATS = QKV_N + B_ROWS_MAX + 6 * NS;   // per-layer bias / gamma / beta slices of this CTA
-  static constexpr int TMEM_COLS = 256;
+  static constexpr int TMEM_COLS = 512;                // one 256-column accumulator per interleaved clip group
   static constexpr int MC_ROWS = 128 / CL;             // A rows each CTA fetches and multicasts (8-row swizzle atoms)
   static_assert(2 * (A_BYTES + NS * 128) <= SLOT_BYTES, "two LayerNorm-stage k-blocks must fit one ring slot");
   static_assert(16 * 128 * 8 <= QKV_BYTES, "statistics exchange area aliases the Q tile");
@@ -171,7 +182,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t full_bar[STAGES];
   __shared__ uint64_t empty_bar[STAGES];
-  __shared__ uint64_t tfull_bar;
+  __shared__ uint64_t tfull_bar[2];   // per interleaved group
   __shared__ uint32_t tmem_base_slot;
   __shared__ float vec_layer[2][Cfg::VEC_FLOATS];   // double-buffered per layer: b_heads | b_w1 | b_fc g1 be1 | b_w2 g2 be2
   __shared__ float vec_in[3 * NS];                  // b_in | layer_norm_in gamma | beta
@@ -184,17 +195,17 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   const int warp = uniform_warp_idx();
   const int lane = threadIdx.x & 31;
   const int rank = static_cast<int>(cluster_ctarank());
-  const int group = static_cast<int>(blockIdx.x) / CL;
   const int T = p.T;
-  const int m0 = group * p.G * T;
-  const int nclips = min(p.G, p.N - group * p.G);
-  const int rows_valid = nclips * T;
+  const int total_groups = (p.N + p.G - 1) / p.G;
+  const int g_first = (static_cast<int>(blockIdx.x) / CL) * p.gpc;   // first clip group of this cluster
+  const int ng = min(p.gpc, total_groups - g_first);                  // groups this cluster interleaves (1 or 2)
   const int NW = p.d_inner / CL;
   const int head = rank / Cfg::PARTS;
   const int num_stages = 1 + 4 * p.L;
+  const int NV = num_stages * ng;                                     // virtual stages: v = stage * ng + group slot
   unsigned long long* const dbg = (p.dbg != nullptr && blockIdx.x == 0 && lane == 0) ? p.dbg : nullptr;
-  auto stamp = [&](int s, int which) {
-    if (dbg != nullptr) dbg[s * 8 + which] = static_cast<unsigned long long>(clock64());
+  auto stamp = [&](int v, int which) {   // stamps follow the cluster's first group only
+    if (dbg != nullptr && v % ng == 0) dbg[(v / ng) * 8 + which] = static_cast<unsigned long long>(clock64());
   };
 
   auto stage_desc = [&](int s) -> EncStage {
@@ -235,7 +246,8 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], MC ? CL : 1);
     }
-    mbar_init(&tfull_bar, 1);
+    mbar_init(&tfull_bar[0], 1);
+    mbar_init(&tfull_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_slot, Cfg::TMEM_COLS);
@@ -261,8 +273,25 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   if (p.dbg != nullptr && rank == 0 && threadIdx.x == 0) {   // per-cluster start time (ns) behind the stage stamps
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    p.dbg[num_stages * 8 + group * 2] = now;
+    p.dbg[num_stages * 8 + g_first * 2] = now;
   }
+
+  // Cluster-barrier participation of the producer and MMA warps: every thread of the cluster has to arrive at every
+  // cluster barrier, but these two warps publish nothing, so each ARRIVES at barrier k + 1 right after its wait on
+  // barrier k (the earliest the ISA allows) and WAITS only when it needs the guarantee (need(k): k barriers completed).
+  // The epilogue warps of one clip group then do not wait for this warp's ring-paced load / issue loops of the other
+  // group.  (Servicing the barriers from inside those polling loops as well — a "barrier pump" — was measured: no gain,
+  // the remaining serialisation is the epilogue chain itself and the memory-system contention between the groups.)
+  int bar_total = 0;
+  for (int v = 0; v < NV; ++v) bar_total += stage_desc(v / ng).end_barriers;
+  int bar_done = 0;
+  auto pump_start = [&]() { if (bar_total > 0) cl_arrive_relaxed(); };
+  auto need = [&](int k) {
+    while (bar_done < k) {
+      cl_wait();
+      if (++bar_done < bar_total) cl_arrive_relaxed();
+    }
+  };
 
   if (warp == 0) {
     // ================================================================= TMA producer
@@ -289,7 +318,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       }
       return pre;
     };
-    auto load_a = [&](const EncStage& d, uint8_t* base, uint64_t* bar, int u) {
+    auto load_a = [&](const EncStage& d, uint8_t* base, uint64_t* bar, int u, int m0) {
       for (int i = 0; i < d.kbps; ++i) {
         const int kc = (u * d.kbps + i) * 64;
         if (MC) {
@@ -300,7 +329,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         }
       }
     };
-    auto finish_loads = [&](const EncStage& d, int pre) {
+    auto finish_loads = [&](const EncStage& d, int pre, int m0) {
       const int units = d.num_kb / d.kbps;
       const uint32_t b_bytes = static_cast<uint32_t>(d.n) * 128u;
       for (int u = 0; u < units; ++u) {
@@ -313,43 +342,45 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               tma_load_2d(base + d.kbps * Cfg::A_BYTES + i * b_bytes, d.tmB, &full_bar[slot],
                           (u * d.kbps + i) * 64, d.b_row);
           }
-          load_a(d, base, &full_bar[slot], u);
+          load_a(d, base, &full_bar[slot], u, m0);
         }
         __syncwarp();
         if (++slot == STAGES) { slot = 0; phase ^= 1u; }
       }
     };
 
-    EncStage cur = stage_desc(0);
-    int pre = prefetch_b(cur);
-    stamp(0, 0);
-    finish_loads(cur, pre);
-    stamp(0, 5);
-    for (int s = 1; s <= num_stages; ++s) {
-      const int nb = cur.end_barriers;
-      EncStage nxt;
-      pre = 0;
-      for (int b = 0; b < nb; ++b) {
-        cl_arrive_relaxed();
-        if (b == 0 && s < num_stages) {
-          nxt = stage_desc(s);
-          pre = prefetch_b(nxt);
-        }
-        cl_wait();
-      }
-      if (s == num_stages) break;
-      fence_proxy_async_all();
-      stamp(s, 0);
-      finish_loads(nxt, pre);
-      stamp(s, 5);
-      cur = nxt;
+    // virtual stage v = stage * ng + group slot; the loads of v + ng (same group, next stage) are issued right after
+    // the barriers of v, i.e. (ng == 2) one virtual stage AHEAD of the barrier sequence
+    auto v_m0 = [&](int v) { return (g_first + v % ng) * p.G * T; };
+    for (int v = 0; v < ng; ++v) {
+      const EncStage d0 = stage_desc(0);
+      const int pre0 = prefetch_b(d0);
+      stamp(v, 0);
+      finish_loads(d0, pre0, v_m0(v));
+      stamp(v, 5);
     }
+    pump_start();
+    int cum = 0;   // barriers up to and including virtual stage v
+    for (int v = 0; v < NV; ++v) {
+      cum += stage_desc(v / ng).end_barriers;
+      if (v + ng >= NV) continue;
+      const EncStage nxt = stage_desc((v + ng) / ng);
+      const int pre = prefetch_b(nxt);          // weight tiles do not depend on the barrier
+      need(cum);                                // the activations of (stage, group) are published
+      fence_proxy_async_all();
+      stamp(v + ng, 0);
+      finish_loads(nxt, pre, v_m0(v + ng));
+      stamp(v + ng, 5);
+    }
+    need(bar_total);
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     int slot = 0;
     uint32_t phase = 0;
-    for (int s = 0; s < num_stages; ++s) {
-      const EncStage d = stage_desc(s);
+    auto issue = [&](int v) {
+      const EncStage d = stage_desc(v / ng);
+      const int gi = v % ng;
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(gi * 256);
       const int units = d.num_kb / d.kbps;
       const uint32_t idesc = make_idesc_e16(128, d.n);
       const uint32_t b_bytes = static_cast<uint32_t>(d.n) * 128u;
@@ -366,43 +397,49 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base, desc_with_lo(da, da_lo + 2 * k), desc_with_lo(db, db_lo + 2 * k), idesc,
+            umma_bf16(d_tmem, desc_with_lo(da, da_lo + 2 * k), desc_with_lo(db, db_lo + 2 * k), idesc,
                       (u > 0 || k > 0) ? 1u : 0u);
           if (d.kbps == 2) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base, desc_with_lo(da, da_lo + (Cfg::A_BYTES >> 4) + 2 * k),
+              umma_bf16(d_tmem, desc_with_lo(da, da_lo + (Cfg::A_BYTES >> 4) + 2 * k),
                         desc_with_lo(db, db_lo + b_step + 2 * k), idesc, 1u);
           }
           if (MC) umma_commit_mc(&empty_bar[slot], ALL); else umma_commit(&empty_bar[slot]);
-          if (last) umma_commit(&tfull_bar);
+          if (last) umma_commit(&tfull_bar[gi]);
         }
         __syncwarp();
         if (++slot == STAGES) { slot = 0; phase ^= 1u; }
       }
-      stamp(s, 1);
-      for (int b = 0; b < d.end_barriers; ++b) { cl_arrive_relaxed(); cl_wait(); }
+      stamp(v, 1);
+    };
+    // like the producer: the MMAs of v + ng are issued after the barriers of v (which also guarantee that the epilogue
+    // has drained that group's accumulator)
+    for (int v = 0; v < ng; ++v) issue(v);
+    pump_start();
+    int cum = 0;
+    for (int v = 0; v < NV; ++v) {
+      cum += stage_desc(v / ng).end_barriers;
+      if (v + ng >= NV) continue;
+      need(cum);   // the epilogue has drained this group's accumulator
+      issue(v + ng);
     }
+    need(bar_total);
   } else {
     // ================================================================= epilogue warps
-    // 8 warps: warp pairs (ew, ew + 4) share a TMEM lane quarter = 32 token rows.  The LayerNorm stages run on the
-    // first four (one row per thread, NS columns in registers); the wide stages (QKV tiles, attention, W1) use all 8.
+    // 8 warps: warp pairs (ew, ew + 4) share a TMEM lane quarter = 32 token rows.  The LayerNorm stages run on four of
+    // them (one row per thread, NS columns in registers): the first four, or — two interleaved groups — the first four
+    // for group A and the other four for group B, so that every thread keeps exactly ONE group's residual-stream
+    // slice in registers; the wide stages (QKV tiles, attention, W1) use all 8.
     const int ew = warp - 2;
     const int half = ew >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = row < rows_valid;
     const int t = row % T;
-    const int clip = group * p.G + row / T;
     const int etid = static_cast<int>(threadIdx.x) - 64;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    uint32_t tph = 0;
-    float keep = 1.0f;
-    if (row_ok && p.lengths != nullptr && t >= __ldg(p.lengths + clip)) keep = 0.0f;
+    uint32_t tph0 = 0, tph1 = 0;   // accumulator-full phase per interleaved group
     const uint32_t my_part = smem_u32(&part[rank * (NS / 32) * 128 + row]);   // 32-column partial rank*NS/32 (+ sub)
     const int col0 = rank * NS;
-    const int warp_valid = min(max(rows_valid - quarter * 32, 0), 32);   // valid token rows of this warp's lane quarter
     uint8_t* const stg_ln = sQKV + 16 * 128 * 8 + (ew & 3) * 4096;       // behind the statistics area (LayerNorm stages)
     uint8_t* const stg_w1 = sQKV + ew * 4096;                            // W1 stage: the Q/K/V tiles are idle
     float xres[NS];   // this thread's slice of the fp32 residual stream: lives in registers across all stages
@@ -434,21 +471,36 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
     if (p.L > 0) load_layer_vectors(0, vec_layer[0]);
     asm volatile("bar.sync 1, 256;" ::: "memory");
 
-    for (int s = 0; s < num_stages; ++s) {
+    for (int vs = 0; vs < NV; ++vs) {
+      const int s = vs / ng;
+      const int gi = vs - s * ng;
       const EncStage d = stage_desc(s);
       const float* lv = vec_layer[d.layer & 1];
+      // this virtual stage's clip group
+      const int group = g_first + gi;
+      const int m0 = group * p.G * T;
+      const int nclips = min(p.G, p.N - group * p.G);
+      const int rows_valid = nclips * T;
+      const bool row_ok = row < rows_valid;
+      const int clip = group * p.G + row / T;
+      const int warp_valid = min(max(rows_valid - quarter * 32, 0), 32);   // valid token rows of this warp's lane quarter
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(gi * 256);
+      uint64_t* const tfull = &tfull_bar[gi];
+      const uint32_t tph = gi == 0 ? tph0 : tph1;
       if (d.kind == 0 || d.kind == 2 || d.kind == 4) {
         // ------------------------------------------------ + bias (+ residual) -> LayerNorm (+ PE | * pad mask)
-        if (half == 0) {
+        if (half == (ng == 2 ? gi : 0)) {
+          float keep = 1.0f;
+          if (row_ok && p.lengths != nullptr && t >= __ldg(p.lengths + clip)) keep = 0.0f;
           const float* bias = d.kind == 0 ? vec_in : lv + Cfg::QKV_N + NW + (d.kind == 2 ? 0 : 3 * NS);
           const float* gamma = bias + NS;
           const float* beta = bias + 2 * NS;
           float v[NS];
 #pragma unroll
           for (int j = 0; j < NS; ++j) v[j] = d.kind != 0 ? xres[j] : 0.0f;
-          mbar_wait(&tfull_bar, tph, 0x0704);
+          mbar_wait(tfull, tph, 0x0704);
           tc_fence_after_sync();
-          if (ew == 0) stamp(s, 2);
+          if (ew == 0) stamp(vs, 2);
 #pragma unroll
           for (int c = 0; c < NS / 32; ++c) {
             uint32_t u[32];
@@ -476,7 +528,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             for (uint32_t r = 0; r < static_cast<uint32_t>(CL); ++r)
               st_cluster_v2f32(mapa_u32(my_part + static_cast<uint32_t>(sub * 128 * 8), r), mean_c, m2_c);
           }
-          if (ew == 0) stamp(s, 4);
+          if (ew == 0) stamp(vs, 4);
           cl_arrive();
           float pev[NS];   // positional encoding row (IN stage only): in flight while the barrier completes
           if (d.kind == 0) {
@@ -491,7 +543,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
             for (int j = 0; j < NS; ++j) pev[j] = 0.0f;
           }
           cl_wait();
-          if (ew == 0) stamp(s, 6);
+          if (ew == 0) stamp(vs, 6);
           float mean = 0.0f;
 #pragma unroll
           for (int r = 0; r < 16; ++r) mean += part[r * 128 + row].x;
@@ -546,7 +598,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
               warp_store_rows128(stg_ln, o, gb + h2 * 128, D * 4, warp_valid, lane);
             }
           }
-          if (ew == 0) stamp(s, 7);
+          if (ew == 0) stamp(vs, 7);
           fence_proxy_async_all();
           cl_arrive();
           cl_wait();
@@ -557,10 +609,10 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
       } else if (d.kind == 1) {
         // ------------------------------------------------ + bias -> bf16 Q / K / V tiles -> attention of this head
         // (next layer's per-column vectors are staged now, while the projection GEMM is still running)
-        if (d.layer + 1 < p.L) load_layer_vectors(d.layer + 1, vec_layer[(d.layer + 1) & 1]);
-        mbar_wait(&tfull_bar, tph, 0x0705);
+        if (gi == 0 && d.layer + 1 < p.L) load_layer_vectors(d.layer + 1, vec_layer[(d.layer + 1) & 1]);
+        mbar_wait(tfull, tph, 0x0705);
         tc_fence_after_sync();
-        if (ew == 0) stamp(s, 2);
+        if (ew == 0) stamp(vs, 2);
 #pragma unroll 1
         for (int c3 = 0; c3 < 3; ++c3) {
           const int cc = half * 3 + c3;        // 32-column chunk 0..5: q q k k v v
@@ -598,7 +650,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         }
         // the Q tile doubles as the statistics exchange area of the next stage: every warp is done reading it
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (ew == 0) stamp(s, 4);
+        if (ew == 0) stamp(vs, 4);
         fence_proxy_async_all();
         cl_arrive();
         cl_wait();
@@ -607,9 +659,9 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
         const float* bias = lv + Cfg::QKV_N;
         uint8_t* hbase = reinterpret_cast<uint8_t*>(p.h16 + static_cast<size_t>(m0 + quarter * 32) * p.d_inner +
                                                     rank * NW);
-        mbar_wait(&tfull_bar, tph, 0x0706);
+        mbar_wait(tfull, tph, 0x0706);
         tc_fence_after_sync();
-        if (ew == 0) stamp(s, 2);
+        if (ew == 0) stamp(vs, 2);
 #pragma unroll 1
         for (int blk = half; blk < NW / 64; blk += 2) {   // 64-column blocks, alternating between the two warps
           uint4 o[8];
@@ -634,13 +686,13 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
           warp_store_rows128(stg_w1, o, hbase + blk * 128, static_cast<size_t>(p.d_inner) * 2, warp_valid, lane);
         }
         tc_fence_before_sync();
-        if (ew == 0) stamp(s, 4);
+        if (ew == 0) stamp(vs, 4);
         fence_proxy_async_all();
         cl_arrive();
         cl_wait();
       }
-      tph ^= 1u;
-      if (ew == 0) stamp(s, 3);
+      if (gi == 0) tph0 ^= 1u; else tph1 ^= 1u;
+      if (ew == 0) stamp(vs, 3);
     }
   }
 
@@ -649,7 +701,7 @@ encoder_stack_kernel(const __grid_constant__ CUtensorMap tmXin, const __grid_con
   if (p.dbg != nullptr && rank == 0 && threadIdx.x == 0) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-    p.dbg[num_stages * 8 + group * 2 + 1] = now;
+    p.dbg[num_stages * 8 + g_first * 2 + 1] = now;
   }
   if (warp == 1) {
     __syncwarp();

@@ -121,6 +121,9 @@ class Encoder(nn.Module):
         self.chunk_groups = 8
         self.split_clusters = True   # 8-11 clip groups: 7 as 16-CTA clusters + the rest as 8-CTA clusters, concurrently
         self.stack_cluster_size = 0  # 0 = automatic; 8 / 16 force the cluster size of the one-launch stack (disables the split)
+        # clip groups per cluster of the one-launch stack when stack_cluster_size is forced: 2 = two groups interleaved
+        # (half the SMs for ~1.5x the time: the pipelined plan's co-running encoder); bit-identical to 1
+        self.stack_groups_per_cluster = 1
         self._resident_counter = None   # int32 [2] CUDA tensor while runner.PipelinedVisualEncoderPlan captures (ops.gate_wait)
         self._x16_override = None       # bf16 [N*T, d_input] copy of the input the plan has already made (skips the cast launch)
 
@@ -144,6 +147,7 @@ class Encoder(nn.Module):
         self.__dict__.setdefault("chunk_groups", 8)
         self.__dict__.setdefault("split_clusters", True)
         self.__dict__.setdefault("stack_cluster_size", 0)
+        self.__dict__.setdefault("stack_groups_per_cluster", 1)
         self.__dict__.setdefault("_resident_counter", None)
         self.__dict__.setdefault("_x16_override", None)
 
@@ -379,7 +383,8 @@ class Encoder(nn.Module):
                     main.wait_event(ev2)
                 else:
                     ops.encoder_stack(x16, stk, n, t, lengths=lengths, scale=scale, eps=self.layer_norm_in.eps, out=out,
-                                      cluster_size=self.stack_cluster_size, resident_counter=self._resident_counter)
+                                      cluster_size=self.stack_cluster_size, resident_counter=self._resident_counter,
+                                      groups_per_cluster=self.stack_groups_per_cluster if self.stack_cluster_size else 1)
                 return (out.view(n, t, self.d_model),)
             groups = 1 if return_attns else max(1, min(self.parallel_chains, n // 4))
             if groups == 1:

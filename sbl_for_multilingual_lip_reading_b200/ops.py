@@ -536,7 +536,7 @@ def encoder_stack_supported(n_head, d_k, d_v, d_model, d_in, d_inner, t, n_layer
 
 
 def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None, workspace=None, debug_stamps=None,
-                  cluster_size=0, resident_counter=None, multicast=True):
+                  cluster_size=0, resident_counter=None, multicast=True, groups_per_cluster=1):
     """The whole encoder stack in one launch.  x16 bf16 [n*t, d_in]; `stk` = dict of STACKED packed tensors
     (w_in, b_in, g_in, be_in, pe, w_heads, b_heads, w_fc, b_fc, g1, be1, w_1, b_1, w_2, b_2, g2, be2, n_layers, d_inner)
     -> fp32 [n*t, 512]."""
@@ -577,6 +577,7 @@ def encoder_stack(x16, stk, n, t, lengths=None, scale=0.125, eps=1e-5, out=None,
     a.debug_stamps = _p(debug_stamps)   # optional int64 [1 + 4*n_layers, 8] device tensor (profiling aid)
     a.resident_counter = _p(resident_counter)   # optional int32 [2] device tensor (co-scheduling gate, see gate_wait)
     a.no_multicast = 0 if multicast else 1
+    a.groups_per_cluster = int(groups_per_cluster)   # 2: two clip groups interleaved per cluster (bit-identical)
     flops = 2 * m * 512 * d_in + nl * (2 * m * 512 * (4 * 512 + 2 * d_inner) + 4 * n * 8 * t * t * 64)
     wbytes = 2 * (512 * d_in + nl * (4 * 512 * 512 + 2 * 512 * d_inner))
     _call("sblk_encoder_stack_fwd", f"encoder stack L={nl} T={t} N={n}", flops, wbytes + m * (2 * d_in + 4 * 512),

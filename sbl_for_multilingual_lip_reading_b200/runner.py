@@ -183,13 +183,15 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
 
     def __init__(self, frontend, encoder, n, t, device=None, pdl=True, lengths=None, u8_input=None,
                  head_sm_limit=None, head_blocks=None, gate=True, gate_timeout_us=300, enc_cluster=None,
-                 head_frac=None):
+                 head_frac=None, enc_gpc=None):
         # head_frac: fraction of the frames of the first conv after the head that still runs inside the head (limited
         # width) — fills the time by which the encoder outlasts prep + stem; None = automatic, 0 = off
         self.head_frac = head_frac
         # head_blocks: residual blocks (after prep + stem) that run next to the encoder on `head_sm_limit` SMs; None =
         # automatic (see _capture).  enc_cluster: CTAs per encoder cluster (8 or 16), None = 8.
         self.enc_cluster = enc_cluster
+        # enc_gpc: clip groups per encoder cluster (1, or 2 = interleaved: half the SMs for ~1.5x the time); None = 1
+        self.enc_gpc = enc_gpc
         self.head_sm_limit, self.head_blocks = head_sm_limit, head_blocks
         self.use_gate, self.gate_timeout_us = bool(gate), int(gate_timeout_us)
         super().__init__(frontend, encoder, n, t, device=device, slots=2, pdl=pdl, lengths=lengths, u8_input=u8_input)
@@ -205,7 +207,15 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
             # step with clusters of 8 against 401 us with 16, 511 us unpipelined)
             self.enc_cluster = 8
         cl = int(self.enc_cluster)
-        if cl not in (8, 16) or not enc._use_fused_stack(self.n, self.t, False) or cl * groups > sms - 16:
+        if self.enc_gpc is None:
+            # BASELINE-sized batches: two clip groups interleaved per encoder cluster — 4 clusters of 8 CTAs hold 32 SMs
+            # for ~310 us instead of 64 SMs for ~215 us, and the frontend of the next batch gets 116 SMs (measured,
+            # tools/exp/head_frac_probe.py: 688.1 -> 657.4 us per step); small batches (configs[2] shard, 3 groups): one
+            # group per cluster is faster (360.4 vs 368.6 us)
+            self.enc_gpc = 2 if (self.n * self.t > 512 and groups >= 6) else 1
+        gpc = int(self.enc_gpc)
+        groups = -(-groups // gpc)   # clusters
+        if cl not in (8, 16) or gpc not in (1, 2) or not enc._use_fused_stack(self.n, self.t, False) or cl * groups > sms - 16:
             raise RuntimeError("PipelinedVisualEncoderPlan needs the one-launch encoder stack in one wave of clusters "
                                f"({groups} clip groups x {cl} CTAs on {sms} SMs); use VisualEncoderPlan for this shape")
         enc_ctas = cl * groups
@@ -213,10 +223,11 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
             self.head_sm_limit = (sms - enc_ctas) & ~1
         if self.head_blocks is None:
             # BASELINE-sized batches: prep + the (tensor-memory-filter) stem + the first residual block fit next to the
-            # ~0.2 ms encoder (measured, tools/exp/head_frac_probe.py: 712.7 us with half a conv in the head, 700.4 with
-            # a whole conv, 675.8 with the whole block, 706.6 with two blocks); small latency-bound batches: the whole
-            # frontend co-runs with it
-            self.head_blocks = 1 if self.n * self.t > 512 else 8
+            # ~0.2 ms one-group-per-cluster encoder (measured, tools/exp/head_frac_probe.py: 712.7 us with half a conv in
+            # the head, 700.4 with a whole conv, 675.8 with the whole block, 706.6 with two blocks); next to the ~0.3 ms
+            # two-groups-per-cluster encoder: layers 1 and 2 (741 / 698 / 657 / 678 us with 2 / 3 / 4 / 5 blocks); small
+            # latency-bound batches: the whole frontend co-runs with it
+            self.head_blocks = (4 if gpc == 2 else 1) if self.n * self.t > 512 else 8
         self.head_blocks = int(self.head_blocks)
         if self.head_frac is None:
             # share of the frames of the first conv AFTER the head that still runs inside it: 675.8 us (0) / 679.9 (0.1) /
@@ -234,13 +245,15 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=ops.enc16_dtype(), device=dev) for _ in range(2)]
         self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
         self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
-        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail)
+        saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
+                 enc.stack_groups_per_cluster)
         try:
             with torch.no_grad():
                 stk = enc._get_packed().stacked
                 if getattr(fe, "l2_prefetch", False):
                     fe.l2_prefetch_extra = [stk[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")]
                 enc.stack_cluster_size = cl
+                enc.stack_groups_per_cluster = gpc
                 with torch.cuda.stream(self.compute):   # warm-up: packs weights, sizes kernels, stages the lengths
                     for _ in range(2):
                         self._forward_eager(self.x[0])
@@ -278,7 +291,8 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                     self.launches_per_forward = ops.launch_count() - before
                     self.graphs[s] = g
         finally:
-            enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail = saved
+            (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
+             enc.stack_groups_per_cluster) = saved
         torch.cuda.synchronize(dev)
         for ev in self.ev_out + self.ev_done:
             ev.record(torch.cuda.current_stream(dev))
@@ -317,14 +331,15 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         to `out_host` when given."""
         s = (self._i - 1) % 2
         enc = self.encoder
-        saved = enc.stack_cluster_size
+        saved = (enc.stack_cluster_size, enc.stack_groups_per_cluster)
         with torch.no_grad(), torch.cuda.stream(self.compute):
             self.compute.wait_event(self.ev_out[s ^ 1])
             try:
                 enc.stack_cluster_size, enc._x16_override = int(self.enc_cluster), self.feat16[s]
+                enc.stack_groups_per_cluster = int(self.enc_gpc)
                 out, = enc(self.feat, self.lengths)
             finally:
-                enc.stack_cluster_size, enc._x16_override = saved, None
+                (enc.stack_cluster_size, enc.stack_groups_per_cluster), enc._x16_override = saved, None
             if out_host is not None:
                 out_host.copy_(out, non_blocking=True)
         return out

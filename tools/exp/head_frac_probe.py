@@ -49,7 +49,8 @@ for var in [int(v) for v in os.environ.get('VARIANTS', '0,1').split(',')]:
     for hf in [float(v) for v in os.environ.get("HEAD_FRACS", "0.5,0.7,0.85,1.0").split(",")]:
         for lim in [int(v) for v in os.environ.get("HEAD_LIMITS", "0").split(",")]:
             p = PipelinedVisualEncoderPlan(fe, enc, N, T, device=dev, head_frac=hf, head_sm_limit=lim or None,
-                                           head_blocks=int(os.environ.get("HEAD_BLOCKS", "0")))
+                                           head_blocks=int(os.environ.get("HEAD_BLOCKS", "0")),
+                                           enc_gpc=int(os.environ.get("ENC_GPC", "1")))
             med, best = time_plan(p)
             print(f"stem variant {var}: pipelined head_frac={hf} head_sm_limit={p.head_sm_limit}: median {med:.1f} us  best {best:.1f} us  "
                   f"({N / med * 1e6:.0f} clips/s)")

@@ -20,7 +20,8 @@ with torch.no_grad():
     groups = (N + (128 // T) - 1) // (128 // T)
     dbg = torch.zeros(((1 + 4 * L) * 8 + 2 * groups,), dtype=torch.int64, device=dev)
     for it in range(3):
-        ops.encoder_stack(x16, pk.stacked, N, T, debug_stamps=dbg)
+        ops.encoder_stack(x16, pk.stacked, N, T, debug_stamps=dbg, cluster_size=int(os.environ.get('CL', 0)),
+                          groups_per_cluster=int(os.environ.get('GPC', 1)))
     torch.cuda.synchronize()
 dall = dbg.cpu()
 d = dall[:(1 + 4 * L) * 8].view(-1, 8)
