@@ -268,6 +268,61 @@ def test_encoder_stack_cluster_sizes_agree(encoder6, dev):
     assert all(torch.equal(outs[0], o) for o in outs[1:])
 
 
+@pytest.mark.parametrize("n,t,ragged", [(32, 29, False), (7, 29, True), (9, 40, True), (1, 5, False), (7, 100, False)])
+def test_encoder_stack_two_groups_per_cluster_is_bit_identical(encoder6, dev, n, t, ragged):
+    """groups_per_cluster=2: a cluster runs two clip groups through the stack alternately (second TMEM accumulator,
+    loads / MMAs of one group behind the epilogues / barriers of the other).  All arithmetic is per group, so the
+    output equals the one-group-per-cluster launch bit for bit — odd group counts (a cluster with a single group),
+    partial groups, ragged lengths, both cluster sizes."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(5000 + 17 * n + t)
+    x16 = ops.cast_enc16(torch.randn(n * t, 512, generator=g).to(dev))
+    lens = torch.randint(1, t + 1, (n,), generator=g).to(torch.int32).to(dev) if ragged else None
+    with torch.no_grad():
+        stk = encoder6._get_packed().stacked
+        ref = ops.encoder_stack(x16, stk, n, t, lengths=lens, cluster_size=8, groups_per_cluster=1).clone()
+        groups = -(-n // max(1, 128 // t))
+        for cl in (8, 16):
+            if cl == 16 and -(-groups // 2) > 7:
+                continue
+            out = ops.encoder_stack(x16, stk, n, t, lengths=lens, cluster_size=cl, groups_per_cluster=2)
+            assert torch.equal(out, ref), f"cluster size {cl}"
+
+
+@pytest.mark.parametrize("n,t", [(1, 1), (1, 2), (2, 5), (3, 7), (2, 29), (1, 40)])
+def test_stem_variants_agree_bit_for_bit(frontend, dev, n, t):
+    """The transposed stem (filter in tensor memory, two output frames per pixel operand, max-pool in registers:
+    csrc/sblk_stem_t.cuh, the default) against the pixel-major stem of round 1 (csrc/sblk_conv3d.cuh): both layouts,
+    odd and even frame counts (a half-empty last frame pair), clip edges, zero halos of the flat layout — and a
+    limited grid (sblk_set_sm_limit), which only moves the work partition."""
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    pk = frontend._get_packed()
+    x = synth.synthetic_clips(n, t, seed=900 + 10 * n + t).to(dev)
+    xp = ops.prep_clip(x)
+    outs = {}
+    try:
+        for var in (0, 1):
+            ops.set_stem_variant(var)
+            outs[var] = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b).clone()
+            dirty = torch.full((ops.flat_rows(n * t, 22, 22), 64), 3.0, dtype=torch.bfloat16, device=dev)
+            fl = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, out=dirty, flat=True)
+            assert torch.equal(fl.dense(), outs[var])
+            grid = fl.data.view(-1, 24, 64)
+            frames = grid[1:].view(n * t, 23, 24, 64)
+            assert float(grid[0].abs().sum() + frames[:, 22].abs().sum() + frames[:, :, 0].abs().sum()
+                         + frames[:, :, 23].abs().sum()) == 0.0
+        ops.set_stem_variant(0)
+        old = ops.set_sm_limit(6)
+        try:
+            few = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b)
+        finally:
+            ops.set_sm_limit(old)
+    finally:
+        ops.set_stem_variant(0)
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(few, outs[0])
+
+
 def test_encoder_stack_rejects_unsupported_shapes(dev):
     from sbl_for_multilingual_lip_reading_b200 import ops, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
