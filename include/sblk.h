@@ -95,6 +95,17 @@ int sblk_prep_clip_u8(const void* x_u8, const void* lut_bf16, const int* crop_yx
  * replaces: Lipreading.frontend3D and _frontend_forward's relayout, transformer/video_frontend.py:99-104,111-115 */
 int sblk_conv3d_bn_relu_pool_fwd(const void* x_prepped_bf16, const void* w_packed_bf16, const float* bias,
                                  void* out_bf16, int N, int T, int flat_out, void* stream);
+/* The same stem WITHOUT the prepped copy of the clip: producer warps of the (transposed, tensor-memory-filter) stem
+ * kernel build the row-Toeplitz entries in shared memory straight from the input — exactly one of
+ *   x_f32  fp32 clips [N,1,T,88,88] (reference layout; T_out == T_in), or
+ *   x_u8   raw uint8 gray frames [N,T_in,H0,W0] + lut_bf16 / crop_yx / (crop_y0, crop_x0) as in sblk_prep_clip_u8,
+ *          clips zero-padded (in normalised space) to T_out frames.
+ * Bit-identical to sblk_prep_clip[_u8] + sblk_conv3d_bn_relu_pool_fwd; saves the 70 MB round trip through HBM and a launch.
+ * replaces: the loader transforms (u8) + Lipreading.frontend3D + relayout, SBL/data_gen.py:122-125,276-296,
+ * transformer/video_frontend.py:99-104,111-115 */
+int sblk_stem_fused_fwd(const float* x_f32, const void* x_u8, const void* lut_bf16, const int* crop_yx, int crop_y0,
+                        int crop_x0, const void* w_packed_bf16, const float* bias, void* out_bf16, int N, int T_in,
+                        int T_out, int H0, int W0, int flat_out, void* stream);
 /* Rows of the zero-haloed flat activation layout for F frames of H x W pixels:
  * pixel (f,y,x) -> row (f*(H+1) + 1 + y)*(W+2) + 1 + x of a [rows, C] bf16 matrix; all other rows are zero. */
 long long sblk_flat_rows(int F, int H, int W);

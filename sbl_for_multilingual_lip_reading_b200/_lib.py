@@ -53,6 +53,7 @@ SIGNATURES = {
     "sblk_prep_clip": (_i, [_vp, _vp, _i, _i, _vp]),
     "sblk_prep_clip_u8": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "sblk_conv3d_bn_relu_pool_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sblk_stem_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_flat_rows": (_ll, [_i, _i, _i]),
     "sblk_flatconv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sblk_conv2d_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -138,7 +138,9 @@ int ensure_init(int* num_sms_out) {
     if ((rc = set_smem(sblk::igemm_kernel<128, false>, sblk::IgemmCfg<128>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::igemm_kernel<256, false>, sblk::IgemmCfg<256>::SMEM_BYTES))) return rc;
     if ((rc = set_smem(sblk::conv3d_bn_relu_pool_kernel, sblk::c3d::SMEM_BYTES))) return rc;
-    if ((rc = set_smem(sblk::stem_t_kernel, sblk::stt::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::stem_t_kernel<0>, sblk::stt::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::stem_t_kernel<1>, sblk::stt::SMEM_BYTES))) return rc;
+    if ((rc = set_smem(sblk::stem_t_kernel<2>, sblk::stt::SMEM_BYTES))) return rc;
 #ifdef SBLK_DEBUG
     if ((rc = set_smem(sblk::flatconv3x3_c64_kernel, sblk::fc::SMEM_BYTES))) return rc;
 #endif
@@ -474,6 +476,67 @@ int sblk_prep_clip_u8(const void* x_u8, const void* lut_bf16, const int* crop_yx
                 T_out, H0, W0);
 }
 
+// launches the transposed stem (sblk_stem_t.cuh): q carries the input source (x8, or the FUSED sources)
+static int launch_stem_t(sblk::StemTParams& q, const void* wp, const float* bias, void* out, int N, int T, int flat_out,
+                         int sms, void* stream) {
+  const long long steps = static_cast<long long>(N) * ((T + 1) / 2) * sblk::stt::TILES_PER_UNIT;
+  if (steps > 0x7fffffffLL / 2) return fail(-1, "sblk stem: batch too large (N=%d T=%d)", N, T);
+  q.N = N;
+  q.T = T;
+  q.wp = static_cast<const __nv_bfloat16*>(wp);
+  q.bias = bias;
+  q.out = static_cast<__nv_bfloat16*>(out);
+  q.flat_out = flat_out ? 1 : 0;
+  {
+    const char* dm = dbg_env("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
+    q.debug_mode = dm ? atoi(dm) : 0;
+    const char* st = dbg_env("SBLK_C3D_STAMPS");      // device pointer (hex) of a [grid][8] uint64 stamp buffer
+    q.dbg = st ? reinterpret_cast<unsigned long long*>(strtoull(st, nullptr, 16)) : nullptr;
+  }
+  // every CTA gets an equal-cost contiguous share of the (frame pair, row pair) steps; at least two tiles per CTA
+  long long g = steps / 2 < 1 ? 1 : steps / 2;
+  if (g > sms) g = sms;
+  if (q.x_f32 != nullptr)
+    return launch(sblk::stem_t_kernel<1>, dim3(static_cast<unsigned>(g)), dim3(sblk::stt::THREADS_FUSED),
+                  sblk::stt::SMEM_BYTES, static_cast<cudaStream_t>(stream), true, "stem_t_kernel<fp32 clip>", q);
+  if (q.x_u8 != nullptr)
+    return launch(sblk::stem_t_kernel<2>, dim3(static_cast<unsigned>(g)), dim3(sblk::stt::THREADS_FUSED),
+                  sblk::stt::SMEM_BYTES, static_cast<cudaStream_t>(stream), true, "stem_t_kernel<uint8 frames>", q);
+  return launch(sblk::stem_t_kernel<0>, dim3(static_cast<unsigned>(g)), dim3(sblk::stt::THREADS), sblk::stt::SMEM_BYTES,
+                static_cast<cudaStream_t>(stream), true, "stem_t_kernel", q);
+}
+
+int sblk_stem_fused_fwd(const float* x_f32, const void* x_u8, const void* lut_bf16, const int* crop_yx, int crop_y0,
+                        int crop_x0, const void* wp, const float* bias, void* out, int N, int T_in, int T_out, int H0,
+                        int W0, int flat_out, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if ((x_f32 == nullptr) == (x_u8 == nullptr))
+    return fail(-1, "sblk_stem_fused_fwd: exactly one of x_f32 / x_u8 must be given");
+  if (!wp || !bias || !out) return fail(-1, "sblk_stem_fused_fwd: null pointer");
+  if (N <= 0 || T_in <= 0 || T_out < T_in)
+    return fail(-1, "sblk_stem_fused_fwd: bad shape N=%d T_in=%d T_out=%d", N, T_in, T_out);
+  if (!aligned16(wp) || !aligned16(out) || (x_f32 && !aligned16(x_f32)))
+    return fail(-1, "sblk_stem_fused_fwd: pointers must be 16-byte aligned");
+  sblk::StemTParams q;
+  memset(&q, 0, sizeof(q));
+  if (x_f32 != nullptr) {
+    if (T_out != T_in) return fail(-1, "sblk_stem_fused_fwd: fp32 clips carry their own frame count (T_out == T_in)");
+    q.x_f32 = x_f32;
+  } else {
+    if (!lut_bf16) return fail(-1, "sblk_stem_fused_fwd: null normalisation table");
+    if (H0 < 88 || W0 < 88) return fail(-1, "sblk_stem_fused_fwd: frames must be at least 88x88 (got %dx%d)", H0, W0);
+    if (!crop_yx && (crop_y0 < 0 || crop_x0 < 0 || crop_y0 + 88 > H0 || crop_x0 + 88 > W0))
+      return fail(-1, "sblk_stem_fused_fwd: crop offset (%d, %d) leaves the %dx%d frame", crop_y0, crop_x0, H0, W0);
+    q.x_u8 = static_cast<const uint8_t*>(x_u8);
+    q.lut_bf16 = static_cast<const uint16_t*>(lut_bf16);
+    q.crop_yx = crop_yx;
+    q.crop_y0 = crop_y0; q.crop_x0 = crop_x0; q.H0 = H0; q.W0 = W0;
+  }
+  q.T_in = T_in;
+  return launch_stem_t(q, wp, bias, out, N, T_out, flat_out, sms, stream);
+}
+
 int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bias, void* out, int N, int T,
                                  int flat_out, void* stream) {
   using namespace sblk::c3d;
@@ -484,27 +547,10 @@ int sblk_conv3d_bn_relu_pool_fwd(const void* xp, const void* wp, const float* bi
   if (!aligned16(xp) || !aligned16(wp) || !aligned16(out))
     return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: pointers must be 16-byte aligned");
   if (g_stem_variant == 0) {
-    const long long steps = static_cast<long long>(N) * ((T + 1) / 2) * sblk::stt::TILES_PER_UNIT;
-    if (steps > 0x7fffffffLL / 2) return fail(-1, "sblk_conv3d_bn_relu_pool_fwd: batch too large (N=%d T=%d)", N, T);
     sblk::StemTParams q;
-    q.N = N;
-    q.T = T;
+    memset(&q, 0, sizeof(q));
     q.x8 = static_cast<const uint4*>(xp);
-    q.wp = static_cast<const __nv_bfloat16*>(wp);
-    q.bias = bias;
-    q.out = static_cast<__nv_bfloat16*>(out);
-    q.flat_out = flat_out ? 1 : 0;
-    {
-      const char* dm = dbg_env("SBLK_C3D_DEBUG_MODE");  // timing experiments only (wrong results when != 0)
-      q.debug_mode = dm ? atoi(dm) : 0;
-      const char* st = dbg_env("SBLK_C3D_STAMPS");      // device pointer (hex) of a [grid][8] uint64 stamp buffer
-      q.dbg = st ? reinterpret_cast<unsigned long long*>(strtoull(st, nullptr, 16)) : nullptr;
-    }
-    // every CTA gets an equal contiguous share of the (frame pair, row pair) steps; at least two tiles per CTA
-    long long g = steps / 2 < 1 ? 1 : steps / 2;
-    if (g > sms) g = sms;
-    return launch(sblk::stem_t_kernel, dim3(static_cast<unsigned>(g)), dim3(sblk::stt::THREADS), sblk::stt::SMEM_BYTES,
-                  static_cast<cudaStream_t>(stream), true, "stem_t_kernel", q);
+    return launch_stem_t(q, wp, bias, out, N, T, flat_out, sms, stream);
   }
   CUtensorMap tmW;
   {

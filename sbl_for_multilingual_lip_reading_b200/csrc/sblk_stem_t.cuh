@@ -51,6 +51,12 @@ constexpr int TMEM_COLS = 512;                   // 288 accumulator + 192 filter
 constexpr int EPI_WARPS = 8;
 constexpr int MMA_WARPS = 2;                     // two issuing threads take alternate tile steps (see the MMA section)
 constexpr int THREADS = 64 + EPI_WARPS * 32 + 32;   // loader, MMA issuer 0, 8 epilogue warps (two per TMEM lane quarter), MMA issuer 1
+// FUSED form: the row-Toeplitz entries are not read from a prepped copy of the clip (sblk_aux.cuh::prep_clip) but built
+// in shared memory by producer warps straight from the fp32 clip / the raw uint8 frames — no 70 MB round trip through
+// HBM, one launch less
+constexpr int PROD_WARPS = 9;                    // warp 0 (the loader of the unfused form) + 8 more
+constexpr int THREADS_FUSED = THREADS + (PROD_WARPS - 1) * 32;
+constexpr int PROD_BATCH = 3;                    // work items (4 entries each) a producer thread keeps in flight
 static_assert(A_COL0 + NP * 4 * A_CHUNK_COLS <= TMEM_COLS, "TMEM budget");
 }  // namespace stt
 
@@ -73,13 +79,21 @@ __device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t
 
 struct StemTParams {
   int N, T;                   // clips, frames per clip
-  const uint4* x8;            // row-Toeplitz clip [N][T+4][2][47*44+4] entries of 8 bf16 (prep_clip)
+  const uint4* x8;            // row-Toeplitz clip [N][T+4][2][47*44+4] entries of 8 bf16 (prep_clip); unused when FUSED
+  // FUSED sources (exactly one is non-null): the reference-layout fp32 clip [N,1,T,88,88], or raw uint8 gray frames
+  // [N,T_in,H0,W0] with the 256-entry bf16 normalisation table and the crop offsets of sblk_prep_clip_u8 (frames
+  // T_in .. T-1 are zero padding in normalised space)
+  const float* x_f32;
+  const uint8_t* x_u8;
+  const uint16_t* lut_bf16;
+  const int* crop_yx;
+  int crop_y0, crop_x0, T_in, H0, W0;
   const __nv_bfloat16* wp;    // packed filter [64][320] bf16, BN folded (sblk_pack_conv3d)
   const float* bias;          // [64] folded BN shift
   __nv_bfloat16* out;         // [F,22,22,64], or the zero-haloed flat layout when flat_out
   int flat_out;
   unsigned long long* dbg;    // optional clock stamps of every CTA [grid][8] (SBLK_DEBUG builds), or nullptr
-  int debug_mode;             // 0 = normal; timing experiments (SBLK_DEBUG builds), bit mask: 1 no MMAs, 2 no loads, 4 no accumulator reads, 8 no pooling / stores, 16 MMAs with N = 32, 32 no stores
+  int debug_mode;             // 0 = normal; timing experiments (SBLK_DEBUG builds), bit mask: 1 no MMAs, 2 no loads, 4 no accumulator reads, 8 no pooling / stores, 16 MMAs with N = 32, 32 no stores, 64 fused producers load nothing, 128 fused producers store nothing
 };
 
 // Epilogue of one warp: pooled columns [11 * HALF, 11 * HALF + 11) of every tile step, for the 32 (frame, channel) lanes
@@ -202,9 +216,147 @@ __device__ __forceinline__ void stem_t_epilogue(const StemTParams& p, uint32_t t
   }
 }
 
-__global__ void __launch_bounds__(stt::THREADS, 1)
+
+// ------------------------------------------------ entry producers of the FUSED forms (SRC 1: fp32 clip, 2: uint8 frames).
+// A stage holds, per existing input frame pp and row-parity plane pl, the entries of plane rows
+// 2*i0 .. 2*i0 + 2*gn + 3 (44 entries of 16 bytes per row): entry (yy, cx) = the 8 pixels 2cx-3 .. 2cx+4 of input row
+// 2*yy + pl - 3, zero outside the frame (sblk_aux.cuh::prep_clip).  Work item = FOUR consecutive entries of one row
+// (cx = 4q .. 4q+3, q < 11): the thread loads the 16 pixels 8q-4 .. 8q+11 (four aligned 16-byte loads of the fp32 clip, or
+// 16 bytes of the uint8 frame through the normalisation table), packs them to eight bf16 pairs P0..P7 and funnel-shifts
+// neighbours, F_k = (P_k >> 16) | (P_{k+1} << 16): entry e is (F_e, F_e+1, F_e+2, F_e+3).  The items of all existing frames
+// are spread over all producer threads; PROD_BATCH items per thread are requested before the first one is used.
+// Bank conflicts: every item's 64 bytes start at a multiple of 64, so threads storing the same entry index would hit the
+// same four banks (4-way); the store order is rotated by rho = (item >> 1) & 3 — a per-thread constant because the
+// thread stride is a multiple of 8 — which makes every quarter-warp store 8 distinct 16-byte slots.
+template <int SRC>
+__device__ __forceinline__ void stem_t_produce(const StemTParams& p, uint8_t* smem, const uint16_t* lut_s,
+                                               uint64_t* full_bar, uint64_t* empty_bar, int s_begin, int s_end,
+                                               int ptid, int lane) {
+  using namespace stt;
+  constexpr int PROD_THREADS = PROD_WARPS * 32;
+  static_assert(PROD_THREADS % 8 == 0, "the rotation must be a per-thread constant");
+  const int T = p.T;
+  const int ppc = (T + 1) >> 1;
+  const int rho = (ptid >> 1) & 3;
+  int stage = 0;
+  uint32_t phase = 0;
+  int s = s_begin;
+  while (s < s_end) {
+    const int u = s / TILES_PER_UNIT;
+    const int i0 = s - u * TILES_PER_UNIT;
+    int gn = TILES_PER_UNIT - i0;
+    if (gn > G) gn = G;
+    if (gn > s_end - s) gn = s_end - s;
+    const int n = u / ppc;
+    const int t0 = (u - n * ppc) * 2;
+    const int nrows = 2 * gn + 4;                      // plane rows per (frame, plane) window; the last one holds 8 entries
+    const int pp_lo = max(0, 2 - t0);
+    const int pp_hi = min(NP - 1, T + 1 - t0);         // existing frames t0 - 2 + pp, pp_lo <= pp <= pp_hi
+    const int rows2 = 2 * nrows;                       // 12, 16, 20 or 24
+    const uint32_t rcp = (65536u + rows2 - 1) / rows2; // x / rows2 == (x * rcp) >> 16 for x < 144
+    const int n_items = (pp_hi - pp_lo + 1) * rows2 * 11;
+    mbar_wait(&empty_bar[stage], phase ^ 1u, 0x0906);
+    uint8_t* const sbase = smem + stage * STAGE_BYTES;
+    for (int it0 = ptid; it0 < n_items; it0 += PROD_THREADS * PROD_BATCH) {
+      uint32_t dsto[PROD_BATCH];        // byte offset of the item's first entry in the stage
+      bool item[PROD_BATCH];            // the item exists (inside the window)
+      bool edge0[PROD_BATCH], edge3[PROD_BATCH];   // pixels -4..-1 / 88..91 of the row: padding
+      bool rowok[PROD_BATCH];           // the row holds data (else: zero entries)
+      float4 vf[PROD_BATCH][4];
+      uint32_t vb[PROD_BATCH][4];       // uint8 input: 16 table indices, four per word
+#pragma unroll
+      for (int b = 0; b < PROD_BATCH; ++b) {
+        const int it = it0 + b * PROD_THREADS;
+        const int plr_all = it / 11;
+        const int q = it - plr_all * 11;
+        const int fi = static_cast<int>((static_cast<uint32_t>(plr_all) * rcp) >> 16);
+        const int plr = plr_all - fi * rows2;
+        const int pl = plr >= nrows ? 1 : 0;
+        const int r = plr - pl * nrows;
+        const int pp = pp_lo + fi;
+        const int tp = t0 - 2 + pp;
+        const int y = 2 * (2 * i0 + r) + pl - 3;
+        item[b] = it < n_items && !(r == nrows - 1 && q >= 2);
+        dsto[b] = static_cast<uint32_t>((pp * 2 + pl) * WIN_BYTES + (r * CONV_HW + 4 * q) * 16);
+        edge0[b] = q == 0;
+        edge3[b] = q == 10;
+        bool row = item[b] && y >= 0 && y < c3d::IN_HW && !(p.debug_mode & 64);   // else: zero entries
+        if (SRC == 1) {
+          const float4* src = reinterpret_cast<const float4*>(
+                                  p.x_f32 + ((static_cast<size_t>(n) * T + tp) * c3d::IN_HW + y) * c3d::IN_HW) + (2 * q - 1);
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          vf[b][0] = (row && !edge0[b]) ? __ldg(src) : z;
+          vf[b][1] = row ? __ldg(src + 1) : z;
+          vf[b][2] = row ? __ldg(src + 2) : z;
+          vf[b][3] = (row && !edge3[b]) ? __ldg(src + 3) : z;
+        } else {
+          row = row && tp < p.T_in;
+          const size_t fr = static_cast<size_t>(n) * p.T_in + (row ? tp : 0);
+          const int cy = (row && p.crop_yx != nullptr) ? __ldg(p.crop_yx + 2 * fr) : p.crop_y0;
+          const int cx = (row && p.crop_yx != nullptr) ? __ldg(p.crop_yx + 2 * fr + 1) : p.crop_x0;
+          const uint8_t* src = p.x_u8 + (fr * p.H0 + (cy + y)) * p.W0 + cx + (8 * q - 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const bool ok = row && !(k == 0 && edge0[b]) && !(k == 3 && edge3[b]);
+            uint32_t w = 0;
+            if (ok) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) w |= static_cast<uint32_t>(__ldg(src + 4 * k + m)) << (8 * m);
+            }
+            vb[b][k] = w;
+          }
+        }
+        rowok[b] = row;
+      }
+#pragma unroll
+      for (int b = 0; b < PROD_BATCH; ++b) {
+        uint32_t P[8];
+        if (SRC == 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            P[2 * k] = pack_bf16x2(vf[b][k].x, vf[b][k].y);
+            P[2 * k + 1] = pack_bf16x2(vf[b][k].z, vf[b][k].w);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t w = vb[b][k];
+            const bool ok = rowok[b] && !(k == 0 && edge0[b]) && !(k == 3 && edge3[b]);
+            const uint32_t lo = static_cast<uint32_t>(lut_s[w & 0xFFu]) | (static_cast<uint32_t>(lut_s[(w >> 8) & 0xFFu]) << 16);
+            const uint32_t hi = static_cast<uint32_t>(lut_s[(w >> 16) & 0xFFu]) | (static_cast<uint32_t>(lut_s[w >> 24]) << 16);
+            P[2 * k] = ok ? lo : 0u;
+            P[2 * k + 1] = ok ? hi : 0u;
+          }
+        }
+        uint32_t F[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) F[k] = __funnelshift_r(P[k], P[k + 1], 16);
+        // entries in the rotated order: step st stores entry (st + rho) & 3
+        uint4 E[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) E[e] = make_uint4(F[e], F[e + 1], F[e + 2], F[e + 3]);
+        if (rho & 1) { const uint4 t = E[0]; E[0] = E[1]; E[1] = E[2]; E[2] = E[3]; E[3] = t; }
+        if (rho & 2) { uint4 t = E[0]; E[0] = E[2]; E[2] = t; t = E[1]; E[1] = E[3]; E[3] = t; }
+        if (item[b] && !(p.debug_mode & 128)) {
+          uint8_t* const dst = sbase + dsto[b];
+#pragma unroll
+          for (int st = 0; st < 4; ++st) *reinterpret_cast<uint4*>(dst + (((st + rho) & 3) << 4)) = E[st];
+        }
+      }
+    }
+    fence_proxy_async_smem();   // generic-proxy entry writes -> visible to the tensor core's operand reads
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full_bar[stage]);
+    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    s += gn;
+  }
+}
+
+template <int SRC>   // input: 0 = prepped copy of the clip (prep_clip), 1 = fp32 clip, 2 = raw uint8 frames
+__global__ void __launch_bounds__(SRC != 0 ? stt::THREADS_FUSED : stt::THREADS, 1)
 stem_t_kernel(const StemTParams p) {
   using namespace stt;
+  constexpr bool FUSED = SRC != 0;
   constexpr uint32_t IDESC = make_idesc_bf16(128, TILE_N);
 
   extern __shared__ uint8_t smem_raw[];
@@ -214,6 +366,7 @@ stem_t_kernel(const StemTParams p) {
   __shared__ uint64_t accempty_bar[ACC_BUFS];
   __shared__ uint64_t filter_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ uint16_t lut_s[256];                              // FUSED, uint8 input: normalisation table
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -236,7 +389,7 @@ stem_t_kernel(const StemTParams p) {
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], FUSED ? PROD_WARPS : 1);
       mbar_init(&empty_bar[s], MMA_WARPS);
     }
 #pragma unroll
@@ -284,11 +437,15 @@ stem_t_kernel(const StemTParams p) {
     if (lane == 0) mbar_arrive(&filter_bar);
   }
 
+  if (SRC == 2) {   // normalisation table (an input of the launch, not of the previous kernel)
+    if (threadIdx.x < 256) lut_s[threadIdx.x] = __ldg(p.lut_bf16 + threadIdx.x);
+    __syncthreads();
+  }
   if (warp == 0) stamp(1);
   grid_dep_wait();
   if (warp == 0) stamp(2);
 
-  if (warp == 0) {
+  if (warp == 0 && !FUSED) {
     // ------------------------------------------------ loader: per group of <= G tiles, the entry windows of the
     // (up to) six input frames, two row-parity planes each
     int stage = 0;
@@ -331,6 +488,9 @@ stem_t_kernel(const StemTParams p) {
       s += gn;
     }
     stamp(6);
+  } else if (FUSED && (warp == 0 || warp >= 3 + EPI_WARPS)) {
+    stem_t_produce<SRC>(p, smem, lut_s, full_bar, empty_bar, s_begin, s_end,
+                        (warp == 0 ? 0 : (warp - (2 + EPI_WARPS)) * 32) + lane, lane);
   } else if (warp == 1 || warp == 2 + EPI_WARPS) {
     // ------------------------------------------------ MMA issuers.  One thread cannot keep the tensor pipe fed here: a
     // tile step is 24 short MMAs (48 cycles each) whose descriptors differ, ~7 uniform-datapath instructions per MMA

@@ -264,16 +264,76 @@ def prep_clip_u8(x_u8, lut, t_out=None, crop=(4, 4), out=None):
     return out, n, t_out
 
 
+class RawClip:
+    """An un-prepped stem input for the FUSED stem (sblk_stem_fused_fwd): the kernel's producer warps build the
+    row-Toeplitz entries themselves, so no prepped copy of the clip is written.  kind "f32": x fp32 [N,1,T,88,88] /
+    [N,T,88,88]; kind "u8": raw uint8 frames [N,T_in,H0,W0] + normalisation table + crop + frame padding."""
+    __slots__ = ("kind", "x", "lut", "crop", "n", "t_in", "t")
+
+    def __init__(self, kind, x, n, t_in, t, lut=None, crop=None):
+        self.kind, self.x, self.n, self.t_in, self.t, self.lut, self.crop = kind, x, n, t_in, t, lut, crop
+
+
+def raw_clip(x):
+    """fp32 clips for the fused stem (same checks as prep_clip; nothing is launched)."""
+    _req(x, F32, "x")
+    if x.dim() == 5:
+        n, c, t, h, w = x.shape
+        if c != 1:
+            raise RuntimeError("raw_clip: expected one (gray) channel")
+    else:
+        n, t, h, w = x.shape
+    if (h, w) != (88, 88):
+        raise RuntimeError(f"raw_clip: frames must be 88x88, got {h}x{w}")
+    return RawClip("f32", x, n, t, t)
+
+
+def raw_clip_u8(x_u8, lut, t_out=None, crop=(4, 4)):
+    """Raw uint8 frames for the fused stem (same checks as prep_clip_u8; nothing is launched)."""
+    if not x_u8.is_cuda or x_u8.dtype != torch.uint8 or not x_u8.is_contiguous() or x_u8.dim() != 4:
+        raise RuntimeError("raw_clip_u8: expected a contiguous CUDA uint8 tensor [N,T,H0,W0] (no CPU fallback exists)")
+    _req(lut, BF16, "lut")
+    if lut.numel() != 256:
+        raise RuntimeError("raw_clip_u8: lut must hold 256 bf16 values")
+    n, t_in, h0, w0 = x_u8.shape
+    t_out = t_in if t_out is None else int(t_out)
+    if torch.is_tensor(crop):
+        _req(crop, torch.int32, "crop")
+        if tuple(crop.shape) != (n * t_in, 2):
+            raise RuntimeError(f"raw_clip_u8: per-frame crop must be int32 [{n * t_in}, 2]")
+    else:
+        crop = (int(crop[0]), int(crop[1]))
+    return RawClip("u8", x_u8, n, t_in, t_out, lut=lut, crop=crop)
+
+
 def conv3d_bn_relu_pool(xp, wp, bias, out=None, flat=False):
-    """prepped clip (out, N, T) of prep_clip -> bf16 NHWC [N*T,22,22,64], or FlatActs when flat=True."""
-    xp, n, t = xp
-    _req(xp, BF16, "xp"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
+    """Stem: prepped clip (out, N, T) of prep_clip[_u8] — or a RawClip (fused: no prepped copy) — -> bf16 NHWC
+    [N*T,22,22,64], or FlatActs when flat=True."""
+    raw = xp if isinstance(xp, RawClip) else None
+    if raw is not None:
+        n, t, dev_ = raw.n, raw.t, raw.x.device
+    else:
+        xp, n, t = xp
+        _req(xp, BF16, "xp")
+        dev_ = xp.device
+    _req(wp, BF16, "wp"); _req(bias, F32, "bias")
     if out is None:
         shape = (flat_rows(n * t, 22, 22), 64) if flat else (n * t, 22, 22, 64)
-        out = torch.empty(shape, dtype=BF16, device=xp.device)
+        out = torch.empty(shape, dtype=BF16, device=dev_)
     _req(out, BF16, "out")
-    _call("sblk_conv3d_bn_relu_pool_fwd", f"conv3d N={n} T={t}", 2 * 64 * 44 * 44 * 245 * n * t,
-          2 * xp.numel() + 2 * out.numel(), _p(xp), _p(wp), _p(bias), _p(out), n, t, 1 if flat else 0, _stream())
+    flops = 2 * 64 * 44 * 44 * 245 * n * t
+    if raw is None:
+        _call("sblk_conv3d_bn_relu_pool_fwd", f"conv3d N={n} T={t}", flops,
+              2 * xp.numel() + 2 * out.numel(), _p(xp), _p(wp), _p(bias), _p(out), n, t, 1 if flat else 0, _stream())
+    elif raw.kind == "f32":
+        _call("sblk_stem_fused_fwd", f"conv3d N={n} T={t}", flops, 4 * raw.x.numel() + 2 * out.numel(),
+              _p(raw.x), None, None, None, 0, 0, _p(wp), _p(bias), _p(out), n, t, t, 88, 88, 1 if flat else 0, _stream())
+    else:
+        crop_t, cy, cx = (raw.crop, 0, 0) if torch.is_tensor(raw.crop) else (None, raw.crop[0], raw.crop[1])
+        h0, w0 = raw.x.shape[2], raw.x.shape[3]
+        _call("sblk_stem_fused_fwd", f"conv3d N={n} T={t}", flops, raw.x.numel() + 2 * out.numel(),
+              None, _p(raw.x), _p(raw.lut), _p(crop_t), cy, cx, _p(wp), _p(bias), _p(out), n, raw.t_in, t, h0, w0,
+              1 if flat else 0, _stream())
     return FlatActs(out, n * t, 22, 22) if flat else out
 
 

@@ -125,6 +125,13 @@ class Lipreading(nn.Module):
         # and the first `head_blocks` residual blocks size their persistent grids for `sm_limit` SMs because another
         # kernel chain (the previous batch's encoder stack) co-runs on the other SMs; `join()` is called once the head
         # is enqueued and makes the current stream wait for that chain before the full-width kernels start
+        # eval path: clip prep fused into the stem kernel (sblk_stem_fused_fwd: the stem's producer warps build the
+        # row-Toeplitz entries from the fp32 clip, no prepped copy of the clip in HBM, one launch less; bit-identical).
+        # Measured (tools/exp/stem_fused_probe.py, head_frac_probe.py): fp32 clips 91.1 -> 86.7 us alone, pipelined step
+        # 661.5 -> 651.3 us; raw uint8 frames 93.2 -> 122.9 us (16 byte loads + 16 table look-ups per work item), so the
+        # uint8 path keeps the separate prep launch unless fuse_prep_u8 is set
+        self.fuse_prep = True
+        self.fuse_prep_u8 = False
         self._overlap = None
         # (scale | None, out_bf16) set by the same plan: the average pool writes mean * scale as bf16 straight into the
         # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
@@ -153,6 +160,8 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("l2_prefetch", True)
         self.__dict__.setdefault("l2_prefetch_extra", None)
         self.__dict__.setdefault("_overlap", None)
+        self.__dict__.setdefault("fuse_prep", True)
+        self.__dict__.setdefault("fuse_prep_u8", False)
         self.__dict__.setdefault("_tail", None)
 
     def _initialize_weights(self):  # same as reference :127-157
@@ -262,7 +271,9 @@ class Lipreading(nn.Module):
             ops.set_sm_limit(head.pop("limit"))
             ov[2]()
 
-        xp = prep(x)
+        # fuse_prep: the stem's producer warps build the row-Toeplitz entries themselves (ops.RawClip) instead of reading
+        # a prepped copy of the clip written by a separate launch (bit-identical)
+        xp = ops.raw_clip(x) if (self.fuse_prep and prep is ops.prep_clip) else prep(x)
         # layer1 / layer2 run on the zero-haloed flat layout (flat shifted-window kernels);
         # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
@@ -408,6 +419,8 @@ class Lipreading(nn.Module):
                 raise RuntimeError("forward_u8: per-frame crop offsets need parallel_chains == 1")
 
         def prep(xs):
+            if self.fuse_prep_u8:
+                return ops.raw_clip_u8(xs, lut, t_out, crop)
             return ops.prep_clip_u8(xs, lut, t_out, crop)
 
         feat = self._frontend_forward(x_u8, prep=prep, frames=t_out)

@@ -323,6 +323,74 @@ def test_stem_variants_agree_bit_for_bit(frontend, dev, n, t):
     assert torch.equal(few, outs[0])
 
 
+@pytest.mark.parametrize("n,t", [(1, 1), (1, 2), (2, 5), (3, 7), (2, 29), (1, 40)])
+def test_fused_stem_is_bit_identical_to_prep_plus_stem(frontend, dev, n, t):
+    """sblk_stem_fused_fwd (the stem's producer warps build the row-Toeplitz entries straight from the fp32 clip or the
+    raw uint8 frames; no prepped copy of the clip) against sblk_prep_clip[_u8] + sblk_conv3d_bn_relu_pool_fwd: both
+    output layouts, odd / even frame counts, clip edges, a limited grid, uniform and per-frame crops, frame padding."""
+    from sbl_for_multilingual_lip_reading_b200 import ops, synth
+    pk = frontend._get_packed()
+    x = synth.synthetic_clips(n, t, seed=1300 + 10 * n + t).to(dev)
+    ref = ops.conv3d_bn_relu_pool(ops.prep_clip(x), pk.c3w, pk.c3b)
+    assert torch.equal(ops.conv3d_bn_relu_pool(ops.raw_clip(x), pk.c3w, pk.c3b), ref)
+    ref_flat = ops.conv3d_bn_relu_pool(ops.prep_clip(x), pk.c3w, pk.c3b, flat=True)
+    dirty = torch.full((ops.flat_rows(n * t, 22, 22), 64), 3.0, dtype=torch.bfloat16, device=dev)
+    got_flat = ops.conv3d_bn_relu_pool(ops.raw_clip(x), pk.c3w, pk.c3b, out=dirty, flat=True)
+    assert torch.equal(got_flat.data, ref_flat.data)
+    old = ops.set_sm_limit(6)
+    try:
+        assert torch.equal(ops.conv3d_bn_relu_pool(ops.raw_clip(x), pk.c3w, pk.c3b), ref)
+    finally:
+        ops.set_sm_limit(old)
+    # raw uint8 frames: uniform crop, frame padding, per-frame crops
+    lut = synth.normalize_lut().to(dev)
+    u8 = synth.synthetic_u8_clips(n, t, h0=100, w0=92, seed=n + t).to(dev)
+    g = torch.Generator().manual_seed(n * 7 + t)
+    offs = torch.stack([torch.randint(0, 13, (n * t,), generator=g), torch.randint(0, 5, (n * t,), generator=g)], 1)
+    for crop, t_out in (((6, 2), t), ((12, 4), t + 3), (offs.int().to(dev), t + 1)):
+        r = ops.conv3d_bn_relu_pool(ops.prep_clip_u8(u8, lut, t_out, crop), pk.c3w, pk.c3b, flat=True)
+        f = ops.conv3d_bn_relu_pool(ops.raw_clip_u8(u8, lut, t_out, crop), pk.c3w, pk.c3b, flat=True)
+        assert torch.equal(f.data, r.data)
+
+
+def test_fused_stem_through_the_modules_and_its_error_behaviour(frontend, dev):
+    """Lipreading.forward / forward_u8 with and without the fused stem return the same bits; the C ABI rejects calls
+    that name no input, both inputs, or an fp32 clip with frame padding."""
+    import ctypes
+    from sbl_for_multilingual_lip_reading_b200 import _lib, ops, synth
+    x = synth.synthetic_clips(3, 7, seed=77).to(dev)
+    u8 = synth.synthetic_u8_clips(2, 6, seed=78).to(dev)
+    saved = (frontend.fuse_prep, frontend.fuse_prep_u8)
+    with torch.no_grad():   # one-time work (weight packing, normalisation table) outside the launch counts
+        frontend(x[:1]), frontend.forward_u8(u8[:1], frames=6)
+    try:
+        outs = []
+        for fuse in (False, True):
+            frontend.fuse_prep = frontend.fuse_prep_u8 = fuse
+            before = ops.launch_count()
+            with torch.no_grad():
+                outs.append((frontend(x), frontend.forward_u8(u8, frames=8)))
+            outs.append(ops.launch_count() - before)
+    finally:
+        frontend.fuse_prep, frontend.fuse_prep_u8 = saved
+    assert torch.equal(outs[0][0], outs[2][0]) and torch.equal(outs[0][1], outs[2][1])
+    assert outs[3] == outs[1] - 2          # one launch less per forward
+    lib = _lib.load()
+    pk = frontend._get_packed()
+    out = torch.empty((7, 22, 22, 64), dtype=torch.bfloat16, device=dev)
+    xa = x[:1].contiguous()
+    p = lambda t_: ctypes.c_void_p(t_.data_ptr())
+    none = ctypes.c_void_p(0)
+    assert lib.sblk_stem_fused_fwd(none, none, none, none, 0, 0, p(pk.c3w), p(pk.c3b), p(out), 1, 7, 7, 88, 88, 0, none) != 0
+    assert "exactly one" in _lib.last_error()
+    assert lib.sblk_stem_fused_fwd(p(xa), p(u8), none, none, 0, 0, p(pk.c3w), p(pk.c3b), p(out), 1, 7, 7, 88, 88, 0, none) != 0
+    assert lib.sblk_stem_fused_fwd(p(xa), none, none, none, 0, 0, p(pk.c3w), p(pk.c3b), p(out), 1, 7, 8, 88, 88, 0, none) != 0
+    assert "T_out == T_in" in _lib.last_error()
+    lut = synth.normalize_lut().to(dev)
+    assert lib.sblk_stem_fused_fwd(none, p(u8), p(lut), none, 9, 4, p(pk.c3w), p(pk.c3b), p(out), 1, 6, 7, 96, 96, 0, none) != 0
+    assert "crop offset" in _lib.last_error()
+
+
 def test_encoder_stack_rejects_unsupported_shapes(dev):
     from sbl_for_multilingual_lip_reading_b200 import ops, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder

@@ -40,19 +40,21 @@ def time_plan(plan, reps=30):
     return ts[len(ts) // 2], ts[0]
 
 
+fe.fuse_prep = bool(int(os.environ.get("FUSE_PREP", "1")))
+print("fuse_prep", fe.fuse_prep)
 for var in [int(v) for v in os.environ.get('VARIANTS', '0,1').split(',')]:
     ops.set_stem_variant(var)
     plain = VisualEncoderPlan(fe, enc, N, T, device=dev)
     med, best = time_plan(plain)
     print(f"stem variant {var}: plain plan median {med:.1f} us  best {best:.1f} us")
     del plain
-    for hf in [float(v) for v in os.environ.get("HEAD_FRACS", "0.5,0.7,0.85,1.0").split(",")]:
+    for hf in [(float(v) if v != "auto" else None) for v in os.environ.get("HEAD_FRACS", "0.5,0.7,0.85,1.0").split(",")]:
         for lim in [int(v) for v in os.environ.get("HEAD_LIMITS", "0").split(",")]:
             p = PipelinedVisualEncoderPlan(fe, enc, N, T, device=dev, head_frac=hf, head_sm_limit=lim or None,
-                                           head_blocks=int(os.environ.get("HEAD_BLOCKS", "0")),
-                                           enc_gpc=int(os.environ.get("ENC_GPC", "1")))
+                                           head_blocks=(int(os.environ["HEAD_BLOCKS"]) if "HEAD_BLOCKS" in os.environ else None),
+                                           enc_gpc=(int(os.environ["ENC_GPC"]) if "ENC_GPC" in os.environ else None))
             med, best = time_plan(p)
-            print(f"stem variant {var}: pipelined head_frac={hf} head_sm_limit={p.head_sm_limit}: median {med:.1f} us  best {best:.1f} us  "
+            print(f"stem variant {var}: pipelined head_frac={p.head_frac} head_blocks={p.head_blocks} gpc={p.enc_gpc} head_sm_limit={p.head_sm_limit}: median {med:.1f} us  best {best:.1f} us  "
                   f"({N / med * 1e6:.0f} clips/s)")
             p.close()
             del p
