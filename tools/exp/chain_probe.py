@@ -34,7 +34,8 @@ def graph_time(fn, reps=12):
     return ts[len(ts) // 2]
 
 
-for (C, H, flat) in ((64, 22, True), (128, 11, True), (256, 6, False), (512, 3, False)):
+SHAPES = [tuple(int(v) for v in t.split(":")) for t in os.environ.get("SHAPES", "64:22:1,128:11:1,256:6:0,512:3:0").split(",")]
+for (C, H, flat) in SHAPES:
     if flat:
         rows = ops.flat_rows(F_, H, H)
         bufs = [ops.FlatActs(torch.randn(rows, C, generator=g).to(bf).to(DEV), F_, H, H) for _ in range(3)]
@@ -58,7 +59,7 @@ for (C, H, flat) in ((64, 22, True), (128, 11, True), (256, 6, False), (512, 3, 
           f"  -> marginal {per:.1f} us per conv ({flops / per / 1e6:.0f} TFLOP/s), first conv {res[0][1]:.1f} us", flush=True)
 
 # strided block heads (3x3/s2 conv + 1x1/s2 downsample in one launch)
-for (Cin, Cout, H) in ((64, 128, 22), (128, 256, 11), (256, 512, 6)):
+for (Cin, Cout, H) in (() if os.environ.get("NO_HEADS") else ((64, 128, 22), (128, 256, 11), (256, 512, 6))):
     x = torch.randn(F_, H, H, Cin, generator=g).to(bf).to(DEV)
     w = (torch.randn(Cout, 3, 3, Cin, generator=g) / (3 * Cin ** 0.5)).to(bf).to(DEV)
     wd = (torch.randn(Cout, 1, 1, Cin, generator=g) / (Cin ** 0.5)).to(bf).to(DEV)
