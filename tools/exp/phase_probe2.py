@@ -84,9 +84,27 @@ def run_both(limit, hb, gpc):
     main.wait_event(done)
 
 
-def run_tail(hb):
-    a = run_blocks(state["a"], hb, 8)
-    ops.avgpool(a, want_f32=False, want_bf16=True)
+def run_tail(hb, limit=0):
+    prev = ops.set_sm_limit(limit)
+    try:
+        a = run_blocks(state["a"], hb, 8)
+        ops.avgpool(a, want_f32=False, want_bf16=True)
+    finally:
+        ops.set_sm_limit(prev)
+
+
+def run_enc_with_tail(limit, hb, gpc):
+    """the other split: full-width head, then the encoder next to the TAIL (layers 3-4 move few activation bytes)"""
+    main = torch.cuda.current_stream()
+    fork, done = torch.cuda.Event(), torch.cuda.Event()
+    fork.record(main)
+    side.wait_event(fork)
+    with torch.cuda.stream(side):
+        run_enc(gpc, gate)
+        done.record(side)
+    ops.gate_wait(gate, 32 if gpc == 2 else 64, 300)
+    run_tail(hb, limit)
+    main.wait_event(done)
 
 
 def graph_time(fn, reps=20):
@@ -127,3 +145,14 @@ for lim in (100, 108, 124, 132):
     h = graph_time(lambda: run_head(lim, hb))
     both = graph_time(lambda: run_both(lim, hb, 2))
     print(f"head_blocks={hb} limit {lim}: head alone {h:.1f} us, encoder || head {both:.1f} us")
+
+print("--- encoder next to the tail instead of the head")
+for hb in (3, 4, 5):
+    run_head(0, hb)
+    torch.cuda.synchronize()
+    hf = graph_time(lambda: run_head(0, hb))
+    for lim, gpc in ((116, 2), (84, 1)):
+        t_alone = graph_time(lambda: run_tail(hb, lim))
+        both = graph_time(lambda: run_enc_with_tail(lim, hb, gpc))
+        print(f"head_blocks={hb}: head on 148 SMs {hf:.1f} us; tail alone on {lim} SMs {t_alone:.1f} us; encoder({gpc} gpc) || tail {both:.1f} us; "
+              f"sum {hf + both:.1f} us")

@@ -27,10 +27,11 @@ def launches(path, last_n=None):
         lines = [l for l in f if l.startswith('"')]
     for r in csv.DictReader(io.StringIO("".join(lines))):
         if r["Metric Name"] == "gpu__time_duration.sum":
-            name = r["Kernel Name"].split("(")[0].replace("sblk::", "")
+            name = r["Kernel Name"].split("(")[0].replace("sblk::", "").replace("void ", "")
             rows.append((name, r["Grid Size"], r["Block Size"], float(r["Metric Value"]) / 1e3))
-    if last_n == -1:  # last forward pass only: from the last prep_clip launch to the end
-        start = max(i for i, r in enumerate(rows) if r[0].startswith("prep_clip"))
+    if last_n == -1:  # last forward pass only: from the last clip-prep / stem launch (the first kernel of a forward) to the end
+        first = "prep_clip" if any(r[0].startswith("prep_clip") for r in rows) else "stem_t_kernel"
+        start = max(i for i, r in enumerate(rows) if r[0].startswith(first))
         rows = rows[start:]
     elif last_n:
         rows = rows[-last_n:]

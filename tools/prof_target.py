@@ -22,6 +22,14 @@ if what == "conv3d":
     out = torch.empty(928, 22, 22, 64, dtype=bf, device=dev)
     for _ in range(iters):
         ops.conv3d_bn_relu_pool(xp, wp, b, out=out)
+elif what == "stemfused":   # the stem with the clip prep fused in (fp32 clips in, no prepped copy)
+    w3 = (torch.randn(64, 1, 5, 7, 7, generator=g) / 16).to(dev)
+    one, zero = torch.ones(64, device=dev), torch.zeros(64, device=dev)
+    wp, b = ops.pack_conv3d(w3, one, zero, zero, one)
+    x = synth.synthetic_clips(32, 29, seed=7).to(dev)
+    out = ops.conv3d_bn_relu_pool(ops.raw_clip(x), wp, b, flat=True)
+    for _ in range(iters):
+        ops.conv3d_bn_relu_pool(ops.raw_clip(x), wp, b, out=out.data, flat=True)
 elif what in ("l1conv", "l2conv", "l3conv", "l4conv"):
     H, C = {"l1conv": (22, 64), "l2conv": (11, 128), "l3conv": (6, 256), "l4conv": (3, 512)}[what]
     x = torch.randn(928, H, H, C, generator=g).to(bf).to(dev)
