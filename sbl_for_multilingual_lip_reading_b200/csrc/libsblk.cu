@@ -777,7 +777,18 @@ static int conv2d_igemm_impl(const void* x, const void* wp, const float* bias, c
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
     const int m_tiles = (M + 127) / 128;
     // CTA-pair kernel (sblk_igemm2.cuh) for every conv with Cout >= 128: half the B bytes per SM
-    const int bn2 = use_cta_pairs() && Cout % 128 == 0 ? ((wp_ds || Cout % 256 != 0) ? 128 : 256) : 0;
+    int bn2 = use_cta_pairs() && Cout % 128 == 0 ? ((wp_ds || Cout % 256 != 0) ? 128 : 256) : 0;
+    if (bn2 == 256) {
+      // small problems (the 8-clip shard of BASELINE configs[2]: 24 pair tiles of 256 x 256 at layer 4 on 74 CTA pairs):
+      // 256 x 128 tiles when they still run as one wave — twice the CTAs, half the k-loop time each.  A tile's time is
+      // ~ its width, so the choice minimises waves x width; ties keep the wider tile (fewer operand bytes per FLOP).
+      // Bit-identical either way: every output element accumulates its K range in the same order.
+      const long long pairs_avail = sms / 2 > 0 ? sms / 2 : 1;
+      const long long t256 = static_cast<long long>((M + 255) / 256) * (Cout / 256);
+      const long long time256 = ((t256 + pairs_avail - 1) / pairs_avail) * 2;
+      const long long time128 = (2 * t256 + pairs_avail - 1) / pairs_avail;
+      if (time128 < time256) bn2 = 128;
+    }
     const int bn = bn2 ? bn2 : wp_ds ? 128 : pick_block_n(m_tiles, Cout, sms);
     if (flat_out && !bn2) return fail(-1, "sblk_conv2d_dual_igemm_fwd: flat_out needs the CTA-pair kernel (Cout %% 128 == 0)");
     cuuint32_t box[2] = {64, static_cast<cuuint32_t>(bn2 ? bn2 / 2 : bn)};
