@@ -1,11 +1,11 @@
-set -x
 mkdir -p gpurun_out
-timeout 600 python bench.py > gpurun_out/r02h_bench_N32_T29.json 2> gpurun_out/r02h_bench.err; echo "bench rc=$?"
+timeout 1500 python -m pytest tests -m gpu -q --tb=short > gpurun_out/pytest_gpu_final.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/pytest_gpu_final.log
+timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_final.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_final.log
+timeout 600 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_final.json 2> gpurun_out/bench_ref_final.err; echo "ref rc=$?"; cat gpurun_out/bench_ref_final.json | cut -c1-600
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/r02h_bench_N32_T29.json'))
-print(d['value'], d['ms_per_step'], d['e2e']['value'], d.get('latency',{}).get('ms_per_step'), d['roofline']['kernel'], d['roofline']['avg_launch_us'], d['roofline']['frac'], d['gpu_launches'], d['clocks'])
-print({k: (d[k] if not isinstance(d[k], dict) else {kk: d[k][kk] for kk in list(d[k])[:6]}) for k in d if k in ('sustained','config2')})
+d=json.load(open('gpurun_out/bench_final.json'))
+print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'u8', d['e2e_u8']['value'], 'lat', d.get('latency',{}).get('ms_per_step'), d['roofline']['kernel'], d['roofline']['frac'], d['gpu_launches'], d['clocks'])
+print('config2', d['config2']['value'], 'sustained', d['sustained']['clips_per_s'], d['sustained']['frac_of_bf16_sustained'], 'cpu', d['cpu_baseline']['value'])
 PY
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02h_launches_forward.csv python tools/prof_target.py forward 2 > gpurun_out/ncu_fwd.log 2>&1; echo "launchlist rc=$?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:stem_t -s 1 -c 1 -o gpurun_out/r02h_stem_fused python tools/prof_target.py stemfused 3 > gpurun_out/ncu_stem.log 2>&1; echo "ncu full rc=$?"; ls -la gpurun_out/*.ncu-rep | tail -2
