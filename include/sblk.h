@@ -351,13 +351,16 @@ int sblk_bidir_mix_fwd(const float* l2r, const float* r2l, float* l2r_out, float
  * rank's gather buffer [world * bytes_per_rank], publishes flag[rank] = epoch in every rank's flag array
  * (unsigned [world]) and returns only when all `world` flags of its own array carry `epoch` (ncclAllGather completion
  * semantics).  peer_bufs_dev / peer_flags_dev: DEVICE arrays of `world` pointers (entry `rank` = the local buffers);
- * counter_dev: device unsigned, zero-initialised; epoch must increase by one per call on every rank. */
+ * counter_dev: device unsigned, zero-initialised; epoch must increase by one per call on every rank.
+ * sblk_set_p2p_timeout_ms: how long a gather kernel waits for its peers (default 30 s; a rank held up by its data
+ * loader is not an error) before it records watchdog code 0x0901 and traps; returns the previous value. */
 int sblk_p2p_alloc(long long bytes, void** dev_ptr, void* ipc_handle_64);
 int sblk_p2p_open(const void* ipc_handle_64, void** dev_ptr);
 int sblk_p2p_close(void* dev_ptr, int opened);
 int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, const void* const* peer_flags_dev,
                         void* counter_dev, int rank, int world, long long bytes_per_rank, unsigned int epoch,
                         void* stream);
+unsigned int sblk_set_p2p_timeout_ms(unsigned int ms);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,7 @@ SIGNATURES = {
     "sblk_p2p_open": (_i, [_vp, ctypes.POINTER(_vp)]),
     "sblk_p2p_close": (_i, [_vp, _i]),
     "sblk_p2p_gather_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _ll, ctypes.c_uint, _vp]),
+    "sblk_set_p2p_timeout_ms": (ctypes.c_uint, [ctypes.c_uint]),
     "sblk_gemm_fmt_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_transpose16": (_i, [_vp, _vp, _ll, _i, _ll, _ll, _i, _vp]),
     "sblk_im2col_t": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _ll, _vp]),

@@ -9,6 +9,9 @@ nn.DataParallel(Transformer(...)), 'optimizer': TransformerOptimizer} into `chec
 `transformer.optimizer.TransformerOptimizer`, ... on `sys.path`.  Here every class that cannot be imported is replaced
 by a stand-in: `nn.Module`-shaped objects only need `_parameters / _buffers / _modules` for `state_dict()`, everything
 else becomes an attribute bag.  No arithmetic happens here.
+
+A reference `.tar` is a whole-object pickle and is loaded with `weights_only=False`: like `torch.load` on the reference
+side it EXECUTES what the file says — load checkpoints from trusted sources only.
 """
 from __future__ import annotations
 
@@ -42,29 +45,45 @@ class _StubObject:
             self.__dict__["_state"] = state
 
 
+def _is_module_state(state):
+    """A pickled nn.Module carries `_parameters` / `_buffers` / `_modules` in its instance state."""
+    return isinstance(state, dict) and "_parameters" in state and "_modules" in state
+
+
 class _TolerantUnpickler(pickle.Unpickler):
     _stubs = {}
 
     def find_class(self, module, name):
         try:
             return super().find_class(module, name)   # includes pickle's Python-2 name compatibility mapping
-        except Exception:
+        except (ImportError, AttributeError):          # the defining module / class is not importable here
             key = (module, name)
             cls = self._stubs.get(key)
             if cls is None:
-                # module-shaped stand-in for everything that lives in the reference's model packages; the instance
-                # state decides: a pickled nn.Module carries `_parameters` / `_modules`
-                base = _StubModule if _looks_like_module_class(module, name) else _StubObject
-                cls = type(name, (base,), {"__module__": module, "_sblk_stub": True})
+                # The pickled INSTANCE STATE decides what the stand-in is (BUILD time, `__setstate__` below): state with
+                # `_parameters` / `_modules` makes it an nn.Module stand-in, anything else (the reference's
+                # `transformer.optimizer.TransformerOptimizer`, argparse namespaces, ...) stays an attribute bag.
+                def __setstate__(self, state, _name=name, _module=module):
+                    if _is_module_state(state):
+                        self.__class__ = _module_stub_class(_module, _name)
+                        nn.Module.__init__(self)
+                        nn.Module.__setstate__(self, state)
+                    else:
+                        _StubObject.__setstate__(self, state)
+                cls = type(name, (_StubObject,), {"__module__": module, "_sblk_stub": True, "__setstate__": __setstate__})
                 self._stubs[key] = cls
             return cls
 
 
-def _looks_like_module_class(module, name):
-    m = module.split(".")[0]
-    return m in ("transformer", "models", "model") or name in (
-        "Transformer", "Encoder", "EncoderLayer", "Decoder", "DecoderLayer", "Lipreading", "ResNet", "BasicBlock",
-        "MultiHeadAttention", "ScaledDotProductAttention", "PositionalEncoding", "PositionwiseFeedForward")
+_MODULE_STUBS = {}
+
+
+def _module_stub_class(module, name):
+    key = (module, name)
+    cls = _MODULE_STUBS.get(key)
+    if cls is None:
+        cls = _MODULE_STUBS[key] = type(name, (_StubModule,), {"__module__": module, "_sblk_stub": True})
+    return cls
 
 
 class _tolerant_pickle:

@@ -418,6 +418,13 @@ int sblk_p2p_close(void* dev_ptr, int opened) {
   return e == cudaSuccess ? 0 : cuda_fail(e, "sblk_p2p_close");
 }
 
+// how long a gather kernel waits for its peers before it gives up (process-wide; an atomic, read at every launch)
+static std::atomic<unsigned int> g_p2p_timeout_ms{30000u};
+
+unsigned int sblk_set_p2p_timeout_ms(unsigned int ms) {
+  return g_p2p_timeout_ms.exchange(ms == 0 ? 1u : ms, std::memory_order_relaxed);
+}
+
 int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, const void* const* peer_flags_dev,
                         void* counter_dev, int rank, int world, long long bytes_per_rank, unsigned int epoch,
                         void* stream) {
@@ -434,7 +441,8 @@ int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, con
                 static_cast<cudaStream_t>(stream), false, "p2p_gather_kernel", static_cast<const uint4*>(local),
                 reinterpret_cast<uint4* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_bufs_dev))),
                 reinterpret_cast<unsigned int* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_flags_dev))),
-                static_cast<unsigned int*>(counter_dev), rank, world, n16, epoch);
+                static_cast<unsigned int*>(counter_dev), rank, world, n16, epoch,
+                static_cast<unsigned long long>(g_p2p_timeout_ms.load(std::memory_order_relaxed)) * 1000000ull);
 }
 
 long long sblk_prep_clip_elems(int N, int T) {

@@ -249,7 +249,7 @@ l2_prefetch_kernel(const L2PrefetchRanges r, int mode) {
 __global__ void __launch_bounds__(256)
 p2p_gather_kernel(const uint4* __restrict__ local, uint4* const* __restrict__ peer_bufs,
                   unsigned int* const* __restrict__ peer_flags, unsigned int* __restrict__ counter, int rank, int world,
-                  long long n16, unsigned int epoch) {
+                  long long n16, unsigned int epoch, unsigned long long timeout_ns) {
   __shared__ int is_last;
   const long long slot = static_cast<long long>(rank) * n16;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
@@ -281,7 +281,7 @@ p2p_gather_kernel(const uint4* __restrict__ local, uint4* const* __restrict__ pe
         unsigned long long now;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
         if (t0 == 0) t0 = now;
-        if (now - t0 > SBLK_WATCHDOG_NS) {
+        if (now - t0 > timeout_ns) {   // a peer did not show up (sblk_set_p2p_timeout_ms; a data-loader stall is not an error)
           unsigned int* wd = g_sblk_watchdog_ptr;
           if (wd != nullptr) {
             atomicCAS_system(wd, 0u, 0x0901u | 0x80000000u);

@@ -47,6 +47,13 @@ def max_over_ranks(value: float, device, group=None) -> float:
     return float(t.item())
 
 
+def set_p2p_timeout_ms(ms: int) -> int:
+    """How long a peer-memory gather waits for the other ranks before its watchdog fires (process-wide, default 30 s);
+    returns the previous value."""
+    from . import _lib
+    return int(_lib.load().sblk_set_p2p_timeout_ms(int(ms)))
+
+
 class P2PGather:
     """One-shot all-gather of every rank's fp32 output block over NVLink / NVSwitch peer memory (`sblk_p2p_gather_fwd`):
     the `DataParallel.gather` of the reference (train.py:114-115) for the one-process-per-GPU layout, as ONE kernel that
@@ -56,7 +63,13 @@ class P2PGather:
     peer that is one step ahead never overwrites a block that may still be read.
 
         g = P2PGather(local_elems, device)          # collective: every rank of `group` must call it
-        full = g(local_out)                          # -> fp32 [world * local_elems] view, valid until the call after next
+        full = g(local_out)                          # -> fp32 [world * local_elems] view of one of the two buffers
+
+    The returned view stays valid only until THIS rank's next call is enqueued: a peer may enter the call after next —
+    which stores into the same buffer — as soon as this rank's next gather kernel has published its flag, so every read
+    of a result has to be stream-ordered in front of the following call (bench.py copies / consumes it on the same
+    stream).  `close()` (collective) unmaps and frees the buffers; the object is also a context manager.  A rank that
+    does not show up within `sblk_set_p2p_timeout_ms` (default 30 s) traps the waiting kernel with watchdog code 0x0901.
     """
 
     def __init__(self, local_elems: int, device, group=None):
@@ -142,9 +155,18 @@ class P2PGather:
         self._owned = []
 
     def close(self):
+        if not self._owned and not self._opened:
+            return
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)
         self._release()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 class _DeviceBuffer:

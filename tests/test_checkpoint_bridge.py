@@ -74,3 +74,40 @@ def test_reference_checkpoint_round_trip(tmp_path):
     """)
     out = subprocess.run([sys.executable, "-c", reader], check=True, timeout=300, capture_output=True, text=True).stdout
     assert "reference loaded" in out
+
+
+def test_stand_in_type_follows_the_pickled_state(tmp_path):
+    """A class that cannot be imported becomes an nn.Module stand-in only if its pickled STATE is a module's
+    (`_parameters` / `_modules`); the reference's `transformer.optimizer.TransformerOptimizer` (a plain object holding
+    an optimizer and counters, SBL/transformer/optimizer.py) stays an attribute bag."""
+    pkg = tmp_path / "pkg" / "transformer"
+    pkg.mkdir(parents=True)
+    (pkg / "optimizer.py").write_text(textwrap.dedent("""
+        class TransformerOptimizer(object):
+            def __init__(self, k, d_model, warmup_steps):
+                self.k, self.init_lr, self.warmup_steps, self.step_num = k, d_model ** (-0.5), warmup_steps, 12
+    """))
+    (pkg / "tiny.py").write_text(textwrap.dedent("""
+        import torch
+        class Tiny(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.fc = torch.nn.Linear(3, 2)
+    """))
+    ckpt = tmp_path / "ck.tar"
+    writer = textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, {str(tmp_path / 'pkg')!r})
+        from transformer.optimizer import TransformerOptimizer
+        from transformer.tiny import Tiny
+        torch.manual_seed(0)
+        torch.save({{'epoch': 1, 'epochs_since_improvement': 0, 'loss': 1.0, 'model': Tiny(),
+                    'optimizer': TransformerOptimizer(0.2, 512, 4000)}}, {str(ckpt)!r})
+    """)
+    subprocess.run([sys.executable, "-c", writer], check=True, timeout=300)
+    from sbl_for_multilingual_lip_reading_b200 import checkpoint
+    obj = torch.load(str(ckpt), map_location="cpu", pickle_module=checkpoint._tolerant_pickle, weights_only=False)
+    assert isinstance(obj["model"], torch.nn.Module) and set(obj["model"].state_dict()) == {"fc.weight", "fc.bias"}
+    opt = obj["optimizer"]
+    assert not isinstance(opt, torch.nn.Module) and opt.step_num == 12 and opt.warmup_steps == 4000
+    assert set(checkpoint.load_reference_checkpoint(str(ckpt))["state_dict"]) == {"fc.weight", "fc.bias"}
