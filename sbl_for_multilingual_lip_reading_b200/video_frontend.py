@@ -252,7 +252,10 @@ class Lipreading(nn.Module):
             raise RuntimeError("Lipreading (libsblk) runs on a B200 CUDA device only; no CPU fallback exists")
         if x.dtype != torch.float32:
             x = x.float()
-        return x.contiguous()
+        x = x.contiguous()
+        if x.data_ptr() % 16:     # a contiguous view at an odd storage offset: the kernels read 16-byte vectors
+            x = x.clone()
+        return x
 
     def _frontend_chain(self, x, pk, feat_out, chain, prep=ops.prep_clip):
         """prep -> Conv3d stem -> ResNet-18 trunk -> average pool for the clips of `x`, on the current stream; writes

@@ -391,6 +391,18 @@ def test_fused_stem_through_the_modules_and_its_error_behaviour(frontend, dev):
     assert "crop offset" in _lib.last_error()
 
 
+def test_frontend_accepts_a_misaligned_input_view(frontend, dev):
+    """A contiguous clip tensor that starts at an odd storage offset (not 16-byte aligned) gives the same features."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(2, 5, seed=9).to(dev)
+    flat = torch.empty(x.numel() + 1, device=dev)
+    flat[1:].copy_(x.view(-1))
+    xv = flat[1:].view_as(x)
+    assert xv.is_contiguous() and xv.data_ptr() % 16 != 0
+    with torch.no_grad():
+        assert torch.equal(frontend(xv), frontend(x))
+
+
 def test_encoder_stack_rejects_unsupported_shapes(dev):
     from sbl_for_multilingual_lip_reading_b200 import ops, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
