@@ -308,6 +308,9 @@ class Encoder(nn.Module):
         lens = [int(v) for v in input_lengths]
         if len(lens) != n:
             raise RuntimeError(f"Encoder: {len(lens)} input_lengths for batch {n}")
+        if n == 0:   # empty batch: nothing to launch (the reference returns empty tensors as well)
+            out = padded_input.new_zeros((0, t, self.d_model), dtype=torch.float32)
+            return (out, [padded_input.new_zeros((0, t, t)) for _ in self.layer_stack]) if return_attns else (out,)
         if self.training:
             # model.train(): dropout active, every block a torch.autograd.Function backed by libsblk (training.py)
             self._check_train_config(t, return_attns)

@@ -441,6 +441,9 @@ class Lipreading(nn.Module):
         """reference :119-125.  model.train(): BatchNorm on batch statistics + autograd through libsblk
         (training.py); model.eval(): running statistics folded into the kernels, output detached from autograd."""
         frameLen = x.size(2)
+        if x.size(0) == 0:   # empty batch (the reference returns an empty tensor as well): nothing to launch
+            self._check_input(x)
+            return x.new_zeros((0, frameLen, self.inputDim), dtype=torch.float32)
         if self.training:
             from . import training
             feat = training.frontend_forward_train(self, self._check_input(x))

@@ -403,6 +403,18 @@ def test_frontend_accepts_a_misaligned_input_view(frontend, dev):
         assert torch.equal(frontend(xv), frontend(x))
 
 
+def test_empty_batch(frontend, encoder6, dev):
+    """N = 0 (e.g. the tail of a sharded loader): empty outputs of the reference's shapes, no launch."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    before = ops.launch_count()
+    with torch.no_grad():
+        f = frontend(torch.empty((0, 1, 29, 88, 88), device=dev))
+        out, = encoder6(f, [])
+        out2, attns = encoder6(f, [], return_attns=True)
+    assert f.shape == (0, 29, 512) and out.shape == (0, 29, 512) and out2.shape == (0, 29, 512)
+    assert len(attns) == 6 and ops.launch_count() == before
+
+
 def test_encoder_stack_rejects_unsupported_shapes(dev):
     from sbl_for_multilingual_lip_reading_b200 import ops, synth
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder

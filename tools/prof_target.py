@@ -87,6 +87,10 @@ if what == "stack":
     enc = Encoder(512, 6, 8, 64, 64, 512, 2048)
     enc.load_state_dict(synth.encoder_state_dict(2, 6))
     enc = enc.to(dev).eval()
+    # SBLK_PROF_STACK="cluster,groups_per_cluster" (e.g. "8,2": the form the pipelined plan runs on 32 SMs)
+    cfg = os.environ.get("SBLK_PROF_STACK")
+    if cfg:
+        enc.stack_cluster_size, enc.stack_groups_per_cluster = (int(v) for v in cfg.split(","))
     feat = torch.randn(32, 29, 512, generator=g).to(dev)
     with torch.no_grad():
         for _ in range(iters):
