@@ -127,6 +127,19 @@ int sblk_conv2d_igemm_fwd(const void* x_bf16, const void* w_packed_bf16, const f
                           const void* residual_bf16, void* out_bf16, int F, int H, int W, int Cin, int Cout,
                           int R, int S, int stride, int pad, int relu, int in_row_pitch, int in_frame_pitch,
                           void* stream);
+/* sblk_conv2d_igemm_fwd with a K-extension: out = act(conv(x, w) + conv1x1_stride2(x2, w2) + bias (+ residual)).
+ * x2 is bf16 NHWC [F,H2,W2,Cin2] (pitches as for x), w2 bf16 [Cout][Cin2]; the 1x1 / pad 0 / stride2 view of x2 must
+ * give the conv's own P x Q output grid.  Both contractions accumulate in ONE fp32 tensor-memory tile (the k-blocks
+ * of (x2, w2) follow the conv's own in the same TMA ring), so a BasicBlock with a downsample branch runs as
+ *   y   = sblk_conv2d_igemm_fwd(x, conv1, stride 2)                                  (256-wide pair tiles)
+ *   out = sblk_conv2d_igemm_ext_fwd(y, conv2, bias2 + bias_ds, x2 = x, w2 = w_ds)    (relu(bn2(conv2 y) + bn_ds(ds x)))
+ * with the branch never rounded to bf16 and no launch of its own.  Cout % 128 == 0 (CTA-pair kernel).
+ * replaces: BasicBlock.forward conv2/bn2, downsample(x), += residual, relu, transformer/video_frontend.py:35-41,68-72 */
+int sblk_conv2d_igemm_ext_fwd(const void* x_bf16, const void* w_packed_bf16, const float* bias,
+                              const void* residual_bf16, void* out_bf16, int F, int H, int W, int Cin, int Cout,
+                              int R, int S, int stride, int pad, int relu, int in_row_pitch, int in_frame_pitch,
+                              const void* x2_bf16, const void* w2_bf16, int H2, int W2, int Cin2, int stride2,
+                              int x2_row_pitch, int x2_frame_pitch, void* stream);
 /* BasicBlock head of layers 2-4 in one launch: out = relu(conv3x3_stride_s(x) + bias) and the downsample branch
  * out_ds = conv1x1_stride_s(x) + bias_ds.  The 1x1 conv reads exactly the centre-tap A tiles of the 3x3 conv, so
  * both share one pass over x (second TMEM accumulator).  w_ds_packed is [Cout][1][1][Cin]; Cout % 128 == 0.

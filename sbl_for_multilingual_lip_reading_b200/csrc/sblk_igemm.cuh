@@ -50,6 +50,13 @@ struct IgemmParams {
   // 16-bit float format of A, B, residual and out_bf16: 0 = bf16 (every conv), 1 = IEEE fp16 (the encoder's linear
   // layers, sblk_common.cuh "enc16"); both run as tcgen05 kind::f16 at the same rate
   int fp16;
+  // CTA-pair im2col kernel only: K-extension.  After the conv's own taps*cblocks k-blocks, ext_cblocks more k-blocks
+  // are accumulated into the SAME tile from a second activation tensor (tmA2: 1x1 / pad 0 / stride ext_stride im2col
+  // view with the same P x Q output grid) and a second filter (tmB2: [N][ext_cblocks*64]).  This is how the 1x1
+  // downsample branch of a BasicBlock is folded into the block's conv2: relu(conv2(y) + ds(x) + bias) in one fp32
+  // accumulator, no bf16 round trip of the branch, no launch of its own.
+  int ext_cblocks = 0;
+  int ext_stride = 1;
 };
 
 template <int BLOCK_N, bool DUAL = false>

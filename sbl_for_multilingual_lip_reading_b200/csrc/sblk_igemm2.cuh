@@ -151,7 +151,8 @@ struct Igemm2Cfg {
 template <int BLOCK_N, bool IM2COL, bool DUAL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Igemm2Cfg<BLOCK_N, DUAL>::THREADS, 1)
 igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-              const __grid_constant__ CUtensorMap tmB2, const IgemmParams p) {
+              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmA2,
+              const IgemmParams p) {
   using Cfg = Igemm2Cfg<BLOCK_N, DUAL>;
   static_assert(BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
   static_assert(!DUAL || (IM2COL && BLOCK_N == 128), "DUAL needs im2col and BLOCK_N = 128");
@@ -178,7 +179,9 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n_tiles = p.N / BLOCK_N;
   const int m_pairs = (p.M + Cfg::PAIR_M - 1) / Cfg::PAIR_M;
   const int num_tiles = m_pairs * n_tiles;
-  const int num_kb = p.taps_r * p.taps_s * p.cblocks;
+  const int num_kb_main = p.taps_r * p.taps_s * p.cblocks;
+  // K-extension (IgemmParams::ext_cblocks): k-blocks of a second (activation, filter) pair behind the conv's own
+  const int num_kb = num_kb_main + ((IM2COL && !DUAL) ? p.ext_cblocks : 0);
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
   const int nstages = p.staged ? STAGES - 1 : STAGES;
@@ -186,7 +189,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (DUAL) tma_prefetch_desc(&tmB2);
+    if (DUAL || (IM2COL && p.ext_cblocks > 0)) tma_prefetch_desc(&tmB2);
+    if (IM2COL && !DUAL && p.ext_cblocks > 0) tma_prefetch_desc(&tmA2);
 #pragma unroll
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);    // used in the leader only: one expect_tx arrive covering both CTAs' bytes
@@ -224,7 +228,7 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       const int n_blk = tile - m_blk * n_tiles;
       const int m0 = m_blk * Cfg::PAIR_M + static_cast<int>(rank) * Cfg::BLOCK_M;
       const int n0 = n_blk * BLOCK_N + static_cast<int>(rank) * Cfg::BH;
-      int img = 0, base_w = 0, base_h = 0;
+      int img = 0, base_w = 0, base_h = 0, ext_w = 0, ext_h = 0;
       if (IM2COL) {
         const int pq = p.P * p.Q;
         img = m0 / pq;
@@ -233,6 +237,8 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int qw = rem - ph * p.Q;
         base_w = qw * p.stride - p.pad;
         base_h = ph * p.stride - p.pad;
+        ext_w = qw * p.ext_stride;   // the extension is a 1x1 / pad 0 view onto the same output grid
+        ext_h = ph * p.ext_stride;
       }
       int cb = 0, r = 0, s = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
@@ -240,18 +246,22 @@ igemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
         uint8_t* b_dst = a_dst + Cfg::A_BYTES;
         const bool centre = DUAL && r == p.taps_r / 2 && s == p.taps_s / 2;
+        const bool ext = IM2COL && !DUAL && kb >= num_kb_main;
         const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's barrier
         if (elect_one()) {
           if (leader)
             mbar_arrive_expect_tx(&full_bar[stage], 2u * (Cfg::A_BYTES + Cfg::B_BYTES + (centre ? Cfg::B_BYTES : 0)));
           if (centre) tma2_load_2d(b_dst + Cfg::B_BYTES, &tmB2, bar, cb * 64, n0);
-          if (IM2COL) {
+          if (ext) {
+            tma2_load_im2col_4d(a_dst, &tmA2, bar, (kb - num_kb_main) * 64, ext_w, ext_h, img, 0, 0);
+            tma2_load_2d(b_dst, &tmB2, bar, (kb - num_kb_main) * 64, n0);
+          } else if (IM2COL) {
             tma2_load_im2col_4d(a_dst, &tmA, bar, cb * 64, base_w, base_h, img, static_cast<uint16_t>(s),
                                 static_cast<uint16_t>(r));
           } else {
             tma2_load_2d(a_dst, &tmA, bar, kb * 64, m0);
           }
-          tma2_load_2d(b_dst, &tmB, bar, kb * 64, n0);
+          if (!ext) tma2_load_2d(b_dst, &tmB, bar, kb * 64, n0);
         }
         __syncwarp();
         if (++cb == p.cblocks) {

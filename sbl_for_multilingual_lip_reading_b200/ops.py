@@ -405,20 +405,13 @@ def conv2d_dual(x, wp, bias, wp_ds, bias_ds, stride=2, relu=True, flat_ws=None):
     return out, out_ds
 
 
-def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
-    """x bf16 NHWC [F,H,W,Cin] (or FlatActs), wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout]."""
+def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None, ext=None):
+    """x bf16 NHWC [F,H,W,Cin] (or FlatActs), wp bf16 [Cout,R,S,Cin] -> bf16 NHWC [F,P,Q,Cout].
+    ext = (x2, w2, stride2): K-extension (sblk_conv2d_igemm_ext_fwd) — the 1x1 / stride2 conv of x2 (NHWC or FlatActs)
+    with w2 [Cout,1,1,Cin2] is accumulated into the same fp32 tile before bias / residual / ReLU: a BasicBlock's
+    downsample branch folded into its conv2 (pass bias = folded bn2 shift + folded downsample shift)."""
     _req(wp, BF16, "wp"); _req(bias, F32, "bias"); _req(residual, BF16, "residual")
-    if isinstance(x, FlatActs):
-        _req(x.data, BF16, "x")
-        f, h, w, cin = x.f, x.h, x.w, x.c
-        xptr = x.data.data_ptr() + (w + 3) * cin * 2           # pixel (0,0,0)
-        row_pitch, frame_pitch = w + 2, (h + 1) * (w + 2)
-        x_elems = x.data.numel()
-    else:
-        _req(x, BF16, "x")
-        f, h, w, cin = x.shape
-        xptr, row_pitch, frame_pitch = x.data_ptr(), 0, 0
-        x_elems = x.numel()
+    xptr, f, h, w, cin, row_pitch, frame_pitch, x_elems = _conv_input(x)
     cout, r, s, cin2 = wp.shape
     if cin2 != cin:
         raise RuntimeError(f"conv2d: Cin mismatch {cin} vs {cin2}")
@@ -430,6 +423,20 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None):
     _req(out, BF16, "out")
     if residual is not None and residual.numel() != out.numel():
         raise RuntimeError("conv2d: residual shape mismatch")
+    if ext is not None:
+        x2, w2, stride2 = ext
+        _req(w2, BF16, "ext w2")
+        x2ptr, f2, h2, w2_, c2, rp2, fp2, x2_elems = _conv_input(x2)
+        if f2 != f or tuple(w2.shape) != (cout, 1, 1, c2):
+            raise RuntimeError(f"conv2d: extension shapes F={f2} w2={tuple(w2.shape)} do not match F={f} Cout={cout} Cin2={c2}")
+        if ((h2 - 1) // stride2 + 1, (w2_ - 1) // stride2 + 1) != (p, q):
+            raise RuntimeError("conv2d: the extension's output grid does not match the conv's")
+        _call("sblk_conv2d_igemm_ext_fwd", f"conv{r}x{s}+ds H={h} {cin}->{cout} s{stride}",
+              2 * f * p * q * cout * (r * s * cin + c2),
+              2 * (x_elems + x2_elems + wp.numel() + w2.numel() + out.numel() + (0 if residual is None else residual.numel())),
+              xptr, _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout, r, s, stride, pad, 1 if relu else 0,
+              row_pitch, frame_pitch, x2ptr, _p(w2), h2, w2_, c2, stride2, rp2, fp2, _stream())
+        return out
     _call("sblk_conv2d_igemm_fwd", f"conv{r}x{s} H={h} {cin}->{cout} s{stride}", 2 * f * p * q * cout * r * s * cin,
           2 * (x_elems + wp.numel() + out.numel() + (0 if residual is None else residual.numel())),
           xptr, _p(wp), _p(bias), _p(residual), _p(out), f, h, w, cin, cout, r, s, stride, pad, 1 if relu else 0,

@@ -132,6 +132,12 @@ class Lipreading(nn.Module):
         # uint8 path keeps the separate prep launch unless fuse_prep_u8 is set
         self.fuse_prep = True
         self.fuse_prep_u8 = False
+        # eval path, layers 3-4: the block head's 1x1 downsample branch is folded into the block's conv2 as a K-extension
+        # (sblk_conv2d_igemm_ext_fwd): conv1 then runs as a plain stride-2 conv on 256-wide pair tiles (the dual kernel
+        # is limited to 128-wide tiles by its second accumulator, i.e. 1.5x the operand bytes per FLOP of a path that is
+        # bound by L2->SM operand delivery), and the branch is added in fp32 inside conv2's accumulator instead of
+        # being rounded to bf16 and read back as a residual.  False = the dual head kernel of round 1.
+        self.fold_downsample = True
         self._overlap = None
         # (scale | None, out_bf16) set by the same plan: the average pool writes mean * scale as bf16 straight into the
         # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
@@ -162,6 +168,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("_overlap", None)
         self.__dict__.setdefault("fuse_prep", True)
         self.__dict__.setdefault("fuse_prep_u8", False)
+        self.__dict__.setdefault("fold_downsample", True)
         self.__dict__.setdefault("_tail", None)
 
     def _initialize_weights(self):  # same as reference :127-157
@@ -220,6 +227,8 @@ class Lipreading(nn.Module):
                 w1, b1 = fold(blk.conv1, blk.bn1)
                 w2, b2 = fold(blk.conv2, blk.bn2)
                 ds = fold(blk.downsample[0], blk.downsample[1]) if blk.downsample is not None else None
+                if ds is not None:   # (filter, shift, bn2 shift + downsample shift: bias of the folded form)
+                    ds = (ds[0], ds[1], (b2 + ds[1]).contiguous())
                 # layer1 / layer2 run on the zero-haloed flat layout (shifted-window kernels): [C, 10*C] packing
                 flat = layer is self.resnet18.layer1 or layer is self.resnet18.layer2
                 if flat and blk.stride == 1:
@@ -327,6 +336,11 @@ class Lipreading(nn.Module):
                     y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True,
                                              flat_ws=self._flat_workspace(a, w1.shape[0], stride, chain))
                     a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res)
+                    continue
+                if self.fold_downsample:
+                    # y = relu(bn1(conv1 x)); out = relu(bn2(conv2 y) + bn_ds(ds x)) in one fp32 accumulator
+                    y = ops.conv2d(a, w1, b1, stride=stride, relu=True)
+                    a = ops.conv2d(y, w2, ds[2], stride=1, relu=True, ext=(a, ds[0], stride))
                     continue
                 y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
             else:

@@ -168,6 +168,71 @@ def test_oracle_basic_block_chain(frontend, dev):
                 bi += 1
 
 
+@pytest.mark.parametrize("f,h,cin,cout,flat_in", [(5, 11, 128, 256, True), (29, 11, 128, 256, False),
+                                                  (7, 6, 256, 512, False), (3, 22, 64, 128, True)])
+def test_conv2d_k_extension_folds_the_downsample_branch(dev, f, h, cin, cout, flat_in):
+    """sblk_conv2d_igemm_ext_fwd: relu(conv3x3(y) + conv1x1_s2(x) + bias) in one accumulator (BasicBlock conv2 + the
+    downsample branch, video_frontend.py:35-41,68-72) against a torch fp32 reference of the same bf16 operands, and
+    against the unfused launches (which round the branch to bf16 first).  Ragged M (last pair tile partly empty),
+    dense and flat (pitched) block inputs, 128- and 256-wide tiles."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(f * 1000 + h)
+    bf = torch.bfloat16
+    p = (h - 1) // 2 + 1
+    x = torch.randn(f, h, h, cin, generator=g).to(bf)
+    y = torch.randn(f, p, p, cout, generator=g).to(bf)
+    w2 = (torch.randn(cout, 3, 3, cout, generator=g) / (3 * cout ** 0.5)).to(bf)
+    wd = (torch.randn(cout, 1, 1, cin, generator=g) / cin ** 0.5).to(bf)
+    bias = torch.randn(cout, generator=g)
+    ref = torch.nn.functional.conv2d(y.float().permute(0, 3, 1, 2), w2.float().permute(0, 3, 1, 2), padding=1)
+    ref = ref + torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), wd.float().permute(0, 3, 1, 2), stride=2)
+    ref = torch.relu(ref + bias.view(1, -1, 1, 1)).permute(0, 2, 3, 1)
+    xd = x.to(dev)
+    if flat_in:
+        xin = ops.FlatActs(torch.zeros(ops.flat_rows(f, h, h), cin, dtype=bf, device=dev), f, h, h)
+        xin.data.view(-1)[:] = 0
+        rows = ((torch.arange(f).view(-1, 1, 1) * (h + 1) + 1 + torch.arange(h).view(1, -1, 1)) * (h + 2) + 1 +
+                torch.arange(h).view(1, 1, -1)).reshape(-1).to(dev)
+        xin.data[rows] = xd.reshape(-1, cin)
+    else:
+        xin = xd
+    yd, w2d, wdd, bd = y.to(dev), w2.to(dev), wd.to(dev), bias.to(dev)
+    got = ops.conv2d(yd, w2d, bd, stride=1, relu=True, ext=(xin, wdd, 2))
+    torch.cuda.synchronize()
+    assert tuple(got.shape) == (f, p, p, cout)
+    assert rel_fro(got, ref) < 4e-3          # one bf16 rounding of the output
+    zero = torch.zeros(cout, device=dev)
+    res = ops.conv2d(xin, wdd, zero, stride=2, relu=False)
+    unfused = ops.conv2d(yd, w2d, bd, stride=1, relu=True, residual=res)
+    assert rel_fro(got, unfused) < 6e-3      # the unfused form rounds the branch to bf16 before adding it
+    # the extension must not disturb the plain conv: zero extension filter == no extension, bit for bit
+    plain = ops.conv2d(yd, w2d, bd, stride=1, relu=True)
+    got0 = ops.conv2d(yd, w2d, bd, stride=1, relu=True, ext=(xin, torch.zeros_like(wdd), 2))
+    assert torch.equal(plain, got0)
+
+
+def test_fold_downsample_matches_dual_heads(frontend, dev):
+    """Lipreading.fold_downsample (layers 3-4: conv1 on 256-wide tiles, branch folded into conv2) against the dual-head
+    path of round 1 and the oracle."""
+    from oracle import visual_encoder_oracle as O
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    x = synth.synthetic_clips(2, 7, seed=21)
+    sd = synth.frontend_state_dict(1, prefix="visual_frontend.")
+    old = frontend.fold_downsample
+    try:
+        with torch.no_grad():
+            frontend.fold_downsample = True
+            a = frontend._frontend_forward(x.to(dev))
+            frontend.fold_downsample = False
+            b = frontend._frontend_forward(x.to(dev))
+            ref = O.lipreading_forward(x, sd, "visual_frontend.")
+    finally:
+        frontend.fold_downsample = old
+    assert rel_fro(a, b) < 4e-3
+    assert rel_fro(a.view(-1, 512), ref.view(-1, 512)) < REL_TOL
+    assert rel_fro(a.view(-1, 512), ref.view(-1, 512)) <= rel_fro(b.view(-1, 512), ref.view(-1, 512)) * 1.1
+
+
 # ------------------------------------------------------------------ edge cases and error behaviour
 def test_dropout_always_on_like_reference(dev):
     """Reference quirk (video_frontend.py:122): dropout(0.5) is active in eval mode; same torch RNG call."""
