@@ -81,6 +81,18 @@ if what == "dual2":
     bz = torch.zeros(128, device=dev)
     for _ in range(iters):
         ops.conv2d_dual(x, wa, bz, wb, bz, stride=2)
+if what in ("fold3", "fold4"):
+    # residual block head with the downsample branch folded into conv2 (layer3.0: 11x11x128 -> 6x6x256,
+    # layer4.0: 6x6x256 -> 3x3x512): conv1 3x3/s2 on 256-wide pair tiles, then conv2 + K-extension
+    cin, cout, h = (128, 256, 11) if what == "fold3" else (256, 512, 6)
+    x = torch.randn(928, h, h, cin, generator=g).to(bf).to(dev)
+    w1 = (torch.randn(cout, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
+    w2 = (torch.randn(cout, 3, 3, cout, generator=g) / (9 * cout) ** 0.5).to(bf).to(dev)
+    wd = (torch.randn(cout, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev)
+    bz = torch.zeros(cout, device=dev)
+    for _ in range(iters):
+        y = ops.conv2d(x, w1, bz, stride=2)
+        ops.conv2d(y, w2, bz, stride=1, ext=(x, wd, 2))
 if what == "stack":
     # the one-launch encoder stack alone, BASELINE configs[1] shape
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
