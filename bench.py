@@ -465,6 +465,15 @@ def run_b200_arm(args):
             smp.stop()
         return sharding.max_over_ranks(dt, dev)
 
+    def cool_down():
+        # every burst leg (device-timed, e2e, e2e_u8, latency) starts from an idle GPU: ~100 ms of back-to-back load is
+        # enough to pull this box into its power cap (the regime the `sustained` key reports), and a leg that merely
+        # runs later in the script would otherwise be measured in a different clock regime than the one before it
+        barrier()
+        time.sleep(args.cool_down_seconds)
+        barrier()
+
+    cool_down()
     e2e_s = e2e_time(plan, main.host_pool, sampler)
     e2e_value = world * B * args.steps / e2e_s
     checksum = float(main.out_host[(args.steps - 1) % 2].double().abs().mean())  # the D2H result is really read
@@ -476,6 +485,7 @@ def run_b200_arm(args):
     if not args.no_u8:
         plan8 = main.make_plan(u8_input=(T, 96, 96))
         host_u8 = [synth.synthetic_u8_clips(B, T, seed=300 + 17 * rank + i).pin_memory() for i in range(main.pool_n)]
+        cool_down()
         u8_s = e2e_time(plan8, host_u8)
         e2e_u8 = {"value": world * B * args.steps / u8_s, "unit": UNIT, "h2d_bytes_per_step": B * T * 96 * 96,
                   "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * u8_s / args.steps,
@@ -488,6 +498,7 @@ def run_b200_arm(args):
     latency = None
     if pipelined:
         lat_n = min(args.steps, 20)
+        cool_down()
         lat_ms = main.time_device(lat_n, 3, plan=main.plan_lat, defer=False)
         latency = {"ms_per_step": lat_ms, "clips_per_s": world * B / (lat_ms * 1e-3), "steps": lat_n,
                    "frac_of_bf16_peak": B / (lat_ms * 1e-3) * fpc / 1e12 / float(peaks["bf16_tflops"]),
@@ -549,6 +560,7 @@ def run_b200_arm(args):
     config2 = None
     if not args.no_config2 and (B, T) != (8, 40):
         c2 = Shape(ctx, 8, 40)
+        cool_down()      # (this leg follows the sustained run)
         c2_ms = c2.time_device(args.steps, args.warmup)
         c2_lat = c2.time_device(min(args.steps, 20), 3, plan=c2.plan_lat, defer=False) if c2.pipelined else None
         f2 = flops_per_clip(40, L)
@@ -679,7 +691,7 @@ def run_b200_arm(args):
             cfg["config2"] = config2
         e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": B * T * 512 * 4, "ms_per_step": 1e3 * e2e_s / args.steps,
-               "regime": "burst: measured right after the device-timed steps, before the sustained run (see `sustained` for the power-capped regime)",
+               "regime": "burst: K steps from an idle GPU (--cool-down-seconds pause after the device-timed leg), before the sustained run (see `sustained` for the power-capped regime)",
                "timing": "wall clock, synchronize on both sides, double-buffered H2D/compute/D2H",
                "result_checksum": checksum,
                "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_ceiling_clips_per_s": h2d_ceiling_clips,
@@ -977,6 +989,8 @@ def main():
     ap.add_argument("--no-u8", action="store_true", help="skip the fused uint8-input end-to-end measurement (e2e_u8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config2", action="store_true", help="skip the BASELINE configs[2] (8 clips x 40 frames per GPU) leg")
+    ap.add_argument("--cool-down-seconds", type=float, default=1.0,
+                    help="idle pause in front of every burst leg after the first (e2e, e2e_u8, latency)")
     ap.add_argument("--sustained-seconds", type=float, default=2.5,
                     help="length of the back-to-back sustained-regime run (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

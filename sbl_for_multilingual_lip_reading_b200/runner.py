@@ -98,6 +98,36 @@ class VisualEncoderPlan:
         out, = self.encoder(feat, self.lengths)
         return out
 
+    def _forward_fused_tail(self, s):
+        """encoder(frontend(x[s])) with the dropout factor drawn off the critical path and the pooling launch writing the
+        encoder's operand (capture-time only; see _capture)."""
+        fe, enc = self.frontend, self.encoder
+        main = torch.cuda.current_stream()
+        scale, join = None, None
+        if getattr(fe, "always_on_dropout", True):
+            fork, drawn = torch.cuda.Event(), torch.cuda.Event()
+            fork.record(main)
+            self._tail_stream.wait_event(fork)
+            with torch.cuda.stream(self._tail_stream):
+                scale = torch.nn.functional.dropout(self._ones, p=0.5)
+                drawn.record(self._tail_stream)
+            join = lambda: main.wait_event(drawn)   # noqa: E731  (called right before the pooling launch)
+        saved = (fe._tail, enc._x16_override)
+        try:
+            fe._tail = (scale, self.feat16[s], join)
+            if self.u8_input is not None:
+                _, h0, w0 = self.u8_input
+                f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
+            else:
+                f = fe(self.x[s])
+            del f   # unwritten: the pooling launch wrote the 16-bit features into feat16[s]
+            fe._tail = None
+            enc._x16_override = self.feat16[s]
+            out, = enc(self.feat, self.lengths)
+        finally:
+            fe._tail, enc._x16_override = saved
+        return out
+
     def _capture(self):
         torch.cuda.synchronize(self.device)
         with torch.no_grad():
@@ -114,11 +144,29 @@ class VisualEncoderPlan:
             # One private memory pool PER graph: with a shared pool the static output of one slot may alias an
             # intermediate buffer of the other slot's graph, and submit_host lets the device->host copy of slot s overlap
             # the replay of slot s^1 (a few hundred MB per pool; HBM is not the constraint here).
+            fe, enc = self.frontend, self.encoder
+            # Fused tail (same as the pipelined plan): the always-on dropout factor of Lipreading.forward (reference :122)
+            # is drawn on a side stream while the trunk runs and applied by the pooling launch, which writes the encoder's
+            # 16-bit operand directly — no dropout / cast launches between the last conv and the encoder stack.
+            # Bit-identical to the module path (same generator draw, same single rounding).
+            fused_tail = (hasattr(fe, "_tail") and hasattr(enc, "_x16_override") and hasattr(enc, "_use_fused_stack")
+                          and getattr(fe, "parallel_chains", 1) == 1 and not fe.training and not enc.training
+                          and enc._use_fused_stack(self.n, self.t, False))
+            if fused_tail:
+                dev = self.device
+                self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=ops.enc16_dtype(), device=dev)
+                               for _ in range(self.slots)]
+                self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
+                self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
+                self._tail_stream = torch.cuda.Stream(device=dev)
             for s in range(self.slots):
                 g = torch.cuda.CUDAGraph()
                 before = ops.launch_count()
                 with torch.cuda.graph(g, stream=self.compute):
-                    self.out[s] = self._forward_eager(self.x[s])
+                    if fused_tail:
+                        self.out[s] = self._forward_fused_tail(s)
+                    else:
+                        self.out[s] = self._forward_eager(self.x[s])
                 self.launches_per_forward = ops.launch_count() - before
                 self.graphs[s] = g
         torch.cuda.synchronize(self.device)

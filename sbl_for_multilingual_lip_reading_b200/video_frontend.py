@@ -350,6 +350,8 @@ class Lipreading(nn.Module):
             end_head()
         tail = self._tail if chain == 0 else None
         if tail is not None:
+            if len(tail) > 2 and tail[2] is not None:
+                tail[2]()   # the plan's side stream has drawn the dropout factor (VisualEncoderPlan._forward_fused_tail)
             ops.avgpool(a, want_f32=False, out_bf16=tail[1], scale=tail[0], enc16=True)   # feat_out stays unwritten (plan-owned path)
         else:
             ops.avgpool(a, out_f32=feat_out)

@@ -646,6 +646,69 @@ def test_pipelined_plan_is_bit_identical_to_eager_modules(frontend, encoder6, de
     assert encoder6.stack_cluster_size == 0 and encoder6._resident_counter is None and frontend._overlap is None
 
 
+@pytest.mark.parametrize("n,t,lens", [(32, 29, None), (8, 40, None), (5, 29, [29, 11, 29, 3, 20])])
+def test_plain_plan_with_fused_tail_is_bit_identical_to_eager_modules(frontend, encoder6, dev, n, t, lens):
+    """runner.VisualEncoderPlan (one batch per replay) with its fused tail — dropout factor drawn on a side stream, the
+    pooling launch writes the encoder's 16-bit operand — returns exactly what the drop-in modules return, through
+    forward_device and through submit_host, and leaves the modules' hooks untouched."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.runner import VisualEncoderPlan
+    lens = [t] * n if lens is None else lens
+    xs = [synth.synthetic_clips(n, t, seed=70 + i) for i in range(3)]
+    with torch.no_grad():
+        want = [encoder6(frontend(x.to(dev)), lens)[0].cpu() for x in xs]
+    plan = VisualEncoderPlan(frontend, encoder6, n, t, device=dev, lengths=lens)
+    try:
+        assert hasattr(plan, "feat16")          # the fused tail is in use for these shapes
+        for i, x in enumerate(xs):
+            with torch.cuda.stream(plan.compute):
+                plan.x[i % 2].copy_(x.to(dev))
+                out = plan.forward_device(i % 2)
+            plan.compute.synchronize()
+            assert torch.equal(out.cpu(), want[i]), f"device path, batch {i}"
+        hin = [x.pin_memory() for x in xs]
+        hout = [torch.empty((n, t, 512), dtype=torch.float32).pin_memory() for _ in xs]
+        for i in range(len(xs)):
+            plan.submit_host(hin[i], hout[i])
+        plan.synchronize()
+        for i in range(len(xs)):
+            assert torch.equal(hout[i], want[i]), f"host path, batch {i}"
+    finally:
+        plan.close()
+    assert frontend._tail is None and encoder6._x16_override is None
+
+
+def test_plain_plan_draws_a_fresh_dropout_mask_every_replay(encoder6, dev):
+    """The reference's always-on dropout (video_frontend.py:122) inside the plain plan's fused tail: a new mask per
+    replay, about half of the features zeroed."""
+    from sbl_for_multilingual_lip_reading_b200 import synth
+    from sbl_for_multilingual_lip_reading_b200.runner import VisualEncoderPlan
+    from sbl_for_multilingual_lip_reading_b200.video_frontend import Lipreading
+    fe = Lipreading()
+    fe.load_state_dict(synth.frontend_state_dict(1))
+    fe = fe.to(dev).eval()
+    assert fe.always_on_dropout
+    x = synth.synthetic_clips(4, 29, seed=9).to(dev)
+    plan = VisualEncoderPlan(fe, encoder6, 4, 29, device=dev)
+    outs = []
+    try:
+        with torch.cuda.stream(plan.compute):
+            for i in range(3):
+                plan.x[i % 2].copy_(x)
+                outs.append(plan.forward_device(i % 2).clone())
+            zero_frac = (plan.feat16[0] == 0).float().mean().item()
+        plan.compute.synchronize()
+    finally:
+        plan.close()
+    fe.always_on_dropout = False
+    with torch.no_grad():
+        clean, = encoder6(fe(x), [29] * 4)
+    assert 0.45 < zero_frac < 0.55
+    for o in outs:
+        assert torch.isfinite(o).all() and not torch.equal(o, clean)
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+
+
 def test_avgpool_with_dropout_factor_matches_pool_then_dropout(dev):
     """sblk_avgpool_scale_fwd: pooling times the pre-drawn dropout factor (F.dropout(ones) under the same seed draws the
     same Philox mask as F.dropout(features)) is bit-identical to pooling followed by the reference's always-on
