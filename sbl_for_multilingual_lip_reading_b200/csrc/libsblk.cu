@@ -1019,6 +1019,13 @@ int sblk_avgpool_scale_fwd(const void* x, const float* scale, float* out_f32, vo
   if ((reinterpret_cast<uintptr_t>(x) & 3u) || (scale && (reinterpret_cast<uintptr_t>(scale) & 7u)) ||
       (out_f32 && (reinterpret_cast<uintptr_t>(out_f32) & 7u)) || (reinterpret_cast<uintptr_t>(out_bf16) & 3u))
     return fail(-1, "sblk_avgpool_fwd: misaligned pointer");
+  if (C % 8 == 0 && aligned16(x) && (!scale || aligned16(scale)) && (!out_f32 || aligned16(out_f32)) &&
+      (!out_bf16 || aligned16(out_bf16))) {
+    const long long items8 = static_cast<long long>(F) * (C / 8);
+    return launch(sblk::avgpool8_kernel, dim3(elementwise_grid(items8, 256, sms)), dim3(256), 0,
+                  static_cast<cudaStream_t>(stream), true, "avgpool8_kernel", static_cast<const uint4*>(x), scale,
+                  out_f32, out_bf16, F, HW, C / 8, (out16_enc && SBLK_ENC_FP16) ? 1 : 0);
+  }
   const long long items = static_cast<long long>(F) * (C / 2);
   return launch(sblk::avgpool_kernel, dim3(elementwise_grid(items, 256, sms)), dim3(256), 0,
                 static_cast<cudaStream_t>(stream), false, "avgpool_kernel", static_cast<const __nv_bfloat16*>(x), scale,

@@ -331,6 +331,56 @@ avgpool_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ sc
   }
 }
 
+// Same pooling, one thread per (frame, 8 channels): 16-byte loads (nine of them in flight per thread for the 3x3 maps
+// of layer 4), 16/32-byte stores; the per-channel summation order is that of avgpool_kernel (bit-identical).
+// PDL-enabled: it is the launch between the last conv and the encoder stack.
+__global__ void __launch_bounds__(256)
+avgpool8_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, float* __restrict__ out_f32,
+                void* __restrict__ out_16, int F, int HW, int C8, int out_fp16) {
+  grid_dep_launch();
+  grid_dep_wait();
+  const long long total = static_cast<long long>(F) * C8;
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const long long f = i / C8;
+    const uint4* src = x + f * HW * C8 + c8;
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.0f;
+#pragma unroll 9
+    for (int q = 0; q < HW; ++q) {
+      const uint4 u = __ldg(src + static_cast<long long>(q) * C8);
+      a[0] += bf16_lo(u.x); a[1] += bf16_hi(u.x); a[2] += bf16_lo(u.y); a[3] += bf16_hi(u.y);
+      a[4] += bf16_lo(u.z); a[5] += bf16_hi(u.z); a[6] += bf16_lo(u.w); a[7] += bf16_hi(u.w);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] *= inv;
+    if (scale != nullptr) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * i);
+      const float4 m1 = __ldg(reinterpret_cast<const float4*>(scale) + 2 * i + 1);
+      a[0] *= m0.x; a[1] *= m0.y; a[2] *= m0.z; a[3] *= m0.w;
+      a[4] *= m1.x; a[5] *= m1.y; a[6] *= m1.z; a[7] *= m1.w;
+    }
+    if (out_f32 != nullptr) {
+      reinterpret_cast<float4*>(out_f32)[2 * i] = make_float4(a[0], a[1], a[2], a[3]);
+      reinterpret_cast<float4*>(out_f32)[2 * i + 1] = make_float4(a[4], a[5], a[6], a[7]);
+    }
+    if (out_16 != nullptr) {
+      uint4 o;
+      if (out_fp16) {
+        o.x = pack_f16x2(a[0], a[1]); o.y = pack_f16x2(a[2], a[3]);
+        o.z = pack_f16x2(a[4], a[5]); o.w = pack_f16x2(a[6], a[7]);
+      } else {
+        o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+        o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+      }
+      reinterpret_cast<uint4*>(out_16)[i] = o;
+    }
+  }
+}
+
 // --------------------------------------------------------------------------------------------
 // y = LayerNorm(x + residual) * gamma + beta  (+ pe[t])  (* pad_mask[b,t]),  D = 512, eps = 1e-5.
 // Reference: attention.py:58, module.py:51, encoder.py:53-55 (+PE), encoder.py:86,89 (mask).
