@@ -117,6 +117,14 @@ long long sblk_flat_rows(int F, int H, int W);
  * replaces: the stride-1 convs of ResNet layer1 and layer2, transformer/video_frontend.py:10-12,28-41 */
 int sblk_flatconv3x3_fwd(const void* x_flat, const void* w_packed_bf16, const float* bias, const void* residual_flat,
                          void* out_flat, int F, int H, int W, int C, int relu, void* stream);
+/* Same conv with the tile order chosen by the caller: reverse != 0 makes every CTA pair walk its contiguous tile range
+ * from the last tile to the first.  Consecutive convs of a stage alternate the direction, so that the rows a pair wrote
+ * (and read as residual) last in one conv — the ones most likely still resident in L2 — are the first it reads in the
+ * next (a layer-1 tensor is 65.6 MB at the BASELINE batch: a conv with residual touches 197 MB against 126 MB of L2).
+ * Bit-identical to sblk_flatconv3x3_fwd. */
+int sblk_flatconv3x3_dir_fwd(const void* x_flat, const void* w_packed_bf16, const float* bias,
+                             const void* residual_flat, void* out_flat, int F, int H, int W, int C, int relu,
+                             int reverse, void* stream);
 /* Implicit-GEMM Conv2d (3x3 pad 1 or 1x1 pad 0, stride 1 or 2) over bf16 NHWC [F,H,W,Cin] with folded BN:
  * out = act(conv(x, w) + bias (+ residual)), bf16 NHWC [F,P,Q,Cout].  Cin % 64 == 0, Cout % 64 == 0.
  * in_row_pitch / in_frame_pitch (pixels, 0 = dense) let x point at pixel (0,0,0) of a pitched layout such as the

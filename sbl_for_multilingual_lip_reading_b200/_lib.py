@@ -56,6 +56,7 @@ SIGNATURES = {
     "sblk_stem_fused_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_flat_rows": (_ll, [_i, _i, _i]),
     "sblk_flatconv3x3_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "sblk_flatconv3x3_dir_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_conv2d_igemm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "sblk_conv2d_igemm_ext_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                        _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -592,7 +592,7 @@ long long sblk_flat_rows(int F, int H, int W) {
 extern "C++" {
 template <int CB>
 static int launch_flatconv2(const void* x, const void* wp, const float* bias, const void* residual, void* out,
-                            long long rows, int H, int W, int relu, int sms, cudaStream_t stream) {
+                            long long rows, int H, int W, int relu, int sms, cudaStream_t stream, int reverse = 0) {
   using Cfg = sblk::Fc2Cfg<CB>;
   constexpr int C = Cfg::C;
   int rc;
@@ -622,6 +622,7 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
   p.num_tiles = (p.m_total + 255) / 256;
   p.H = H; p.W = W; p.relu = relu; p.has_res = residual ? 1 : 0;
   p.bias = bias;
+  p.reverse = reverse ? 1 : 0;
   const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
   p.dbg = nullptr;
   {
@@ -656,6 +657,11 @@ static int launch_flatconv2(const void* x, const void* wp, const float* bias, co
 
 int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
                          int H, int W, int C, int relu, void* stream) {
+  return sblk_flatconv3x3_dir_fwd(x, wp, bias, residual, out, F, H, W, C, relu, 0, stream);
+}
+
+int sblk_flatconv3x3_dir_fwd(const void* x, const void* wp, const float* bias, const void* residual, void* out, int F,
+                             int H, int W, int C, int relu, int reverse, void* stream) {
 #ifdef SBLK_DEBUG
   using namespace sblk::fc;
 #endif
@@ -670,13 +676,13 @@ int sblk_flatconv3x3_fwd(const void* x, const void* wp, const float* bias, const
     return fail(-1, "sblk_flatconv3x3_fwd: pointers must be 16-byte aligned");
   const long long rows = sblk_flat_rows(F, H, W);
   if (rows > 0x7fffffffLL - 1024) return fail(-1, "sblk_flatconv3x3_fwd: problem too large");
-  if (C == 128) return launch_flatconv2<2>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+  if (C == 128) return launch_flatconv2<2>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream), reverse);
 #ifndef SBLK_DEBUG
-  return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+  return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream), reverse);
 #else
   const char* v2 = dbg_env("SBLK_FLATCONV2");   // 0 = v1 single-CTA kernel for C == 64 (A/B timing experiments)
   if (v2 == nullptr || atoi(v2) != 0)
-    return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream));
+    return launch_flatconv2<1>(x, wp, bias, residual, out, rows, H, W, relu, sms, static_cast<cudaStream_t>(stream), reverse);
   CUtensorMap tmX, tmW, tmR;
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows)};

@@ -83,6 +83,11 @@ struct FlatConv2Params {
   const float* bias;           // [C] folded BN shift
   unsigned long long* dbg;     // profiling aid (SBLK_FLAT_STAMPS=1): per-tile clock64 stamps of CTA 0, or nullptr
   int debug_mode;              // SBLK_DEBUG builds, timing experiments (wrong results): 16 = issue the MMAs with N = 32
+  // 1 = every CTA pair walks its tile range from the last tile to the first.  Consecutive convs of a stage alternate the
+  // direction: the activation rows a pair wrote (and read) LAST in one conv are the first it reads in the next, i.e. the
+  // ones most likely still in L2 (a layer-1 tensor is 65.6 MB, conv + residual + output 197 MB against 126 MB of L2).
+  // Same tiles, same arithmetic: bit-identical.
+  int reverse;
 };
 
 template <int CB>
@@ -126,6 +131,9 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int my_cnt = base_cnt + (pair_id < rem ? 1 : 0);
   const int tile_begin = pair_id * base_cnt + min(pair_id, rem);
   const int tile_end = tile_begin + my_cnt;
+  // j-th tile of this pair (every role walks j = 0 .. my_cnt-1)
+  const int tile_first = p.reverse ? tile_end - 1 : tile_begin;
+  const int tile_step = p.reverse ? -1 : 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmX);
@@ -170,7 +178,8 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     grid_dep_wait();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = tile_begin; tile < tile_end; ++tile) {
+    for (int j = 0; j < my_cnt; ++j) {
+      const int tile = tile_first + j * tile_step;
       const int row0 = tile * 256 + static_cast<int>(rank) * Cfg::TILE_M;   // first output row of this CTA
       mbar_wait(&a_empty[stage], phase ^ 1u, 0x0701);
       uint8_t* a_dst = smem + Cfg::OFF_A + stage * Cfg::A_STAGE_BYTES;
@@ -203,7 +212,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (j_next >= my_cnt) return;
         const int rb = j_next % R_BUFS;
         if (p.has_res) {
-          const int row0 = (tile_begin + j_next) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
+          const int row0 = (tile_first + j_next * tile_step) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
           uint8_t* r_dst = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
           mbar_arrive_expect_tx(&r_full[rb], Cfg::R_BYTES);
 #pragma unroll
@@ -217,7 +226,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int j = 0; j < R_BUFS; ++j) recycle(j);   // first round: the tiles are free, only the residuals are missing
       for (int j = 0; j < my_cnt; ++j) {
         const int rb = j % R_BUFS;
-        const int row0 = (tile_begin + j) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
+        const int row0 = (tile_first + j * tile_step) * 256 + static_cast<int>(rank) * Cfg::TILE_M;
         mbar_wait(&s_ready[rb], static_cast<uint32_t>(j / R_BUFS) & 1u, 0x0702);
         const uint8_t* stg = smem + Cfg::OFF_R + rb * Cfg::R_BYTES;
 #pragma unroll
@@ -341,7 +350,7 @@ flatconv2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int Hp = p.H + 1;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
     for (int j = grp; j < my_cnt; j += Cfg::EPI_GROUPS) {
-      const int tile = tile_begin + j;
+      const int tile = tile_first + j * tile_step;
       const int row0 = tile * 256 + static_cast<int>(rank) * Cfg::TILE_M;
       const int acc = j & (ACC_STAGES - 1);
       const uint32_t acc_phase = static_cast<uint32_t>(j >> 2) & 1u;

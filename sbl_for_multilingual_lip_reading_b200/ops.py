@@ -346,8 +346,10 @@ def pack_flat_weight(wp):
     return torch.cat([wp.view(c, 9 * c), torch.eye(c, dtype=BF16, device=wp.device)], dim=1).contiguous()
 
 
-def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None):
-    """Stride-1 3x3 conv over FlatActs (C -> C, C = 64 or 128) -> FlatActs.  wp bf16 [C, 10*C] (pack_flat_weight)."""
+def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None, reverse=False):
+    """Stride-1 3x3 conv over FlatActs (C -> C, C = 64 or 128) -> FlatActs.  wp bf16 [C, 10*C] (pack_flat_weight).
+    reverse: every CTA pair walks its tile range backwards (sblk_flatconv3x3_dir_fwd) — alternate it between the
+    consecutive convs of a stage so each conv starts on the rows the previous one touched last (L2 reuse); same bits."""
     _req(x.data, BF16, "x"); _req(wp, BF16, "wp"); _req(bias, F32, "bias")
     c = x.c
     if tuple(wp.shape) != (c, 10 * c):
@@ -359,10 +361,10 @@ def conv3x3_flat(x, wp, bias, relu=True, residual=None, out=None):
     if out is None:
         out = torch.empty_like(x.data)
     _req(out, BF16, "out")
-    _call("sblk_flatconv3x3_fwd", f"flatconv3x3 H={x.h} {c}->{c}", 2 * x.f * x.h * x.w * c * 9 * c,
+    _call("sblk_flatconv3x3_dir_fwd", f"flatconv3x3 H={x.h} {c}->{c}", 2 * x.f * x.h * x.w * c * 9 * c,
           2 * (x.data.numel() + wp.numel() + out.numel() + (0 if residual is None else residual.data.numel())),
           _p(x.data), _p(wp), _p(bias), None if residual is None else _p(residual.data), _p(out), x.f, x.h, x.w, c,
-          1 if relu else 0, _stream())
+          1 if relu else 0, 1 if reverse else 0, _stream())
     return FlatActs(out, x.f, x.h, x.w)
 
 

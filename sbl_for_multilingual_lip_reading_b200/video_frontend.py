@@ -138,6 +138,10 @@ class Lipreading(nn.Module):
         # bound by L2->SM operand delivery), and the branch is added in fp32 inside conv2's accumulator instead of
         # being rounded to bf16 and read back as a residual.  False = the dual head kernel of round 1.
         self.fold_downsample = True
+        # layers 1-2: consecutive flat convs walk their tiles in alternating directions (ops.conv3x3_flat reverse=):
+        # each conv starts on the rows the previous launch touched last, the part of a 65.6 MB tensor that is still in
+        # L2 (bit-identical; measured in DESIGN.md "[r2d] Alternating tile direction")
+        self.alternate_tile_order = True
         self._overlap = None
         # (scale | None, out_bf16) set by the same plan: the average pool writes mean * scale as bf16 straight into the
         # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
@@ -169,6 +173,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("fuse_prep", True)
         self.__dict__.setdefault("fuse_prep_u8", False)
         self.__dict__.setdefault("fold_downsample", True)
+        self.__dict__.setdefault("alternate_tile_order", True)
         self.__dict__.setdefault("_tail", None)
 
     def _initialize_weights(self):  # same as reference :127-157
@@ -290,6 +295,11 @@ class Lipreading(nn.Module):
         # from layer3 on, activations are dense NHWC and the convs are TMA-im2col implicit GEMMs
         a = ops.conv3d_bn_relu_pool(xp, pk.c3w, pk.c3b, flat=True)
         pf_stream = None
+        rev = [False]   # direction of the previous flat launch (the stem writes its output front to back)
+
+        def flip():
+            rev[0] = (not rev[0]) if self.alternate_tile_order else False
+            return rev[0]
         for bi, (stride, w1, b1, w2, b2, ds) in enumerate(pk.blocks):
             split = 0
             if ov is not None and bi == ov[1]:
@@ -300,8 +310,9 @@ class Lipreading(nn.Module):
                         and a.f >= 2):
                     split = min(a.f - 1, max(1, int(round(a.f * float(ov[3])))))
                     y = ops.FlatActs(torch.empty_like(a.data), a.f, a.h, a.w)
+                    split_rev = flip()
                     ops.conv3x3_flat(ops.flat_frames(a, 0, split), w1, b1, relu=True,
-                                     out=ops.flat_frames(y, 0, split).data)
+                                     out=ops.flat_frames(y, 0, split).data, reverse=split_rev)
                 end_head()
             if self.l2_prefetch and chain == 0 and bi in (0, 4, 6):
                 # Weights of the layers still to come are pulled into L2 by a tiny kernel on a side stream while the
@@ -326,16 +337,17 @@ class Lipreading(nn.Module):
             if isinstance(a, ops.FlatActs) and stride == 1 and ds is None:
                 if split:
                     ops.conv3x3_flat(ops.flat_frames(a, split, a.f), w1, b1, relu=True,
-                                     out=ops.flat_frames(y, split, a.f).data)
+                                     out=ops.flat_frames(y, split, a.f).data, reverse=split_rev)
                 else:
-                    y = ops.conv3x3_flat(a, w1, b1, relu=True)
-                a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a)
+                    y = ops.conv3x3_flat(a, w1, b1, relu=True, reverse=flip())
+                a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=a, reverse=flip())
                 continue
             if ds is not None:   # conv1 and the 1x1 downsample branch share one pass over the block input
                 if w2.dim() == 2:  # layer2: the block stays in the flat layout (conv2 is a flat stride-1 conv)
                     y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True,
                                              flat_ws=self._flat_workspace(a, w1.shape[0], stride, chain))
-                    a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res)
+                    rev[0] = False   # the dual head writes its tiles front to back
+                    a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res, reverse=flip())
                     continue
                 if self.fold_downsample:
                     # y = relu(bn1(conv1 x)); out = relu(bn2(conv2 y) + bn_ds(ds x)) in one fp32 accumulator

@@ -792,6 +792,31 @@ def test_flat_conv_over_frame_ranges_is_bit_identical(dev, c, h):
         assert torch.equal(parts, whole.data)
 
 
+@pytest.mark.parametrize("c,h,f", [(64, 22, 61), (128, 11, 61), (64, 22, 1), (128, 11, 300)])
+def test_flat_conv_reverse_tile_order_is_bit_identical(dev, c, h, f):
+    """sblk_flatconv3x3_dir_fwd: walking every CTA pair's tile range backwards (the frontend alternates the direction
+    between consecutive convs for L2 reuse) changes nothing in the output, with / without residual, full / limited grid."""
+    from sbl_for_multilingual_lip_reading_b200 import ops
+    g = torch.Generator().manual_seed(13 + f)
+    rows = ops.flat_rows(f, h, h)
+    data = torch.zeros(rows, c, dtype=torch.bfloat16, device=dev)
+    v = data[(h + 2):(h + 2) + f * (h + 1) * (h + 2)].view(f, h + 1, h + 2, c)
+    v[:, :h, 1:h + 1, :] = torch.randn(f, h, h, c, generator=g).to(torch.bfloat16).to(dev)
+    x = ops.FlatActs(data, f, h, h)
+    w = ops.pack_flat_weight((torch.randn(c, 3, 3, c, generator=g) / (9 * c) ** 0.5).to(torch.bfloat16).to(dev))
+    bias = torch.randn(c, generator=g).to(dev)
+    for res, limit in ((None, 0), (x, 0), (x, 20)):
+        prev = ops.set_sm_limit(limit) if limit else None
+        try:
+            fwd = ops.conv3x3_flat(x, w, bias, relu=True, residual=res)
+            bwd = ops.conv3x3_flat(x, w, bias, relu=True, residual=res, reverse=True)
+        finally:
+            if prev is not None:
+                ops.set_sm_limit(prev)
+        torch.cuda.synchronize(dev)
+        assert torch.equal(fwd.data, bwd.data)
+
+
 def test_gate_wait_times_out_and_rejects_bad_arguments(dev):
     """sblk_gate_wait is a scheduling hint: with nobody bumping the counter it must give up after its timeout (not
     hang) and still advance its target word; bad arguments fail loudly."""
