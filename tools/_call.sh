@@ -1,7 +1,8 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 50 --warmup 5 > gpurun_out/r02o_bench_N32_T29_8gpu.json 2> gpurun_out/bench8_err.log; echo "bench8 rc=$?"; tail -3 gpurun_out/bench8_err.log
+timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -k "plan" 2>&1 | tail -3
+for i in 1 2; do
+timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-config2 --sustained-seconds 0 > gpurun_out/b5.json 2>/dev/null
 python -c "
 import json
-d=json.load(open('gpurun_out/r02o_bench_N32_T29_8gpu.json'))
-print({k:d.get(k) for k in ('value','ms_per_step','n_gpus','gather_verified','h2d_ceiling_gbs')}); print('e2e', d['e2e']['value'], 'u8', d.get('e2e_u8',{}).get('value'), 'c2', d['config2'].get('value'), d['config2'].get('gather_verified'), 'sus', d['sustained']['clips_per_s'])
-"
+d=json.load(open('gpurun_out/b5.json')); print('K=20:', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], 'u8', d['e2e_u8']['value'], 'lat', d['latency']['ms_per_step'])"
+done
