@@ -304,6 +304,8 @@ class Shape:
         rank's block into every peer's buffer over NVLink and waits for all peers' blocks; or NCCL.  Returns the
         gathered [world*B*T*512] fp32 view."""
         import torch.distributed as dist
+        if os.environ.get("SBLK_BENCH_NO_GATHER"):   # diagnosis only (what the gather + its lock-step cost): the line says so
+            return out.view(-1)
         if self.p2p is not None:
             return self.p2p(out.view(-1))
         if self.gathered is not None:
@@ -328,11 +330,18 @@ class Shape:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record(plan.compute)
-            if defer and self.pending is not None:
+            gather_first = bool(os.environ.get("SBLK_BENCH_GATHER_FIRST"))   # diagnosis: the round-2 issue order
+            if defer and self.pending is not None and gather_first:
                 self.gather_stream.wait_event(e0)
                 with torch.cuda.stream(self.gather_stream):
                     self.gather_outputs(self.pending)
             out = plan.forward_device(s)
+            if defer and self.pending is not None and not gather_first:
+                # issued BEHIND the replay: the step's first kernels (encoder clusters, gated stem) get their SMs before
+                # the gather's small CTAs look for room beside them
+                self.gather_stream.wait_event(e0)
+                with torch.cuda.stream(self.gather_stream):
+                    self.gather_outputs(self.pending)
             if defer:
                 plan.compute.wait_stream(self.gather_stream)
                 self.pending = out
@@ -366,6 +375,11 @@ class Shape:
         return sharding.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs), self.ctx.dev) / steps
 
     def verify_gather(self):
+        if os.environ.get("SBLK_BENCH_NO_GATHER"):
+            return "skipped: SBLK_BENCH_NO_GATHER diagnostic run (no output gathering in the timed region)"
+        return self._verify_gather()
+
+    def _verify_gather(self):
         """One untimed check that the gather the timed region uses delivers what NCCL's all-gather delivers."""
         import torch
         import torch.distributed as dist

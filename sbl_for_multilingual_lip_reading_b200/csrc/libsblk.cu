@@ -435,9 +435,13 @@ int sblk_p2p_gather_fwd(const void* local, const void* const* peer_bufs_dev, con
   if (bytes_per_rank <= 0 || (bytes_per_rank & 15) || !aligned16(local))
     return fail(-1, "sblk_p2p_gather_fwd: block must be a positive multiple of 16 bytes, 16-byte aligned");
   const long long n16 = bytes_per_rank / 16;
-  long long grid = (n16 + 255) / 256;
-  if (grid > 32) grid = 32;   // 8192 threads x 16 B x `world` stores in flight: enough for NVLink, few SMs
-  return launch(sblk::p2p_gather_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 0,
+  // 64 CTAs of 128 threads (8192 threads x 16 B x `world` stores in flight: enough for NVLink).  Small CTAs on purpose:
+  // the gather runs next to the compute graph, whose persistent kernels hold every SM with one big CTA — a 128-thread
+  // CTA with 40 registers per thread still fits beside a stem CTA (608 threads x 96 registers), a 256-thread one does not
+  // and made the stem's CTAs on 32 SMs start late (2 GPUs: 0.650 -> see DESIGN.md 6 [r2d])
+  long long grid = (n16 + 127) / 128;
+  if (grid > 64) grid = 64;
+  return launch(sblk::p2p_gather_kernel, dim3(static_cast<unsigned>(grid)), dim3(128), 0,
                 static_cast<cudaStream_t>(stream), false, "p2p_gather_kernel", static_cast<const uint4*>(local),
                 reinterpret_cast<uint4* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_bufs_dev))),
                 reinterpret_cast<unsigned int* const*>(const_cast<void* const*>(reinterpret_cast<const void* const*>(peer_flags_dev))),

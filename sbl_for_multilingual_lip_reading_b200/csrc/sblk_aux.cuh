@@ -246,7 +246,7 @@ l2_prefetch_kernel(const L2PrefetchRanges r, int mode) {
 // Epochs increase by one per call; callers alternate two buffers so a peer that runs one step ahead never overwrites
 // a block that may still be read.
 // --------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 p2p_gather_kernel(const uint4* __restrict__ local, uint4* const* __restrict__ peer_bufs,
                   unsigned int* const* __restrict__ peer_flags, unsigned int* __restrict__ counter, int rank, int world,
                   long long n16, unsigned int epoch, unsigned long long timeout_ns) {
