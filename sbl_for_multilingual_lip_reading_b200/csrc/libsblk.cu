@@ -1404,7 +1404,7 @@ int sblk_colreduce(int mode, const void* a, const void* b, const void* c, const 
   if ((rc = launch(sblk::colreduce_kernel, dim3(static_cast<unsigned>(grid)), dim3(256), 256 * 16 * sizeof(float), s, false,
                    "colreduce_kernel", p)))
     return rc;
-  return launch(sblk::colreduce_finish_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, s, false,
+  return launch(sblk::colreduce_finish_kernel, dim3((2 * C + 31) / 32), dim3(256), 0, s, false,
                 "colreduce_finish_kernel", static_cast<const float*>(workspace), out_2C, static_cast<int>(grid), 2 * C);
 }
 
@@ -1424,6 +1424,7 @@ int sblk_bn_apply_fwd(const void* x, const void* residual, const float* mean, co
   if ((rc = ensure_init(&sms))) return rc;
   if (!x || !mean || !rstd || !gamma || !beta || !out) return fail(-1, "sblk_bn_apply_fwd: null pointer");
   if (M <= 0 || C <= 0 || C % 8 != 0) return fail(-1, "sblk_bn_apply_fwd: bad shape M=%lld C=%d (C %% 8 == 0)", M, C);
+  if (256 % (C / 8) != 0) return fail(-1, "sblk_bn_apply_fwd: C=%d not supported (C / 8 must divide 256: per-thread constant channels)", C);
   if (!aligned16(x) || !aligned16(out) || (residual && !aligned16(residual))) return fail(-1, "sblk_bn_apply_fwd: pointers must be 16-byte aligned");
   const long long total8 = M * (C / 8);
   return launch(sblk::bn_apply_kernel, dim3(elementwise_grid(total8, 256, sms)), dim3(256), 0,
@@ -1437,6 +1438,7 @@ int sblk_bn_bwd(const void* dy, const void* out_act, const void* x, const float*
   if ((rc = ensure_init(&sms))) return rc;
   if (!dy || !x || !mean || !rstd || !gamma || !sums_2C || !dx) return fail(-1, "sblk_bn_bwd: null pointer");
   if (M <= 0 || C <= 0 || C % 8 != 0) return fail(-1, "sblk_bn_bwd: bad shape M=%lld C=%d (C %% 8 == 0)", M, C);
+  if (256 % (C / 8) != 0) return fail(-1, "sblk_bn_bwd: C=%d not supported (C / 8 must divide 256: per-thread constant channels)", C);
   if (!aligned16(dy) || !aligned16(x) || !aligned16(dx) || (out_act && !aligned16(out_act)) || (dres && !aligned16(dres)))
     return fail(-1, "sblk_bn_bwd: pointers must be 16-byte aligned");
   const long long total8 = M * (C / 8);
@@ -1520,7 +1522,7 @@ int sblk_ln_bwd(const float* dy, const float* z, const float* gamma, const int* 
   if (grid > cap) grid = cap;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if ((rc = launch(sblk::ln_bwd_kernel, dim3(grid), dim3(256), 0, s, false, "ln_bwd_kernel", p))) return rc;
-  return launch(sblk::colreduce_finish_kernel, dim3(4), dim3(256), 0, s, false, "colreduce_finish_kernel",
+  return launch(sblk::colreduce_finish_kernel, dim3(1024 / 32), dim3(256), 0, s, false, "colreduce_finish_kernel",
                 static_cast<const float*>(workspace), dgamma_dbeta_1024, grid, 1024);
 }
 

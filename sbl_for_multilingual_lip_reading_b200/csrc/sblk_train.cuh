@@ -299,14 +299,26 @@ colreduce_kernel(const ColReduceParams p) {
   }
 }
 
-// out[j] = sum over blocks of part[block][j], j < 2*C, in block order (deterministic)
+// out[j] = sum over blocks of part[block][j], j < 2*C, in a fixed order (deterministic): a CTA owns 32 columns, thread
+// (cx, sy) adds the blocks sy, sy + 8, ... of column cx in order, the eight slice sums are then added in slice order.
+// (One thread per column walking all ~600 partial blocks was a chain of dependent L2 round trips: ~40 us per call, the
+// fixed cost of every BatchNorm statistic / bias-gradient reduction of the training step.)  Launch: ceil(n / 32) CTAs.
 __global__ void __launch_bounds__(256)
 colreduce_finish_kernel(const float* __restrict__ part, float* __restrict__ out, int nblocks, int n) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
+  __shared__ float red[8][32];
+  const int cx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + cx;
   float s = 0.0f;
-  for (int b = 0; b < nblocks; ++b) s += part[static_cast<long long>(b) * n + j];
-  out[j] = s;
+  if (j < n)
+    for (int b = sy; b < nblocks; b += 8) s += part[static_cast<long long>(b) * n + j];
+  red[sy][cx] = s;
+  __syncthreads();
+  if (sy == 0 && j < n) {
+    float t = red[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cx];
+    out[j] = t;
+  }
 }
 
 // BatchNorm training statistics from (sum, sumsq): mean, rstd = 1/sqrt(biased var + eps), and the running-stat update
@@ -337,9 +349,17 @@ bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual,
                 const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ beta,
                 uint4* __restrict__ out, long long total8, int C, int relu) {
   const int c8n = C / 8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % c8n) * 8;
+  // the grid stride (gridDim.x * 256) is a multiple of C/8 (a power of two <= 64: checked by the launcher), so a thread
+  // sees the same 8 channels in every trip: their statistics / affine parameters are loaded once (they were 32 scalar
+  // loads per 16-byte vector)
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int c0 = static_cast<int>(i0 % c8n) * 8;
+  float mn[8], rs[8], gm[8], bt[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mn[e] = __ldg(mean + c0 + e); rs[e] = __ldg(rstd + c0 + e); gm[e] = __ldg(gamma + c0 + e); bt[e] = __ldg(beta + c0 + e);
+  }
+  for (long long i = i0; i < total8; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 u = __ldg(x + i);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
     uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
@@ -348,9 +368,8 @@ bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual,
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = c0 + 2 * j;
-      float a = (bf16_lo(w[j]) - __ldg(mean + c)) * __ldg(rstd + c) * __ldg(gamma + c) + __ldg(beta + c);
-      float b = (bf16_hi(w[j]) - __ldg(mean + c + 1)) * __ldg(rstd + c + 1) * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+      float a = (bf16_lo(w[j]) - mn[2 * j]) * rs[2 * j] * gm[2 * j] + bt[2 * j];
+      float b = (bf16_hi(w[j]) - mn[2 * j + 1]) * rs[2 * j + 1] * gm[2 * j + 1] + bt[2 * j + 1];
       if (residual != nullptr) { a += bf16_lo(rw[j]); b += bf16_hi(rw[j]); }
       if (relu) { a = fmaxf(a, 0.0f); b = fmaxf(b, 0.0f); }
       o[j] = pack_bf16x2(a, b);
@@ -367,9 +386,16 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ out_
                     const float* __restrict__ sums, uint4* __restrict__ dx, uint4* __restrict__ dres, long long total8,
                     int C, float inv_count) {
   const int c8n = C / 8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i % c8n) * 8;
+  // per-thread constant channels (see bn_apply_kernel): statistics, scale and the two reduction sums loaded once
+  const long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const int c0 = static_cast<int>(i0 % c8n) * 8;
+  float mn[8], rsv[8], gm[8], sm0[8], sm1[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mn[e] = __ldg(mean + c0 + e); rsv[e] = __ldg(rstd + c0 + e); gm[e] = __ldg(gamma + c0 + e);
+    sm0[e] = __ldg(sums + c0 + e); sm1[e] = __ldg(sums + C + c0 + e);
+  }
+  for (long long i = i0; i < total8; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 ud = __ldg(dy + i), ux = __ldg(x + i);
     uint4 uo = make_uint4(0u, 0u, 0u, 0u);
     if (out_act != nullptr) uo = __ldg(out_act + i);
@@ -386,10 +412,10 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ out_
       float g[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int c = c0 + 2 * j + e;
-        const float rs = __ldg(rstd + c);
-        const float xh = (xv[e] - __ldg(mean + c)) * rs;
-        g[e] = __ldg(gamma + c) * rs * (d[e] - __ldg(sums + c) * inv_count - xh * __ldg(sums + C + c) * inv_count);
+        const int c = 2 * j + e;
+        const float rs = rsv[c];
+        const float xh = (xv[e] - mn[c]) * rs;
+        g[e] = gm[c] * rs * (d[e] - sm0[c] * inv_count - xh * sm1[c] * inv_count);
       }
       o[j] = pack_bf16x2(g[0], g[1]);
       oz[j] = pack_bf16x2(d[0], d[1]);
