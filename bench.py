@@ -591,6 +591,7 @@ def run_b200_arm(args):
     line_extra = {}
     breakdown = []
     if rank == 0:
+        ctx_sms = int(ops.init())
         prev_pdl = ops.set_pdl(False)
         prev_cl = enc.stack_cluster_size
         if pipelined:
@@ -648,11 +649,45 @@ def run_b200_arm(args):
         if pipelined and rows[0][0][0] == "sblk_encoder_stack_fwd":
             # in the pipelined plan the stack runs on the side stream next to the next batch's prep + stem: the largest
             # kernel group of the step's critical path is reported as well
-            roof["note"] = ("latency-bound dependent chain (25 GEMM stages on 64 SMs); overlapped with the next batch's "
-                            "clip prep + stem by the pipelined plan, see critical_path and path")
+            roof["note"] = ("latency-bound dependent chain (25 GEMM stages) holding `sms_held` of the GPU's SMs; overlapped "
+                            "with the next batch's frontend head by the pipelined plan in the `as_pipelined` form, see "
+                            "critical_path and path")
             nxt = [r for r in rows if r[0][0] != "sblk_encoder_stack_fwd"]
             if nxt:
                 roof["critical_path"] = roofline_of(nxt[0])
+            # the figures above time the stack in its one-group-per-cluster form (clusters of `enc_cluster` CTAs, one per
+            # clip group); the pipelined plan launches it with `enc_gpc` groups interleaved per cluster on fewer SMs.
+            # Time that form alone as well and say how many SMs each form holds: `frac` divides by the WHOLE GPU's peak.
+            try:
+                gpc, cl = int(plan.enc_gpc), int(plan.enc_cluster)
+                groups = -(-B // max(1, 128 // T))
+                roof["sms_held"] = cl * groups
+                roof["frac_of_held_sms_peak"] = roof["frac"] * ctx_sms / max(1, cl * groups)
+                if gpc > 1:
+                    saved = (enc.stack_cluster_size, enc.stack_groups_per_cluster)
+                    enc.stack_cluster_size, enc.stack_groups_per_cluster = cl, gpc
+                    feat_probe = torch.randn(B, T, 512, device=dev)
+                    ts = []
+                    with torch.no_grad():
+                        for rep in range(6):
+                            ctx.flush.zero_()
+                            sink2 = []
+                            with ops.trace(sink2):
+                                enc(feat_probe, [T] * B)
+                            torch.cuda.synchronize(dev)
+                            ts += [r_["start"].elapsed_time(r_["end"]) for r_ in sink2
+                                   if r_["name"] == "sblk_encoder_stack_fwd"]
+                    enc.stack_cluster_size, enc.stack_groups_per_cluster = saved
+                    us = sorted(ts[1:])[len(ts[1:]) // 2] * 1e3
+                    held = cl * -(-groups // gpc)
+                    ach = roof["achieved"] * roof["avg_launch_us"] / us
+                    roof["as_pipelined"] = {"groups_per_cluster": gpc, "sms_held": held, "avg_launch_us": us,
+                                            "achieved": ach, "frac": ach / roof["peak"],
+                                            "frac_of_held_sms_peak": ach / roof["peak"] * ctx_sms / max(1, held),
+                                            "what": "the stack launch of the pipelined plan (same kernel, clip groups "
+                                                    "interleaved per cluster) timed alone like the figures above"}
+            except Exception as e:  # noqa: BLE001  (a diagnostic key must not cost the line)
+                roof["as_pipelined"] = {"error": str(e)}
         path_tf = value / world * fpc / 1e12
         roof["path"] = {"flops_per_clip": fpc, "achieved_tflops_per_gpu": path_tf,
                         "frac_of_bf16_peak": path_tf / float(peaks["bf16_tflops"]),
