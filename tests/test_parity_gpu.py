@@ -285,6 +285,24 @@ def test_c_abi_rejects_bad_arguments(dev):
     with pytest.raises(RuntimeError, match="expected dtype"):
         ops.conv2d(torch.zeros(1, 22, 22, 64, device=dev), torch.zeros(64, 3, 3, 64, dtype=torch.bfloat16, device=dev),
                    torch.zeros(64, device=dev))
+    # K-extension (sblk_conv2d_igemm_ext_fwd): the branch's output grid must be the conv's; Cout must allow the CTA-pair kernel
+    bf = torch.bfloat16
+    y = torch.zeros(2, 6, 6, 128, dtype=bf, device=dev)
+    w = torch.zeros(128, 3, 3, 128, dtype=bf, device=dev)
+    with pytest.raises(RuntimeError, match="output grid"):
+        ops.conv2d(y, w, torch.zeros(128, device=dev), ext=(torch.zeros(2, 9, 9, 64, dtype=bf, device=dev),
+                                                           torch.zeros(128, 1, 1, 64, dtype=bf, device=dev), 2))
+    with pytest.raises(RuntimeError, match="do not match"):
+        ops.conv2d(y, w, torch.zeros(128, device=dev), ext=(torch.zeros(2, 11, 11, 64, dtype=bf, device=dev),
+                                                           torch.zeros(64, 1, 1, 64, dtype=bf, device=dev), 2))
+    lib_err = None
+    try:   # Cout = 64: no CTA-pair kernel -> the C ABI refuses (no silent fallback)
+        ops.conv2d(torch.zeros(2, 6, 6, 64, dtype=bf, device=dev), torch.zeros(64, 3, 3, 64, dtype=bf, device=dev),
+                   torch.zeros(64, device=dev), ext=(torch.zeros(2, 11, 11, 64, dtype=bf, device=dev),
+                                                     torch.zeros(64, 1, 1, 64, dtype=bf, device=dev), 2))
+    except RuntimeError as e:
+        lib_err = str(e)
+    assert lib_err is not None and "CTA-pair" in lib_err
 
 
 # ------------------------------------------------------------------ one-launch encoder stack (cluster kernel)
