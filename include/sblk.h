@@ -148,19 +148,23 @@ int sblk_conv2d_igemm_ext_fwd(const void* x_bf16, const void* w_packed_bf16, con
                               int R, int S, int stride, int pad, int relu, int in_row_pitch, int in_frame_pitch,
                               const void* x2_bf16, const void* w2_bf16, int H2, int W2, int Cin2, int stride2,
                               int x2_row_pitch, int x2_frame_pitch, void* stream);
-/* A whole BasicBlock with 256 output channels (ResNet layer 3) in ONE launch:
- *   y1  = relu(conv3x3_stride(x, w1) + bias1)                                   (workspace y1_ws, bf16 [F,P,Q,256])
+/* A whole BasicBlock of ResNet layer 3 (Cout = 256) or layer 4 (Cout = 512) in ONE launch:
+ *   y1  = relu(conv3x3_stride(x, w1) + bias1)                                   (workspace y1_ws, bf16 [F,P,Q,Cout])
  *   out = relu(conv3x3(y1, w2) + bias2 + (w_ds ? conv1x1_stride(x, w_ds) : x))   (bias2 includes the downsample shift)
- * Pair tiles are made of whole frames, so conv2 of a tile depends on conv1 of the same tile only: every CTA pair runs
- * conv1 over its tiles, then conv2 over the same tiles, with a pair-wide barrier per tile and no grid-wide
- * synchronisation.  Bit-identical to sblk_conv2d_igemm_fwd + sblk_conv2d_igemm[_ext]_fwd.  w_ds must be given exactly
- * when stride == 2 or Cin != 256; x may be pitched (flat layout) only then.  Returns -2 (nothing launched) when a CTA
- * pair would own more than 8 tiles: launch the convs one by one.
- * replaces: BasicBlock.forward of ResNet layer3, transformer/video_frontend.py:28-41,68-72 */
-int sblk_conv_block256_fwd(const void* x_bf16, const void* w1_packed_bf16, const float* bias1,
-                           const void* w2_packed_bf16, const float* bias2, const void* w_ds_packed_bf16, void* y1_ws,
-                           void* out_bf16, int F, int H, int W, int Cin, int stride, int in_row_pitch,
-                           int in_frame_pitch, void* stream);
+ * Pair tiles are made of whole frames, so conv2 of a tile depends on conv1 of the same frames only: every CTA pair runs
+ * conv1 over its work units, then conv2 over the same units — no grid-wide synchronisation, no second launch.  Cout =
+ * 256: one unit per frame group, a pair-wide mbarrier per tile.  Cout = 512: two column tiles per frame group on
+ * neighbouring CTA pairs, which meet at a self-resetting counter pair in flags_ws (uint32 [sblk_conv_block_flag_words],
+ * zeroed ONCE by the caller; one workspace per stream).  The grid never exceeds the SMs of sblk_set_sm_limit, which is
+ * what keeps the waiting pairs deadlock-free next to a co-running kernel.  Bit-identical to sblk_conv2d_igemm_fwd +
+ * sblk_conv2d_igemm[_ext]_fwd.  w_ds must be given exactly when the block changes shape; x may be pitched (flat layout)
+ * only then.  Returns -2 (nothing launched) when a CTA pair would own more than 8 units: launch the convs one by one.
+ * replaces: BasicBlock.forward of ResNet layer3 / layer4, transformer/video_frontend.py:28-41,68-72 */
+int sblk_conv_block_flag_words(int F, int H, int W, int stride);
+int sblk_conv_block_fwd(const void* x_bf16, const void* w1_packed_bf16, const float* bias1, const void* w2_packed_bf16,
+                        const float* bias2, const void* w_ds_packed_bf16, void* y1_ws, void* flags_ws, void* out_bf16,
+                        int F, int H, int W, int Cin, int Cout, int stride, int in_row_pitch, int in_frame_pitch,
+                        void* stream);
 /* BasicBlock head of layers 2-4 in one launch: out = relu(conv3x3_stride_s(x) + bias) and the downsample branch
  * out_ds = conv1x1_stride_s(x) + bias_ds.  The 1x1 conv reads exactly the centre-tap A tiles of the 3x3 conv, so
  * both share one pass over x (second TMEM accumulator).  w_ds_packed is [Cout][1][1][Cin]; Cout % 128 == 0.

@@ -764,40 +764,54 @@ static int encode_im2col_map(CUtensorMap* tm, const void* ptr, int F, int c, int
   return 0;
 }
 
-int sblk_conv_block256_fwd(const void* x, const void* w1, const float* bias1, const void* w2, const float* bias2,
-                           const void* w_ds, void* y1_ws, void* out, int F, int H, int W, int Cin, int stride,
-                           int in_row_pitch, int in_frame_pitch, void* stream) {
-  int sms, rc;
-  if ((rc = ensure_init(&sms))) return rc;
-  if (!x || !w1 || !bias1 || !w2 || !bias2 || !y1_ws || !out) return fail(-1, "sblk_conv_block256_fwd: null pointer");
-  if (F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 64 != 0) return fail(-1, "sblk_conv_block256_fwd: bad shape F=%d H=%d W=%d Cin=%d", F, H, W, Cin);
-  if (stride != 1 && stride != 2) return fail(-1, "sblk_conv_block256_fwd: stride %d not implemented", stride);
-  if ((w_ds != nullptr) != (stride == 2 || Cin != 256))
-    return fail(-1, "sblk_conv_block256_fwd: a downsample filter is needed exactly when the block changes shape (stride %d, Cin %d)", stride, Cin);
-  if (!aligned16(x) || !aligned16(w1) || !aligned16(w2) || (w_ds && !aligned16(w_ds)) || !aligned16(y1_ws) || !aligned16(out) ||
-      !aligned16(bias1) || !aligned16(bias2))
-    return fail(-1, "sblk_conv_block256_fwd: pointers must be 16-byte aligned");
-  constexpr int Cout = 256;
+int sblk_conv_block_flag_words(int F, int H, int W, int stride) {
+  if (F <= 0 || H <= 0 || W <= 0 || (stride != 1 && stride != 2)) return -1;
   const int P = (H + 2 - 3) / stride + 1, Q = (W + 2 - 3) / stride + 1;
   const int pq = P * Q;
-  if (pq > 256) return fail(-1, "sblk_conv_block256_fwd: %dx%d output maps do not fit a 256-row pair tile", P, Q);
+  if (pq > 256) return -1;
+  const long long M = static_cast<long long>(F) * pq;
+  const int rpt = (256 / pq) * pq;
+  return static_cast<int>(2 * ((M + rpt - 1) / rpt));
+}
+
+int sblk_conv_block_fwd(const void* x, const void* w1, const float* bias1, const void* w2, const float* bias2,
+                        const void* w_ds, void* y1_ws, void* flags_ws, void* out, int F, int H, int W, int Cin, int Cout,
+                        int stride, int in_row_pitch, int in_frame_pitch, void* stream) {
+  int sms, rc;
+  if ((rc = ensure_init(&sms))) return rc;
+  if (!x || !w1 || !bias1 || !w2 || !bias2 || !y1_ws || !out) return fail(-1, "sblk_conv_block_fwd: null pointer");
+  if (F <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cin % 64 != 0) return fail(-1, "sblk_conv_block_fwd: bad shape F=%d H=%d W=%d Cin=%d", F, H, W, Cin);
+  if (Cout != 256 && Cout != 512) return fail(-1, "sblk_conv_block_fwd: Cout=%d (256 or 512: ResNet layer 3 / layer 4)", Cout);
+  if (stride != 1 && stride != 2) return fail(-1, "sblk_conv_block_fwd: stride %d not implemented", stride);
+  if ((w_ds != nullptr) != (stride == 2 || Cin != Cout))
+    return fail(-1, "sblk_conv_block_fwd: a downsample filter is needed exactly when the block changes shape (stride %d, %d -> %d)", stride, Cin, Cout);
+  if (Cout > 256 && !flags_ws) return fail(-1, "sblk_conv_block_fwd: Cout=%d needs the flag workspace (sblk_conv_block_flag_words zeroed uint32)", Cout);
+  if (!aligned16(x) || !aligned16(w1) || !aligned16(w2) || (w_ds && !aligned16(w_ds)) || !aligned16(y1_ws) || !aligned16(out) ||
+      !aligned16(bias1) || !aligned16(bias2) || (flags_ws && (reinterpret_cast<uintptr_t>(flags_ws) & 3u)))
+    return fail(-1, "sblk_conv_block_fwd: pointers must be 16-byte aligned");
+  const int P = (H + 2 - 3) / stride + 1, Q = (W + 2 - 3) / stride + 1;
+  const int pq = P * Q;
+  if (pq > 256) return fail(-1, "sblk_conv_block_fwd: %dx%d output maps do not fit a 256-row pair tile", P, Q);
   const long long M64 = static_cast<long long>(F) * pq;
-  if (M64 > 0x7fffffffLL - 256) return fail(-1, "sblk_conv_block256_fwd: problem too large");
+  if (M64 > 0x7fffffffLL - 256) return fail(-1, "sblk_conv_block_fwd: problem too large");
   sblk::BlockConvParams p;
   p.M = static_cast<int>(M64); p.P = P; p.Q = Q;
+  p.N = Cout; p.n_tiles = Cout / 256;
   p.rows_per_tile = (256 / pq) * pq;
   p.num_tiles = (p.M + p.rows_per_tile - 1) / p.rows_per_tile;
-  const int pairs = p.num_tiles < sms / 2 ? p.num_tiles : sms / 2;
-  if (pairs < 1 || (p.num_tiles + pairs - 1) / pairs > sblk::BLK_MAX_TILES)
-    return fail(-2, "sblk_conv_block256_fwd: %d tiles on %d CTA pairs: more than %d tiles per pair (launch the convs one by one)",
-                p.num_tiles, pairs, sblk::BLK_MAX_TILES);
+  const int units = p.num_tiles * p.n_tiles;
+  const int pairs = units < sms / 2 ? units : sms / 2;
+  if (pairs < 1 || (units + pairs - 1) / pairs > sblk::BLK_MAX_TILES)
+    return fail(-2, "sblk_conv_block_fwd: %d work units on %d CTA pairs: more than %d tiles per pair (launch the convs one by one)",
+                units, pairs, sblk::BLK_MAX_TILES);
   p.c1_cblocks = Cin / 64; p.c1_stride = stride; p.c2_cblocks = Cout / 64;
   p.ext_cblocks = w_ds ? Cin / 64 : 0; p.ext_stride = stride;
   p.bias1 = bias1; p.bias2 = bias2;
   p.residual = w_ds ? nullptr : static_cast<const __nv_bfloat16*>(x);
   if (!w_ds && (in_row_pitch > 0 || in_frame_pitch > 0))
-    return fail(-1, "sblk_conv_block256_fwd: the identity residual needs a dense NHWC block input");
+    return fail(-1, "sblk_conv_block_fwd: the identity residual needs a dense NHWC block input");
   p.y1 = static_cast<__nv_bfloat16*>(y1_ws); p.out = static_cast<__nv_bfloat16*>(out);
+  p.flags = static_cast<unsigned int*>(flags_ws);
   CUtensorMap tmA1, tmB1, tmA2, tmB2, tmA3, tmB3;
   if ((rc = encode_im2col_map(&tmA1, x, F, Cin, W, H, in_row_pitch, in_frame_pitch, 3, 3, 1, stride))) return rc;
   if ((rc = encode_im2col_map(&tmA2, y1_ws, F, Cout, Q, P, 0, 0, 3, 3, 1, 1))) return rc;
@@ -805,18 +819,18 @@ int sblk_conv_block256_fwd(const void* x, const void* w1, const float* bias1, co
   if (w_ds && (rc = encode_im2col_map(&tmA3, x, F, Cin, W, H, in_row_pitch, in_frame_pitch, 1, 1, 0, stride))) return rc;
   cuuint32_t box[2] = {64, 128};
   {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * Cin), Cout};
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * Cin), static_cast<cuuint64_t>(Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(9 * Cin) * 2};
     if ((rc = encode_tiled(&tmB1, w1, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * Cout), Cout};
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(9 * Cout), static_cast<cuuint64_t>(Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(9 * Cout) * 2};
     if ((rc = encode_tiled(&tmB2, w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }
   tmB3 = tmB2;
   if (w_ds) {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Cin), Cout};
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Cin), static_cast<cuuint64_t>(Cout)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(Cin) * 2};
     if ((rc = encode_tiled(&tmB3, w_ds, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   }

@@ -29,14 +29,21 @@ struct BlockConvParams {
   int num_tiles;       // ceil(M / rows_per_tile)
   int c1_cblocks;      // Cin / 64 of conv1 (3x3, pad 1, stride c1_stride over x)
   int c1_stride;
-  int c2_cblocks;      // 256 / 64 of conv2 (3x3, pad 1, stride 1 over y1)
+  int N;               // output channels of both convs: 256 (layer 3) or 512 (layer 4)
+  int n_tiles;         // N / 256 column tiles per frame group; work unit = (frame-group tile, column tile)
+  int c2_cblocks;      // N / 64 of conv2 (3x3, pad 1, stride 1 over y1)
   int ext_cblocks;     // k-blocks of the 1x1 / stride ext_stride downsample branch over x behind conv2's own (0 = none)
   int ext_stride;
   const float* bias1;              // [256] folded bn1 shift
   const float* bias2;              // [256] folded bn2 shift (+ folded downsample shift when ext_cblocks > 0)
-  const __nv_bfloat16* residual;   // [M, 256] identity residual of conv2 (blocks without a downsample branch) or nullptr
-  __nv_bfloat16* y1;               // [M, 256] workspace: relu(bn1(conv1 x))
-  __nv_bfloat16* out;              // [M, 256]
+  const __nv_bfloat16* residual;   // [M, N] identity residual of conv2 (blocks without a downsample branch) or nullptr
+  __nv_bfloat16* y1;               // [M, N] workspace: relu(bn1(conv1 x))
+  __nv_bfloat16* out;              // [M, N]
+  // n_tiles > 1: conv2 of a unit needs conv1 of ALL column tiles of its frame group, computed by neighbouring CTA pairs
+  // (unit indices are adjacent, so they run at the same time).  flags[tile] counts the epilogue warps that have published
+  // their y1 rows (n_tiles x 2 CTAs x 8 warps), flags[num_tiles + tile] the producers that have seen it; the last one
+  // resets both, so the counters are zero again when the kernel ends (zero-initialised once by the caller).
+  unsigned int* flags;
 };
 
 constexpr int BLK_MAX_TILES = 8;   // tiles one CTA pair may own (y1-ready barriers); more -> the caller launches conv by conv
@@ -74,8 +81,9 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
 
   const int pair_id = blockIdx.x >> 1;
   const int num_pairs = gridDim.x >> 1;
-  const int n_my = pair_id < p.num_tiles ? (p.num_tiles - pair_id + num_pairs - 1) / num_pairs : 0;   // my tiles
-  const int n_items = 2 * n_my;                      // item i: phase i / n_my (0 conv1, 1 conv2), my tile i % n_my
+  const int num_units = p.num_tiles * p.n_tiles;     // unit = (frame-group tile, column tile), column tile fastest
+  const int n_my = pair_id < num_units ? (num_units - pair_id + num_pairs - 1) / num_pairs : 0;   // my units
+  const int n_items = 2 * n_my;                      // item i: phase i / n_my (0 conv1, 1 conv2), my unit i % n_my
   const int nkb1 = 9 * p.c1_cblocks;
   const int nkb2_main = 9 * p.c2_cblocks;
   const int nkb2 = nkb2_main + p.ext_cblocks;
@@ -106,7 +114,6 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2cta(&tmem_base_slot, Cfg::TMEM_COLS);
-  for (int e = threadIdx.x; e < BLOCK_N; e += blockDim.x) bias_s[e] = __ldg(p.bias1 + e);
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -120,17 +127,51 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     int stage = 0;
     uint32_t phase = 0;
     grid_dep_wait();
-    const int n0 = static_cast<int>(rank) * Cfg::BH;
     for (int it = 0; it < n_items; ++it) {
       const int ph2 = it >= n_my ? 1 : 0;
       const int j = it - ph2 * n_my;
-      const int tile = pair_id + j * num_pairs;
+      const int unit = pair_id + j * num_pairs;
+      const int tile = unit / p.n_tiles;
+      const int n0 = (unit - tile * p.n_tiles) * BLOCK_N + static_cast<int>(rank) * Cfg::BH;
       const int m0 = tile * p.rows_per_tile + static_cast<int>(rank) * Cfg::BLOCK_M;
       const int img = m0 / pq;
       const int rem = m0 - img * pq;
       const int oh = rem / p.Q;
       const int ow = rem - oh * p.Q;
-      if (ph2) {
+      if (ph2 && p.n_tiles > 1) {
+        // conv1's rows of this frame group — all column tiles, i.e. the epilogue warps of n_tiles CTA pairs — are in
+        // global memory once the group's counter has reached n_tiles x 2 CTAs x 8 warps
+        if (lane == 0) {
+          const unsigned int target = static_cast<unsigned int>(p.n_tiles * 2 * Cfg::EPI_WARPS);
+          unsigned int seen, polls = 0;
+          unsigned long long t0 = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.flags + tile) : "memory");
+            if (seen >= target) break;
+            if ((++polls & 255u) == 0u) {
+              unsigned long long now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              if (now - t0 > SBLK_WATCHDOG_NS) {
+                unsigned int* wd = g_sblk_watchdog_ptr;
+                if (wd != nullptr) {
+                  atomicCAS_system(wd, 0u, 0x0a07u | 0x80000000u);
+                  __threadfence_system();
+                }
+                __trap();
+              }
+            }
+          } while (true);
+          // every producer of the group (n_tiles pairs x 2 CTAs) passes here exactly once: the last one resets the counters
+          if (atomicAdd(p.flags + p.num_tiles + tile, 1u) == static_cast<unsigned int>(2 * p.n_tiles - 1)) {
+            p.flags[tile] = 0u;
+            p.flags[p.num_tiles + tile] = 0u;
+          }
+        }
+        __syncwarp();
+        __threadfence();
+        asm volatile("fence.proxy.async;" ::: "memory");
+      } else if (ph2) {
         // conv1's rows of this tile (written by the epilogue warps of BOTH CTAs) are in global memory
         mbar_wait(&y1_ready[j], 0, 0x0a01);
         __threadfence();
@@ -217,24 +258,29 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
     uint8_t* const stg = smem + Cfg::OFF_STG + ew * Cfg::STG_WARP_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    int cur_bias = -1;
     grid_dep_wait();
     for (int it = 0; it < n_items; ++it) {
       const int ph2 = it >= n_my ? 1 : 0;
       const int j = it - ph2 * n_my;
-      const int tile = pair_id + j * num_pairs;
+      const int unit = pair_id + j * num_pairs;
+      const int tile = unit / p.n_tiles;
+      const int n_blk = unit - tile * p.n_tiles;
       const int row_in_tile = static_cast<int>(rank) * Cfg::BLOCK_M + row;
       const int m = tile * p.rows_per_tile + row_in_tile;
       const bool row_ok = row_in_tile < p.rows_per_tile && m < p.M;   // rows past the tile's whole frames belong to the next tile
-      const int ncol0 = c_begin * 32;
-      if (it == n_my) {   // phase change (block-uniform): the eight epilogue warps swap the bias vector
+      const int ncol0 = n_blk * BLOCK_N + c_begin * 32;   // first output channel of this warp
+      const int bkey = ph2 * p.n_tiles + n_blk;
+      if (bkey != cur_bias) {   // phase / column-tile change (block-uniform): the eight epilogue warps swap the bias slice
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        bias_s[threadIdx.x - 64] = __ldg(p.bias2 + (threadIdx.x - 64));
+        bias_s[threadIdx.x - 64] = __ldg((ph2 ? p.bias2 : p.bias1) + n_blk * BLOCK_N + (threadIdx.x - 64));
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        cur_bias = bkey;
       }
       const float* bs = bias_s;
       uint4 res[NCH * 4];
       if (ph2 && p.residual != nullptr && row_ok) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * BLOCK_N + ncol0);
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.N + ncol0);
 #pragma unroll
         for (int q = 0; q < NCH * 4; ++q) res[q] = __ldg(rp + q);
       } else {
@@ -246,7 +292,7 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(acc * BLOCK_N + c_begin * 32);
       __nv_bfloat16* const dst = ph2 ? p.out : p.y1;
-      const unsigned long long row_off_b = static_cast<unsigned long long>(m) * BLOCK_N * 2ull;
+      const unsigned long long row_off_b = static_cast<unsigned long long>(m) * p.N * 2ull;
 #pragma unroll
       for (int c2 = 0; c2 < NCH / 2; ++c2) {
         uint32_t v2[2][32];
@@ -256,7 +302,7 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         uint4 o[8];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-          const int cl = (c_begin + c2 * 2 + hh) * 32;
+          const int cl = (c_begin + c2 * 2 + hh) * 32;   // column inside the 256-wide tile
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 b0 = *reinterpret_cast<const float4*>(&bs[cl + 8 * q]);
@@ -291,8 +337,12 @@ igemm2_block_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_const
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive_release_cluster(mapa_u32(smem_u32(&y1_ready[j]), 0));
-          mbar_arrive_release_cluster(mapa_u32(smem_u32(&y1_ready[j]), 1));
+          if (p.n_tiles > 1) {
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.flags + tile) : "memory");
+          } else {
+            mbar_arrive_release_cluster(mapa_u32(smem_u32(&y1_ready[j]), 0));
+            mbar_arrive_release_cluster(mapa_u32(smem_u32(&y1_ready[j]), 1));
+          }
         }
       }
       if (++acc == Cfg::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }

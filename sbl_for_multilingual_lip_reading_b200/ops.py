@@ -446,33 +446,53 @@ def conv2d(x, wp, bias, stride=1, relu=True, residual=None, out=None, ext=None):
     return out
 
 
-def conv_block256(x, w1, b1, w2, b2, w_ds=None, stride=1, out=None, y1=None):
-    """A whole BasicBlock with 256 output channels in one launch (sblk_conv_block256_fwd): x bf16 NHWC [F,H,W,Cin] or
-    FlatActs; w1 [256,3,3,Cin], w2 [256,3,3,256], w_ds [256,1,1,Cin] or None (identity residual); b2 must already include
-    the folded downsample shift.  Returns out bf16 [F,P,Q,256], or None when the problem has more tiles per CTA pair
-    than the kernel takes (the caller then launches the two convs one by one)."""
+_BLOCK_FLAGS = {}   # (device index, stream) -> zeroed uint32 counters of conv_block (self-resetting: zeroed once)
+
+
+def _block_flags(dev, words):
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(_stream()))
+    t = _BLOCK_FLAGS.get(key)
+    if t is None or t.numel() < words:
+        t = torch.zeros(max(1024, words), dtype=torch.int32, device=dev)
+        _BLOCK_FLAGS[key] = t
+    return t
+
+
+def conv_block(x, w1, b1, w2, b2, w_ds=None, stride=1, out=None, y1=None, flags=None):
+    """A whole BasicBlock of ResNet layer 3 / layer 4 in one launch (sblk_conv_block_fwd): x bf16 NHWC [F,H,W,Cin] or
+    FlatActs; w1 [Cout,3,3,Cin], w2 [Cout,3,3,Cout] with Cout 256 or 512, w_ds [Cout,1,1,Cin] or None (identity residual);
+    b2 must already include the folded downsample shift.  `flags`: zeroed int32 counters for Cout = 512 (default: one
+    cached tensor per device and stream).  Returns out bf16 [F,P,Q,Cout], or None when the problem has more work units per
+    CTA pair than the kernel takes (the caller then launches the two convs one by one)."""
     _req(w1, BF16, "w1"); _req(b1, F32, "b1"); _req(w2, BF16, "w2"); _req(b2, F32, "b2"); _req(w_ds, BF16, "w_ds")
     xptr, f, h, w, cin, row_pitch, frame_pitch, x_elems = _conv_input(x)
-    if tuple(w1.shape) != (256, 3, 3, cin) or tuple(w2.shape) != (256, 3, 3, 256):
-        raise RuntimeError(f"conv_block256: filter shapes {tuple(w1.shape)} / {tuple(w2.shape)} do not match Cin={cin}, Cout=256")
-    if w_ds is not None and tuple(w_ds.shape) != (256, 1, 1, cin):
-        raise RuntimeError(f"conv_block256: downsample filter shape {tuple(w_ds.shape)} != {(256, 1, 1, cin)}")
+    cout = w1.shape[0]
+    if tuple(w1.shape) != (cout, 3, 3, cin) or tuple(w2.shape) != (cout, 3, 3, cout):
+        raise RuntimeError(f"conv_block: filter shapes {tuple(w1.shape)} / {tuple(w2.shape)} do not match Cin={cin}, Cout={cout}")
+    if w_ds is not None and tuple(w_ds.shape) != (cout, 1, 1, cin):
+        raise RuntimeError(f"conv_block: downsample filter shape {tuple(w_ds.shape)} != {(cout, 1, 1, cin)}")
     p = (h + 2 - 3) // stride + 1
     q = (w + 2 - 3) // stride + 1
     if out is None:
-        out = torch.empty((f, p, q, 256), dtype=BF16, device=w1.device)
+        out = torch.empty((f, p, q, cout), dtype=BF16, device=w1.device)
     if y1 is None:
-        y1 = torch.empty((f, p, q, 256), dtype=BF16, device=w1.device)
+        y1 = torch.empty((f, p, q, cout), dtype=BF16, device=w1.device)
     _req(out, BF16, "out"); _req(y1, BF16, "y1")
-    if out.numel() != f * p * q * 256 or y1.numel() != out.numel():
-        raise RuntimeError("conv_block256: out / y1 must hold F*P*Q*256 elements")
+    if out.numel() != f * p * q * cout or y1.numel() != out.numel():
+        raise RuntimeError("conv_block: out / y1 must hold F*P*Q*Cout elements")
     lib = _lib.load()
-    flops = 2 * f * p * q * 256 * (9 * cin + 9 * 256 + (cin if w_ds is not None else 0))
+    if cout > 256 and flags is None:
+        words = int(lib.sblk_conv_block_flag_words(f, h, w, stride))
+        if words <= 0:
+            raise RuntimeError("conv_block: bad shape")
+        flags = _block_flags(w1.device, words)
+    _req(flags, torch.int32, "flags")
+    flops = 2 * f * p * q * cout * (9 * cin + 9 * cout + (cin if w_ds is not None else 0))
     nbytes = 2 * (x_elems + w1.numel() + w2.numel() + 3 * out.numel())
     try:
-        _call("sblk_conv_block256_fwd", f"block H={h} {cin}->256 s{stride}", flops, nbytes,
-              xptr, _p(w1), _p(b1), _p(w2), _p(b2), _p(w_ds), _p(y1), _p(out), f, h, w, cin, stride, row_pitch,
-              frame_pitch, _stream())
+        _call("sblk_conv_block_fwd", f"block H={h} {cin}->{cout} s{stride}", flops, nbytes,
+              xptr, _p(w1), _p(b1), _p(w2), _p(b2), _p(w_ds), _p(y1), _p(flags), _p(out), f, h, w, cin, cout, stride,
+              row_pitch, frame_pitch, _stream())
     except RuntimeError as e:
         if "tiles per pair" in str(e):
             return None

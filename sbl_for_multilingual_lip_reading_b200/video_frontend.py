@@ -142,10 +142,14 @@ class Lipreading(nn.Module):
         # each conv starts on the rows the previous launch touched last, the part of a 65.6 MB tensor that is still in
         # L2 (bit-identical; measured in DESIGN.md "[r2d] Alternating tile direction")
         self.alternate_tile_order = True
-        # eval path, layer 3 (256 channels, 6x6 maps): a whole residual block as ONE launch (ops.conv_block256: pair tiles of
-        # whole frames go through conv1 and conv2 without any dependency on other tiles) — one launch boundary less per
-        # block; bit-identical to the two launches
+        # eval path, layers 3-4: a whole residual block as ONE launch (ops.conv_block: pair tiles of whole frames go through
+        # conv1 and conv2 without any dependency on other frames) — one launch boundary less per block; bit-identical
+        # to the two launches.  fuse_blocks_max: widest block that is fused.  256 = layer 3 only: a layer-4 block (512
+        # channels = two column tiles per frame group on neighbouring CTA pairs) has ONE work unit per pair at the BASELINE
+        # batch, so the conv1 -> conv2 hand-over is exposed and the single launch is no faster than two (measured:
+        # 45.7 vs 45.7 us and 58.0 vs 56.7 us per block, tools/exp/fuse_blocks_probe.py)
         self.fuse_blocks = True
+        self.fuse_blocks_max = 256
         self._overlap = None
         # (scale | None, out_bf16) set by the same plan: the average pool writes mean * scale as bf16 straight into the
         # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
@@ -179,6 +183,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("fold_downsample", True)
         self.__dict__.setdefault("alternate_tile_order", True)
         self.__dict__.setdefault("fuse_blocks", True)
+        self.__dict__.setdefault("fuse_blocks_max", 256)
         self.__dict__.setdefault("_tail", None)
 
     def _initialize_weights(self):  # same as reference :127-157
@@ -354,8 +359,8 @@ class Lipreading(nn.Module):
                     rev[0] = False   # the dual head writes its tiles front to back
                     a = ops.conv3x3_flat(y, w2, b2, relu=True, residual=res, reverse=flip())
                     continue
-                if self.fold_downsample and self.fuse_blocks and w1.shape[0] == 256:
-                    fused = ops.conv_block256(a, w1, b1, w2, ds[2], w_ds=ds[0], stride=stride)
+                if self.fold_downsample and self.fuse_blocks and w1.shape[0] in (256, 512) and w1.shape[0] <= self.fuse_blocks_max:
+                    fused = ops.conv_block(a, w1, b1, w2, ds[2], w_ds=ds[0], stride=stride)
                     if fused is not None:
                         a = fused
                         continue
@@ -366,9 +371,9 @@ class Lipreading(nn.Module):
                     continue
                 y, res = ops.conv2d_dual(a, w1, b1, ds[0], ds[1], stride=stride, relu=True)
             else:
-                if (self.fuse_blocks and w1.shape[0] == 256 and stride == 1 and not isinstance(a, ops.FlatActs)
-                        and a.shape[-1] == 256):
-                    fused = ops.conv_block256(a, w1, b1, w2, b2, stride=1)
+                if (self.fuse_blocks and w1.shape[0] in (256, 512) and w1.shape[0] <= self.fuse_blocks_max and stride == 1
+                        and not isinstance(a, ops.FlatActs) and a.shape[-1] == w1.shape[0]):
+                    fused = ops.conv_block(a, w1, b1, w2, b2, stride=1)
                     if fused is not None:
                         a = fused
                         continue

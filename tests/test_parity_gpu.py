@@ -233,22 +233,25 @@ def test_fold_downsample_matches_dual_heads(frontend, dev):
     assert rel_fro(a.view(-1, 512), ref.view(-1, 512)) <= rel_fro(b.view(-1, 512), ref.view(-1, 512)) * 1.1
 
 
-@pytest.mark.parametrize("f,h,cin,stride,flat_in", [(29, 11, 128, 2, True), (928, 11, 128, 2, True), (5, 6, 256, 1, False),
-                                                    (928, 6, 256, 1, False), (1, 6, 256, 1, False), (9, 12, 64, 2, False)])
-def test_conv_block256_is_bit_identical_to_the_two_launches(dev, f, h, cin, stride, flat_in):
-    """sblk_conv_block256_fwd (a whole layer-3 BasicBlock in one launch: pair tiles of whole frames run conv1 and then
-    conv2, video_frontend.py:28-41,68-72) against the conv-by-conv launches: same bits, for head blocks (stride 2 +
-    folded downsample branch, flat or dense input) and identity blocks, one tile / partial last tile / two tiles per
-    CTA pair, and a limited grid (more tiles per pair)."""
+@pytest.mark.parametrize("f,h,cin,cout,stride,flat_in", [
+    (29, 11, 128, 256, 2, True), (928, 11, 128, 256, 2, True), (5, 6, 256, 256, 1, False), (928, 6, 256, 256, 1, False),
+    (1, 6, 256, 256, 1, False), (9, 12, 64, 256, 2, False),
+    (928, 6, 256, 512, 2, False), (928, 3, 512, 512, 1, False), (30, 6, 256, 512, 2, False), (3, 3, 512, 512, 1, False)])
+def test_conv_block_is_bit_identical_to_the_two_launches(dev, f, h, cin, cout, stride, flat_in):
+    """sblk_conv_block_fwd (a whole layer-3 / layer-4 BasicBlock in one launch: pair tiles of whole frames run conv1 and
+    then conv2, video_frontend.py:28-41,68-72) against the conv-by-conv launches: same bits, for head blocks (stride 2 +
+    folded downsample branch, flat or dense input) and identity blocks, Cout = 256 (pair-wide mbarrier) and 512 (two
+    column tiles on neighbouring pairs, self-resetting global counters — launched three times to check the reset), one
+    tile / partial last tile / several units per CTA pair, and a limited grid."""
     from sbl_for_multilingual_lip_reading_b200 import ops
-    g = torch.Generator().manual_seed(f * 10 + h)
+    g = torch.Generator().manual_seed(f * 10 + h + cout)
     bf = torch.bfloat16
     x = torch.randn(f, h, h, cin, generator=g).to(bf).to(dev)
-    w1 = (torch.randn(256, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
-    w2 = (torch.randn(256, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).to(bf).to(dev)
-    b1, b2 = torch.randn(256, generator=g).to(dev), torch.randn(256, generator=g).to(dev)
-    head = stride == 2 or cin != 256
-    wd = (torch.randn(256, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev) if head else None
+    w1 = (torch.randn(cout, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
+    w2 = (torch.randn(cout, 3, 3, cout, generator=g) / (9 * cout) ** 0.5).to(bf).to(dev)
+    b1, b2 = torch.randn(cout, generator=g).to(dev), torch.randn(cout, generator=g).to(dev)
+    head = stride == 2 or cin != cout
+    wd = (torch.randn(cout, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev) if head else None
     if flat_in:
         xin = ops.FlatActs(torch.zeros(ops.flat_rows(f, h, h), cin, dtype=bf, device=dev), f, h, h)
         rows = ((torch.arange(f).view(-1, 1, 1) * (h + 1) + 1 + torch.arange(h).view(1, -1, 1)) * (h + 2) + 1 +
@@ -261,22 +264,22 @@ def test_conv_block256_is_bit_identical_to_the_two_launches(dev, f, h, cin, stri
         want = ops.conv2d(y, w2, b2, stride=1, relu=True, ext=(xin, wd, stride))
     else:
         want = ops.conv2d(y, w2, b2, stride=1, relu=True, residual=x)
-    for limit in (0, 24):
+    for limit in (0, 0, 0, 24):
         prev = ops.set_sm_limit(limit) if limit else None
         try:
-            got = ops.conv_block256(xin, w1, b1, w2, b2, w_ds=wd, stride=stride)
+            got = ops.conv_block(xin, w1, b1, w2, b2, w_ds=wd, stride=stride)
         finally:
             if prev is not None:
                 ops.set_sm_limit(prev)
         torch.cuda.synchronize(dev)
-        if got is None:      # more than 8 tiles per CTA pair on the limited grid: the caller falls back (checked below)
+        if got is None:      # more than 8 units per CTA pair on the limited grid: the caller launches conv by conv
             assert limit and f > 100
             continue
         assert torch.equal(got, want), (limit,)
 
 
 def test_fuse_blocks_leaves_the_frontend_bit_identical(frontend, dev):
-    """Lipreading.fuse_blocks (layer 3 as one launch per block) returns exactly the features of the conv-by-conv path."""
+    """Lipreading.fuse_blocks (layers 3-4 as one launch per block) returns exactly the features of the conv-by-conv path."""
     from sbl_for_multilingual_lip_reading_b200 import synth
     x = synth.synthetic_clips(3, 9, seed=33).to(dev)
     old = frontend.fuse_blocks

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Layer-3 residual blocks as one launch (ops.conv_block256) against the two launches: block marginal cost in a graph, then
+"""Layer-3 / layer-4 residual blocks as one launch (ops.conv_block) against the two launches: block marginal cost in a graph, then
 the plain / pipelined plans with Lipreading.fuse_blocks on / off."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -35,15 +35,15 @@ def graph_time(fn, reps=14):
     ts = sorted(ts[2:])
     return ts[len(ts) // 2]
 
-for (cin, h, stride) in ((128, 11, 2), (256, 6, 1)):
+for (cin, cout, h, stride) in ((128, 256, 11, 2), (256, 256, 6, 1), (256, 512, 6, 2), (512, 512, 3, 1)):
     x = torch.randn(F_, h, h, cin, generator=g).to(bf).to(dev)
-    w1 = (torch.randn(256, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
-    w2 = (torch.randn(256, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).to(bf).to(dev)
-    wd = (torch.randn(256, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev) if stride == 2 else None
-    b = torch.zeros(256, device=dev)
+    w1 = (torch.randn(cout, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
+    w2 = (torch.randn(cout, 3, 3, cout, generator=g) / (9 * cout) ** 0.5).to(bf).to(dev)
+    wd = (torch.randn(cout, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev) if stride == 2 else None
+    b = torch.zeros(cout, device=dev)
     p = (h - 1) // stride + 1
-    outs = [torch.empty(F_, p, p, 256, dtype=bf, device=dev) for _ in range(2)]
-    y1 = torch.empty(F_, p, p, 256, dtype=bf, device=dev)
+    outs = [torch.empty(F_, p, p, cout, dtype=bf, device=dev) for _ in range(2)]
+    y1 = torch.empty(F_, p, p, cout, dtype=bf, device=dev)
     def two(i):
         y = ops.conv2d(x, w1, b, stride=stride, relu=True)
         if wd is not None:
@@ -51,11 +51,11 @@ for (cin, h, stride) in ((128, 11, 2), (256, 6, 1)):
         else:
             ops.conv2d(y, w2, b, stride=1, relu=True, residual=x, out=outs[i % 2])
     def one(i):
-        ops.conv_block256(x, w1, b, w2, b, w_ds=wd, stride=stride, out=outs[i % 2], y1=y1)
+        ops.conv_block(x, w1, b, w2, b, w_ds=wd, stride=stride, out=outs[i % 2], y1=y1)
     for name, fn in (("two launches", two), ("one launch", one)):
         res = [(n, graph_time(lambda: [fn(i) for i in range(n)])) for n in (1, 2, 4)]
         per = (res[-1][1] - res[0][1]) / (res[-1][0] - res[0][0])
-        print(f"{cin}->256 H={h} s{stride}  {name}: " + "  ".join(f"{n}x {t:.1f} us" for n, t in res) + f"  -> marginal {per:.1f} us", flush=True)
+        print(f"{cin}->{cout} H={h} s{stride}  {name}: " + "  ".join(f"{n}x {t:.1f} us" for n, t in res) + f"  -> marginal {per:.1f} us", flush=True)
     two(0); one(1); torch.cuda.synchronize()
     print("   identical:", torch.equal(outs[0], outs[1]), flush=True)
 
@@ -82,10 +82,10 @@ def time_plan(plan, reps=30):
     return ts[len(ts) // 2], ts[0]
 
 for rep in range(2):
-    for fuse in (False, True):
-        fe.fuse_blocks = fuse
+    for fuse in (0, 256, 512):
+        fe.fuse_blocks, fe.fuse_blocks_max = bool(fuse), fuse or 512
         plain = VisualEncoderPlan(fe, enc, N, T, device=dev)
         med, best = time_plan(plain); del plain
         pl = PipelinedVisualEncoderPlan(fe, enc, N, T, device=dev)
         med2, best2 = time_plan(pl); pl.close(); del pl
-        print(f"fuse_blocks={fuse}: plain plan median {med:.1f} best {best:.1f} | pipelined median {med2:.1f} best {best2:.1f} ({N / med2 * 1e6:.0f} clips/s)", flush=True)
+        print(f"fuse_blocks up to {fuse}: plain plan median {med:.1f} best {best:.1f} | pipelined median {med2:.1f} best {best2:.1f} ({N / med2 * 1e6:.0f} clips/s)", flush=True)
