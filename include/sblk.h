@@ -158,7 +158,7 @@ int sblk_conv2d_igemm_ext_fwd(const void* x_bf16, const void* w_packed_bf16, con
  * zeroed ONCE by the caller; one workspace per stream).  The grid never exceeds the SMs of sblk_set_sm_limit, which is
  * what keeps the waiting pairs deadlock-free next to a co-running kernel.  Bit-identical to sblk_conv2d_igemm_fwd +
  * sblk_conv2d_igemm[_ext]_fwd.  w_ds must be given exactly when the block changes shape; x may be pitched (flat layout)
- * only then.  Returns -2 (nothing launched) when a CTA pair would own more than 8 units: launch the convs one by one.
+ * only then.  Returns -2 (nothing launched) when a CTA pair would own more than 32 units: launch the convs one by one.
  * replaces: BasicBlock.forward of ResNet layer3 / layer4, transformer/video_frontend.py:28-41,68-72 */
 int sblk_conv_block_flag_words(int F, int H, int W, int stride);
 int sblk_conv_block_fwd(const void* x_bf16, const void* w1_packed_bf16, const float* bias1, const void* w2_packed_bf16,

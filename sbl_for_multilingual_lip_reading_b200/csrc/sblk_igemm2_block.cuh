@@ -46,7 +46,7 @@ struct BlockConvParams {
   unsigned int* flags;
 };
 
-constexpr int BLK_MAX_TILES = 8;   // tiles one CTA pair may own (y1-ready barriers); more -> the caller launches conv by conv
+constexpr int BLK_MAX_TILES = 32;   // units one CTA pair may own (y1-ready barriers); more -> the caller launches conv by conv
 
 __device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
