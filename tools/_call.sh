@@ -1,7 +1,3 @@
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29537 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02s_bench_N32_T29_8gpu.json 2> gpurun_out/bench8_err.log; echo "bench8 rc=$?"
-python -c "
-import json
-d=json.load(open('gpurun_out/r02s_bench_N32_T29_8gpu.json'))
-print({k:d.get(k) for k in ('value','ms_per_step','n_gpus','gather_verified','h2d_ceiling_gbs')}); print('e2e', d['e2e']['value'], 'u8', d.get('e2e_u8',{}).get('value'), 'c2', d['config2'].get('value'), d['config2'].get('gather_verified'), 'sus', d['sustained']['clips_per_s'])
-"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm2_block -s 2 -c 1 -o gpurun_out/r02s_block3b python tools/prof_target.py block3b 3 > gpurun_out/ncu_block3b.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_block3b.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:igemm2_block -s 2 -c 1 -o gpurun_out/r02s_block3a python tools/prof_target.py block3a 3 > gpurun_out/ncu_block3a.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu_block3a.log

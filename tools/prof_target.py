@@ -93,6 +93,17 @@ if what in ("fold3", "fold4"):
     for _ in range(iters):
         y = ops.conv2d(x, w1, bz, stride=2)
         ops.conv2d(y, w2, bz, stride=1, ext=(x, wd, 2))
+if what in ("block3a", "block3b"):
+    # a whole layer-3 residual block as one launch (igemm2_block_kernel): head block (11x11x128 -> 6x6x256, stride 2 +
+    # folded downsample branch) or identity block (6x6x256)
+    cin, h, stride = (128, 11, 2) if what == "block3a" else (256, 6, 1)
+    x = torch.randn(928, h, h, cin, generator=g).to(bf).to(dev)
+    w1 = (torch.randn(256, 3, 3, cin, generator=g) / (9 * cin) ** 0.5).to(bf).to(dev)
+    w2 = (torch.randn(256, 3, 3, 256, generator=g) / (9 * 256) ** 0.5).to(bf).to(dev)
+    wd = (torch.randn(256, 1, 1, cin, generator=g) / cin ** 0.5).to(bf).to(dev) if stride == 2 else None
+    bz = torch.zeros(256, device=dev)
+    for _ in range(iters):
+        ops.conv_block(x, w1, bz, w2, bz, w_ds=wd, stride=stride)
 if what == "stack":
     # the one-launch encoder stack alone, BASELINE configs[1] shape
     from sbl_for_multilingual_lip_reading_b200.encoder import Encoder
