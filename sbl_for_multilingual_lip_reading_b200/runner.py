@@ -231,10 +231,15 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
 
     def __init__(self, frontend, encoder, n, t, device=None, pdl=True, lengths=None, u8_input=None,
                  head_sm_limit=None, head_blocks=None, gate=True, gate_timeout_us=300, enc_cluster=None,
-                 head_frac=None, enc_gpc=None):
+                 head_frac=None, enc_gpc=None, l2_prefetch=False):
         # head_frac: fraction of the frames of the first conv after the head that still runs inside the head (limited
         # width) — fills the time by which the encoder outlasts prep + stem; None = automatic, 0 = off
         self.head_frac = head_frac
+        # l2_prefetch: keep the frontend's L2 weight-prefetch launches inside the step.  They pay for themselves in the
+        # one-batch-per-replay plan (the encoder's weight chain starts cold: 746 vs 883 us) but not here, where the encoder
+        # runs at the START of the step and the hints compete with the head for HBM (tools/exp/l2_prefetch_ab.py: 622.7 ->
+        # 608-610 us with the L2 flushed between steps, 661-665 -> 654-657 us back to back; 42 -> 18 launches per step)
+        self.l2_prefetch = bool(l2_prefetch)
         # head_blocks: residual blocks (after prep + stem) that run next to the encoder on `head_sm_limit` SMs; None =
         # automatic (see _capture).  enc_cluster: CTAs per encoder cluster (8 or 16), None = 8.
         self.enc_cluster = enc_cluster
@@ -295,9 +300,12 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
         saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
                  enc.stack_groups_per_cluster)
+        saved_pf = (getattr(fe, "l2_prefetch", False), getattr(fe, "l2_prefetch_extra", None))
         try:
             with torch.no_grad():
                 stk = enc._get_packed().stacked
+                fe.l2_prefetch = bool(saved_pf[0]) and self.l2_prefetch
+                fe.l2_prefetch_extra = None
                 if getattr(fe, "l2_prefetch", False):
                     fe.l2_prefetch_extra = [stk[k] for k in ("w_in", "w_heads", "w_fc", "w_1", "w_2")]
                 enc.stack_cluster_size = cl
@@ -341,6 +349,8 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         finally:
             (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
              enc.stack_groups_per_cluster) = saved
+            keep_extra = fe.l2_prefetch_extra if fe.l2_prefetch else saved_pf[1]
+            fe.l2_prefetch, fe.l2_prefetch_extra = saved_pf[0], keep_extra
         torch.cuda.synchronize(dev)
         for ev in self.ev_out + self.ev_done:
             ev.record(torch.cuda.current_stream(dev))
