@@ -298,6 +298,8 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
         self.feat16 = [torch.zeros((self.n * self.t, fe.inputDim), dtype=ops.enc16_dtype(), device=dev) for _ in range(2)]
         self.feat = torch.empty((self.n, self.t, fe.inputDim), dtype=torch.float32, device=dev)
         self._ones = torch.ones((self.n * self.t, fe.inputDim), dtype=torch.float32, device=dev)
+        self._tail_stream = torch.cuda.Stream(device=dev)
+        self._scale = [torch.empty_like(self._ones) for _ in range(2)]
         saved = (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
                  enc.stack_groups_per_cluster)
         saved_pf = (getattr(fe, "l2_prefetch", False), getattr(fe, "l2_prefetch_extra", None))
@@ -332,9 +334,25 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                             ops.gate_wait(self.gate, enc_ctas, self.gate_timeout_us)
                         # the always-on dropout of Lipreading.forward (reference :122): its factor mask / (1 - p) is drawn
                         # here, in front of the (non-critical) head, and applied by the pooling launch that ends the trunk
-                        scale = (torch.nn.functional.dropout(self._ones, p=0.5)
-                                 if getattr(fe, "always_on_dropout", True) else None)
-                        fe._tail = (scale, self.feat16[s])
+                        # The draw is forked onto a side stream right before layer 4 is enqueued: its two small launches
+                        # cost 10-12 us of the step at the start of the replay (in stream OR on a side stream: they take
+                        # SMs while the encoder's clusters and the gated stem are being placed, tools/exp/
+                        # pipeline_switches_probe.py), while the 132-CTA grids of layer 4 leave 16 SMs idle anyway.
+                        scale, tail_join = None, None
+                        if getattr(fe, "always_on_dropout", True):
+                            scale = self._scale[s]
+                            drawn = torch.cuda.Event()
+
+                            def draw(scale=scale, drawn=drawn, main=main):
+                                ev = torch.cuda.Event()
+                                ev.record(main)
+                                self._tail_stream.wait_event(ev)
+                                with torch.cuda.stream(self._tail_stream):
+                                    scale.copy_(torch.nn.functional.dropout(self._ones, p=0.5))
+                                    drawn.record(self._tail_stream)
+                            fe._block_hook = (6, draw)
+                            tail_join = (lambda ev: (lambda: main.wait_event(ev)))(drawn)
+                        fe._tail = (scale, self.feat16[s], tail_join)
                         fe._overlap = (self.head_sm_limit, self.head_blocks, lambda: main.wait_event(done),
                                        self.head_frac)
                         if self.u8_input is not None:
@@ -342,13 +360,14 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                             f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
                         else:
                             f = fe(self.x[s])
-                        fe._overlap = fe._tail = None
+                        fe._overlap = fe._tail = fe._block_hook = None
                         del f   # unwritten: the pooling launch wrote the bf16 features into feat16[s]
                     self.launches_per_forward = ops.launch_count() - before
                     self.graphs[s] = g
         finally:
             (enc.stack_cluster_size, enc._resident_counter, fe._overlap, enc._x16_override, fe._tail,
              enc.stack_groups_per_cluster) = saved
+            fe._block_hook = None
             keep_extra = fe.l2_prefetch_extra if fe.l2_prefetch else saved_pf[1]
             fe.l2_prefetch, fe.l2_prefetch_extra = saved_pf[0], keep_extra
         torch.cuda.synchronize(dev)

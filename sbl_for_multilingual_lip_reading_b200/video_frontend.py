@@ -155,6 +155,10 @@ class Lipreading(nn.Module):
         # plan's feature buffer — `scale` is F.dropout(ones, p=0.5) drawn at the start of the replay, i.e. the always-on
         # dropout of forward() moved off the critical path (bit-identical) — and forward() skips its own dropout
         self._tail = None
+        # (block index, callable) set by a plan while it captures: called on the main stream right before that residual
+        # block is enqueued (the pipelined plan forks its dropout draw in front of layer 4, whose 132-CTA grids leave
+        # SMs idle)
+        self._block_hook = None
 
     # ---- pickling / state: the packed cache holds plain tensors but is cheap to rebuild; drop it ----------
     def __getstate__(self):
@@ -166,6 +170,7 @@ class Lipreading(nn.Module):
         st["l2_prefetch_extra"] = None
         st["_overlap"] = None
         st["_tail"] = None
+        st["_block_hook"] = None
         return st
 
     def __setstate__(self, st):
@@ -185,6 +190,7 @@ class Lipreading(nn.Module):
         self.__dict__.setdefault("fuse_blocks", True)
         self.__dict__.setdefault("fuse_blocks_max", 256)
         self.__dict__.setdefault("_tail", None)
+        self.__dict__.setdefault("_block_hook", None)
 
     def _initialize_weights(self):  # same as reference :127-157
         for m in self.modules():
@@ -324,6 +330,8 @@ class Lipreading(nn.Module):
                     ops.conv3x3_flat(ops.flat_frames(a, 0, split), w1, b1, relu=True,
                                      out=ops.flat_frames(y, 0, split).data, reverse=split_rev)
                 end_head()
+            if self._block_hook is not None and chain == 0 and bi == self._block_hook[0]:
+                self._block_hook[1]()
             if self.l2_prefetch and chain == 0 and bi in (0, 4, 6):
                 # Weights of the layers still to come are pulled into L2 by a tiny kernel on a side stream while the
                 # current layer computes (layers 3-4 move few activation bytes, so the lines survive).  Benchmarks flush
