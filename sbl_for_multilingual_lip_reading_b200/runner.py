@@ -343,7 +343,10 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                             scale = self._scale[s]
                             drawn = torch.cuda.Event()
 
-                            def draw(scale=scale, drawn=drawn, main=main):
+                            fired = []
+
+                            def draw(scale=scale, drawn=drawn, main=main, fired=fired):
+                                fired.append(True)
                                 ev = torch.cuda.Event()
                                 ev.record(main)
                                 self._tail_stream.wait_event(ev)
@@ -360,6 +363,9 @@ class PipelinedVisualEncoderPlan(VisualEncoderPlan):
                             f = fe.forward_u8(self.x[s], frames=self.t, crop=((h0 - 88) // 2, (w0 - 88) // 2))
                         else:
                             f = fe(self.x[s])
+                        if fe._block_hook is not None and not fired:
+                            raise RuntimeError("PipelinedVisualEncoderPlan: the frontend never reached residual block 6 "
+                                               "(the dropout factor was not drawn)")
                         fe._overlap = fe._tail = fe._block_hook = None
                         del f   # unwritten: the pooling launch wrote the bf16 features into feat16[s]
                     self.launches_per_forward = ops.launch_count() - before
